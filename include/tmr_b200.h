@@ -1,0 +1,166 @@
+/*
+ * tmr_b200.h — C ABI of libtmr_b200.so: the TMRNet temporal-memory-relation head on B200 (sm_100a).
+ *
+ * The reference (lucieDLE/TMRNet, pure Python/PyTorch) has no FFI of its own; its seam for this
+ * path is the nn.Module surface plus two free functions.  Every entry point
+ * below names the reference code it replaces (paths relative to the reference root; NLB =
+ * "code/Training TMRNet/NLBlock_MutiConv6_3.py", TRAIN =
+ * "code/Training TMRNet/train_non-local_mutiConv_resnet.py", EVAL =
+ * "code/eval/python/test_singlenet_phase_non-local_pretrained_2fc_copy_mutiConv6_resnest.py").
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const float*` / `float*` is a DEVICE pointer to fp32,
+ *     contiguous, 16-byte aligned, unless the parameter name ends in `_host`;
+ *   - the caller (PyTorch) owns all memory, including packed weights and workspaces, whose sizes
+ *     come from the *_bytes() queries; the library keeps no mutable global state and is re-entrant
+ *     per (device, stream) — the reference calls forward from one thread per GPU (TRAIN:776-778);
+ *   - every function returns 0 on success, non-zero on error; tmr_last_error() returns the
+ *     thread-local message of the last failure.  There is no CPU path: a missing device is an error;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised.
+ *   - D (bank row width / LSTM hidden) must be 512 and F (backbone width) 2048 as in the reference;
+ *     L (memory length), seq (clip length), C (phases, <= 32) and B (clips) are runtime values.
+ */
+#ifndef TMR_B200_H_
+#define TMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMR_OK 0
+#define TMR_ERR_ARG 1
+#define TMR_ERR_CUDA 2
+#define TMR_ERR_UNSUPPORTED 3
+
+/* math mode of the GEMM-shaped stages */
+#define TMR_MATH_FP32 0  /* fp32 FFMA on CUDA cores (exact-order reference path)          */
+#define TMR_MATH_TF32 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (default fast) */
+
+/* window padding at the start of the bank / of a video */
+#define TMR_PAD_REPEAT 0 /* reference semantics (TRAIN:298-326): repeat-fill, leaks into previous video */
+#define TMR_PAD_ZERO 1   /* zero rows before the clip's own video start (what north_star describes)     */
+
+const char* tmr_last_error(void);
+int tmr_version(void);
+/* Compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int tmr_device_arch(void);
+
+/* ---- a1/a2: index tables --------------------------------------------------------------------
+ * Replaces get_useful_start_idx (TRAIN:288-295) + the dict_*_start_idx_LFB construction
+ * (TRAIN:643-644).  Host-side, closed form of the reference walk:
+ *   frame2row[g] = bank row of g if g can start a clip, else the row of the smallest valid start
+ *   > g (or -1 past the last one); frame2vstart[g] = first global frame of g's video.
+ * lens_host[V] are the per-video frame counts.  Outputs are HOST arrays of sum(lens) int32
+ * (frame2vstart_host may be NULL).  *n_rows_out receives the number of valid clip starts. */
+int tmr_build_frame2row(const int64_t* lens_host, int V, int seq, int32_t* frame2row_host,
+                        int32_t* frame2vstart_host, int64_t* n_rows_out);
+
+/* ---- a3: memory-bank window gather ------------------------------------------------------------
+ * Replaces get_long_feature + np.array + torch.Tensor(...).to(device) (TRAIN:298-326, 873-876).
+ * out[b,k,:] = bank[row(b,k),:], row(b,k) = frame2row[starts[b]-k-1] (0 if the key is negative);
+ * TMR_PAD_ZERO writes zeros where the key precedes the clip's own video (needs frame2vstart).
+ * starts: device int64[B] global clip-start frame ids; frame2row/frame2vstart: device int32.
+ * rows_out (nullable): device int32[B*L] receiving the gathered row ids (-1 for zero rows). */
+int tmr_gather_windows(const float* bank, int64_t n_rows, const int32_t* frame2row,
+                       const int32_t* frame2vstart, int64_t n_frames, const int64_t* starts, int B,
+                       int L, int D, int pad_mode, float* out, int32_t* rows_out, void* stream);
+
+/* ---- weight packing (once per weight update; caller owns the packed buffers) -------------------
+ * Inputs use the reference state-dict layouts. */
+size_t tmr_timeconv_packed_bytes(int D);
+/* time_conv.timeconv{1,2,3}.weight (D,D,{3,5,7}) + .bias (D) */
+int tmr_timeconv_pack(const float* w3, const float* b3, const float* w5, const float* b5,
+                      const float* w7, const float* b7, int D, void* packed, void* stream);
+
+size_t tmr_nlblock_packed_bytes(int D);
+/* nl_block.linear{1..4}.weight (D,D) + .bias (D), nl_block.layer_norm.weight/bias (1,D) */
+int tmr_nlblock_pack(const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, const float* w4, const float* b4,
+                     const float* ln_w, const float* ln_b, int D, void* packed, void* stream);
+
+size_t tmr_lstm_packed_bytes(int F, int D);
+/* lstm.weight_ih_l0 (4D,F), lstm.weight_hh_l0 (4D,D), lstm.bias_ih_l0 (4D), lstm.bias_hh_l0 (4D) */
+int tmr_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int F,
+                  int D, void* packed, void* stream);
+
+size_t tmr_classifier_packed_bytes(int D, int C);
+/* fc_h_c.weight (D,2D) + bias (D), fc_c.weight (C,D) + bias (C) */
+int tmr_classifier_pack(const float* w_h, const float* b_h, const float* w_c, const float* b_c,
+                        int D, int C, void* packed, void* stream);
+
+/* ---- a5: TimeConv.forward (NLB:43-79) ---------------------------------------------------------
+ * x (B,L,D) -> out (B,L,D): out[b,k,c] = max(x[k], k>0 ? max(x[k],x[k-1]) : max(x[k],0),
+ * conv3, conv5, conv7) with zero "same" padding inside each window.  Any L >= 1. */
+int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D, float* out,
+                         int math_mode, void* stream);
+
+/* ---- a6: NLBlock.forward, eval mode (NLB:25-40) -----------------------------------------------
+ * St (B,D), Lt (B,L,D) -> out (B,D).  workspace >= tmr_nlblock_workspace_bytes(B,D). */
+size_t tmr_nlblock_workspace_bytes(int B, int D);
+int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B, int L, int D,
+                    float* out, void* workspace, size_t workspace_bytes, int math_mode,
+                    void* stream);
+
+/* ---- a7: nn.LSTM(2048,512,batch_first) from zero state, last step only (TRAIN:224,241-244) ------
+ * Per-clip form: x (B,seq,F) -> out (B,D).  Also the bank builder's head half
+ * (resnet_lstm_LFB.forward, TRAIN:277-285). */
+size_t tmr_lstm_workspace_bytes(int64_t n_rows_x, int B, int D);
+int tmr_lstm_last_fwd(const void* packed, const float* x, int B, int seq, int F, int D, float* out,
+                      void* workspace, size_t workspace_bytes, int math_mode, void* stream);
+/* Frame-deduplicated form: feats (n_frames,F) holds every frame once; clip b covers frames
+ * starts[b] .. starts[b]+seq-1 (device int64[B]).  The input projection runs once per frame.
+ * workspace >= tmr_lstm_workspace_bytes(n_frames, B, D). */
+int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_frames,
+                             const int64_t* starts, int B, int seq, int F, int D, float* out,
+                             void* workspace, size_t workspace_bytes, int math_mode, void* stream);
+
+/* ---- a8 + a9: classifier and eval post-processing (TRAIN:249-252 eval mode, EVAL:122-125,491-493)
+ * logits = fc_c(relu(fc_h_c([St || y1]))); score = max softmax probability; pred = first argmax.
+ * logits (B,C) fp32, pred int64[B], score fp32[B] (pred/score nullable).
+ * workspace >= tmr_classifier_workspace_bytes(B,D). */
+size_t tmr_classifier_workspace_bytes(int B, int D);
+int tmr_fc_argmax_fwd(const void* packed, const float* St, const float* y1, int B, int D, int C,
+                      float* logits, int64_t* pred, float* score, void* workspace,
+                      size_t workspace_bytes, int math_mode, void* stream);
+
+/* ---- a11: whole head, resnet_lstm.forward minus `share` (TRAIN:237-253 / EVAL:110-126) --------
+ * x (B,seq,F) backbone features, long_feature (B,L,D).  timeconv_packed may be NULL for the
+ * NL-only wiring (train_only_non-local_pretrained.py:226-240). */
+size_t tmr_head_workspace_bytes(int B, int seq, int L, int D);
+int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const void* nlblock_packed,
+                 const void* classifier_packed, const float* x, const float* long_feature, int B,
+                 int seq, int L, int F, int D, int C, float* logits, int64_t* pred, float* score,
+                 void* workspace, size_t workspace_bytes, int math_mode, void* stream);
+
+/* ---- bank-level head: the eval loop body (EVAL:470-499) for clips taken from resident per-frame
+ * features and a resident memory bank, without materialising per-clip copies of the frames:
+ *   feats        (n_feat_frames,F): backbone features of global frames frame0 .. frame0+n_feat_frames-1,
+ *                which must cover starts[b] .. starts[b]+seq-1 for every clip of the batch;
+ *   bank         (n_rows,D), frame2row/frame2vstart (n_frames_total) as in tmr_gather_windows;
+ *   starts       device int64[B] GLOBAL clip-start frame ids.
+ * Runs: input projection once per frame -> LSTM -> window gather -> TimeConv -> NLBlock -> FCs ->
+ * softmax score / argmax.  St_out (nullable, (B,D)) receives the LSTM state of each clip (the row a
+ * bank builder would store, TRAIN:277-285).  workspace >= tmr_head_frames_workspace_bytes(...). */
+size_t tmr_head_frames_workspace_bytes(int64_t n_feat_frames, int B, int L, int D);
+int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
+                        const void* nlblock_packed, const void* classifier_packed,
+                        const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                        int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
+                        int64_t n_frames_total, const int64_t* starts, int B, int seq, int L, int F,
+                        int D, int C, int pad_mode, float* logits, int64_t* pred, float* score,
+                        float* St_out, void* workspace, size_t workspace_bytes, int math_mode,
+                        void* stream);
+
+/* ---- generic fp32 linear used by the stages above (exposed for tests) --------------------------
+ * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N. */
+int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,
+                   float* out, int relu, int math_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMR_B200_H_ */

@@ -1,0 +1,102 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the host
+index logic matches the reference-generated KATs, the module surface mirrors the reference's
+state-dict keys, and the product refuses CPU tensors (no fallback)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tmr_oracle as orc
+import tmrnet_b200 as tb
+from tmrnet_b200 import _lib, ops, synth
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _lib.header_symbols()
+    assert len(declared) >= 20
+    assert declared == sorted(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tmr_version() >= 100
+
+
+def test_no_oracle_import_in_product():
+    root = os.path.dirname(os.path.abspath(tb.__file__))
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "tmr_oracle" not in txt and "import oracle" not in txt, f
+
+
+def _kat(golden_dir):
+    z = np.load(os.path.join(golden_dir, "gather_kat.npz"))
+    for i, (seq, L) in enumerate(z["meta"]):
+        yield int(seq), int(L), z[f"c{i}_lengths"].tolist(), z[f"c{i}_starts"], z[f"c{i}_rows"].astype(np.int64)
+
+
+def test_build_frame2row_matches_reference_walk(golden_dir):
+    for seq, L, lengths, starts, rows in _kat(golden_dir):
+        f2r, f2v, n_rows = ops.build_frame2row(lengths, seq)
+        assert n_rows == len(starts)
+        assert np.array_equal(f2r.astype(np.int64), orc.frame2row_closed_form(lengths, seq))
+        got = orc.window_rows_closed_form(starts, f2r.astype(np.int64), L)
+        assert np.array_equal(got, rows)
+        base = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+        assert np.array_equal(f2v, np.repeat(base, lengths))
+
+
+def test_index_from_reference_dict(golden_dir):
+    for seq, L, lengths, starts, rows in _kat(golden_dir):
+        a = tb.LFBIndex.from_lengths(lengths, seq)
+        assert tb.get_useful_start_idx(seq, lengths) == starts.tolist()
+        assert dict(a) == orc.build_start_dict(starts.tolist())
+        b = tb.LFBIndex.from_dict(dict(a))
+        n = len(b.frame2row_host)
+        assert np.array_equal(a.frame2row_host[:n], b.frame2row_host)
+        with pytest.raises(KeyError):
+            a.check_starts([int(sum(lengths))])
+
+
+def test_invalid_start_raises_keyerror():
+    idx = tb.LFBIndex.from_lengths([7, 6, 5], 4)
+    idx.check_starts([0, 3, 7, 14])
+    for bad in (4, 6, 15, -1, 99):
+        with pytest.raises(KeyError):
+            idx.check_starts([0, bad])
+
+
+def test_state_dict_keys_match_reference_shapes():
+    m = tb.resnet_lstm(num_class=7)
+    sd = m.state_dict()
+    want = synth.head_state_dict(num_class=7)
+    assert sorted(sd) == sorted(want)
+    for k, v in want.items():
+        assert tuple(sd[k].shape) == v.shape, k
+    m.load_reference_state_dict({**{k: torch.from_numpy(v) for k, v in want.items()},
+                                 "share.conv1.weight": torch.zeros(1)})
+    assert torch.equal(m.nl_block.layer_norm.weight, torch.from_numpy(want["nl_block.layer_norm.weight"]))
+    nlonly = tb.resnet_lstm(num_class=8, use_timeconv=False)
+    assert not any(k.startswith("time_conv") for k in nlonly.state_dict())
+    assert nlonly.fc_c.weight.shape == (8, 512)
+
+
+def test_cpu_tensors_are_refused():
+    m = tb.resnet_lstm().eval()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="CUDA-only"):
+            m(torch.zeros(1, 10, 2048), torch.zeros(1, 30, 512))
+        with pytest.raises(RuntimeError, match="CUDA-only"):
+            tb.TimeConv()(torch.zeros(1, 30, 512))
+
+
+def test_bank_pickle_roundtrip(tmp_path):
+    bank = synth.bank(17, seed=3)
+    p = tmp_path / "g_LFB_test.pkl"
+    tb.save_bank(torch.from_numpy(bank), str(p))
+    import pickle
+    raw = pickle.load(open(p, "rb"))
+    assert raw.dtype == np.float64 and raw.shape == (17, 512)
+    assert np.array_equal(raw.astype(np.float32), bank)

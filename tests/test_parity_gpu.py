@@ -1,0 +1,374 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the committed golden
+fixtures.  Run on the B200 box: python -m pytest tests -m gpu.
+
+Tolerances (BASELINE.json north_star): window indices / gathered values / argmax bit-exact;
+logits within 1e-3 relative (max|d| / max|ref|), fp32 accumulate.  The fp32 CUDA-core mode is
+held to 2e-5; the TF32 tensor-core mode to 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import tmr_oracle as orc
+import tmrnet_b200 as tb
+from tmrnet_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32", "tf32"]
+TOL = {"fp32": 2e-5, "tf32": 1e-3}
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def rel_err(got, ref):
+    got = got.detach().double().cpu() if isinstance(got, torch.Tensor) else torch.as_tensor(got).double()
+    ref = ref.detach().double().cpu() if isinstance(ref, torch.Tensor) else torch.as_tensor(ref).double()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def _need_mode(mode):
+    if mode == "tf32":
+        from tmrnet_b200 import _lib
+        x = torch.zeros(1, 1, 512, device=_dev())
+        try:
+            m = _model(7)
+            ops.timeconv_max(m.time_conv.packed(), x, "tf32")
+        except _lib.TmrError as e:
+            if "tcgen05" in str(e):
+                pytest.fail(f"TF32 tensor-core path unavailable on the GPU box: {e}")
+            raise
+
+
+_models = {}
+
+
+def _model(C=7, seed=1234, use_timeconv=True):
+    key = (C, seed, use_timeconv)
+    if key not in _models:
+        sd = synth.head_state_dict(num_class=C, seed=seed, with_timeconv=use_timeconv)
+        m = tb.resnet_lstm(num_class=C, use_timeconv=use_timeconv)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        _models[key] = (m.to(_dev()).eval(), sd)
+    return _models[key][0]
+
+
+def _sd(C=7, seed=1234, use_timeconv=True):
+    _model(C, seed, use_timeconv)
+    return _models[(C, seed, use_timeconv)][1]
+
+
+def _kat(golden_dir):
+    z = np.load(os.path.join(golden_dir, "gather_kat.npz"))
+    for i, (seq, L) in enumerate(z["meta"]):
+        yield int(seq), int(L), z[f"c{i}_lengths"].tolist(), z[f"c{i}_starts"], z[f"c{i}_rows"].astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------
+# a1-a3: window gather — bit-exact indices and values
+# ------------------------------------------------------------------------------------------
+def test_gather_rows_bit_exact_vs_reference_kats(golden_dir):
+    dev = _dev()
+    for seq, L, lengths, starts, rows in _kat(golden_dir):
+        idx = tb.LFBIndex.from_lengths(lengths, seq)
+        bank = torch.from_numpy(synth.bank(len(starts), seed=seq * 100 + L)).to(dev)
+        out, got_rows = tb.get_long_feature(starts.tolist(), idx, bank, L, return_rows=True)
+        assert np.array_equal(got_rows.cpu().numpy().astype(np.int64), rows)
+        assert torch.equal(out.cpu(), bank.cpu()[torch.from_numpy(rows)])
+        # plain reference-style dict gives the same windows
+        out2 = tb.get_long_feature(starts.tolist(), dict(idx), bank, L)
+        assert torch.equal(out, out2)
+
+
+def test_gather_matches_golden_values(golden_dir):
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    seed, seq, L, B = (int(v) for v in z["meta"])
+    lengths = z["lengths"].tolist()
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    bank64 = synth.bank(len(idx), seed=seed).astype(np.float64)          # reference bank dtype
+    out = tb.get_long_feature(z["pick"], idx, tb.to_device_bank(bank64), L)
+    assert np.array_equal(out.cpu().numpy(), z["long_feature"])
+
+
+def test_gather_zero_pad_mode():
+    dev = _dev()
+    lengths, seq, L = [25, 14, 40], 10, 12
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    starts = np.array(tb.get_useful_start_idx(seq, lengths))
+    bank = torch.from_numpy(synth.bank(len(starts), seed=9)).to(dev)
+    out, rows = tb.get_long_feature(starts, idx, bank, L, pad_mode="zero", return_rows=True)
+    f2v = idx.frame2vstart_host
+    want = np.zeros((len(starts), L), np.int64)
+    for b, s in enumerate(starts):
+        for k in range(L):
+            key = s - k - 1
+            want[b, k] = idx[key] if key >= f2v[s] else -1
+    assert np.array_equal(rows.cpu().numpy(), want)
+    ref = torch.where(torch.from_numpy(want >= 0)[..., None], bank.cpu()[torch.from_numpy(np.maximum(want, 0))],
+                      torch.zeros(()))
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_gather_full_bank_checksum():
+    """Full-size property (BASELINE config 2 shape): for every clip far enough inside its video the
+    window is the reversed run of the L rows before it, so sum over windows is a sliding-window sum."""
+    dev = _dev()
+    lengths = synth.video_lengths(40)
+    seq, L = 10, 30
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    starts = synth.clip_starts(lengths, seq)
+    n = len(starts)
+    bank = torch.from_numpy(synth.bank(n, seed=1234)).to(dev)
+    st = torch.from_numpy(starts).to(dev)
+    out, rows = tb.get_long_feature(st, idx, bank, L, return_rows=True)
+    rows = rows.long()
+    assert int(rows.min()) >= 0 and int(rows.max()) < n
+    own = torch.arange(n, device=dev)
+    f2v = torch.from_numpy(idx.frame2vstart_host).to(dev).long()
+    interior = (st - f2v[st]) >= L          # at least L clips of the same video precede it
+    want = own[:, None] - 1 - torch.arange(L, device=dev)[None, :]
+    assert torch.equal(rows[interior], want[interior])
+    assert torch.equal(out, bank[rows])
+
+
+# ------------------------------------------------------------------------------------------
+# a5: TimeConv
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_timeconv_matches_golden_and_oracle(golden_dir, mode):
+    _need_mode(mode)
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    m = _model(7)
+    x = torch.from_numpy(z["long_feature"]).to(_dev())
+    with torch.no_grad():
+        m.time_conv.math_mode = mode
+        got = m.time_conv(x)
+    assert rel_err(got, z["Lt"]) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,L", [(1, 1), (3, 2), (5, 10), (9, 30), (2, 60), (3, 120), (7, 33), (130, 30)])
+def test_timeconv_l_sweep(mode, B, L):
+    _need_mode(mode)
+    m = _model(7)
+    x = torch.from_numpy(synth.bank(B * L, seed=B * 1000 + L).reshape(B, L, 512))
+    ref = orc.timeconv(x, _sd(7))
+    got = ops.timeconv_max(m.time_conv.packed(), x.to(_dev()), mode)
+    assert rel_err(got, ref) < TOL[mode]
+
+
+def test_timeconv_pool_branch_uses_zero_pad():
+    """k=0 takes max(x, 0): with strongly negative inputs and zero conv weights the output is 0 at
+    k=0 and max(x[k], x[k-1]) elsewhere (NLB:67-68)."""
+    dev = _dev()
+    tc = tb.TimeConv().to(dev)
+    with torch.no_grad():
+        for p in tc.parameters():
+            p.fill_(0.0)
+        for c in (tc.timeconv1, tc.timeconv2, tc.timeconv3):
+            c.bias.fill_(-100.0)
+        x = -torch.rand(2, 5, 512, device=dev) - 1.0
+        y = tc(x)
+    assert torch.equal(y[:, 0], torch.zeros_like(y[:, 0]))
+    assert torch.equal(y[:, 1:], torch.maximum(x[:, 1:], x[:, :-1]))
+
+
+# ------------------------------------------------------------------------------------------
+# a6: NLBlock
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_nlblock_matches_golden(golden_dir, mode):
+    _need_mode(mode)
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    m = _model(7)
+    dev = _dev()
+    m.nl_block.math_mode = mode
+    with torch.no_grad():
+        got = m.nl_block(torch.from_numpy(z["St"]).to(dev), torch.from_numpy(z["Lt"]).to(dev))
+        got_nl = m.nl_block(torch.from_numpy(z["St"]).to(dev), torch.from_numpy(z["long_feature"]).to(dev))
+    assert rel_err(got, z["y1"]) < TOL[mode]
+    assert rel_err(got_nl, z["y1_nlonly"]) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,L", [(1, 1), (2, 7), (33, 10), (129, 30), (5, 60), (4, 120), (3, 40)])
+def test_nlblock_sweep(mode, B, L):
+    _need_mode(mode)
+    m = _model(7)
+    St = torch.from_numpy(synth.bank(B, seed=L))
+    Lt = torch.from_numpy(synth.bank(B * L, seed=L + 1).reshape(B, L, 512)) * 3.0
+    ref = orc.nlblock(St, Lt, _sd(7))
+    got = ops.nlblock(m.nl_block.packed(), St.to(_dev()), Lt.to(_dev()), mode)
+    assert rel_err(got, ref) < TOL[mode]
+
+
+def test_attention_softmax_is_peaked_correctly():
+    """Large score spread: softmax over L must follow exp() exactly, not saturate (online softmax)."""
+    m = _model(7)
+    B, L = 4, 30
+    St = torch.from_numpy(synth.bank(B, seed=5)) * 8.0
+    Lt = torch.from_numpy(synth.bank(B * L, seed=6).reshape(B, L, 512)) * 20.0
+    ref = orc.nlblock(St, Lt, _sd(7), dtype=torch.float64)
+    got = ops.nlblock(m.nl_block.packed(), St.to(_dev()), Lt.to(_dev()), "fp32")
+    assert rel_err(got, ref) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# a7: LSTM
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_lstm_matches_golden(golden_dir, mode):
+    _need_mode(mode)
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    seed, seq, L, B = (int(v) for v in z["meta"])
+    feats = synth.features(int(z["lengths"].sum()), seed=seed)
+    x = torch.from_numpy(np.stack([feats[s:s + seq] for s in z["pick"]])).to(_dev())
+    m = _model(7)
+    got = ops.lstm_last(m.packs()[0], x, mode)
+    assert rel_err(got, z["St"]) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,seq", [(1, 1), (3, 2), (130, 10), (17, 4)])
+def test_lstm_sweep_and_frame_dedup(mode, B, seq):
+    _need_mode(mode)
+    m = _model(7)
+    n_frames = B + seq - 1
+    feats = torch.from_numpy(synth.features(n_frames, seed=B + seq))
+    starts = torch.arange(B)
+    x = torch.stack([feats[s:s + seq] for s in range(B)])
+    ref = orc.lstm_last(x, _sd(7))
+    got = ops.lstm_last(m.packs()[0], x.to(_dev()), mode)
+    got_f = ops.lstm_last_frames(m.packs()[0], feats.to(_dev()), starts.to(_dev()), seq, mode)
+    assert rel_err(got, ref) < TOL[mode]
+    assert rel_err(got_f, ref) < TOL[mode]
+    if mode == "fp32":
+        assert torch.equal(got, got_f)        # dedup only skips recomputation: same arithmetic
+
+
+def test_lstm_LFB_module_builds_bank_rows(golden_dir):
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    seed, seq, L, B = (int(v) for v in z["meta"])
+    feats = synth.features(int(z["lengths"].sum()), seed=seed)
+    x = torch.from_numpy(np.stack([feats[s:s + seq] for s in z["pick"]])).to(_dev())
+    lfb = tb.resnet_lstm_LFB(sequence_length=seq)
+    sd = _sd(7)
+    lfb.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items() if k.startswith("lstm.")})
+    lfb = lfb.to(_dev()).eval()
+    with torch.no_grad():
+        got = lfb(x.reshape(-1, 2048))
+    assert rel_err(got, z["St"]) < TOL["fp32"]
+
+
+# ------------------------------------------------------------------------------------------
+# a8/a9: classifier + eval post-processing
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [6, 7, 8])
+def test_classifier_and_argmax(C):
+    m = _model(C)
+    B = 301
+    St = torch.from_numpy(synth.bank(B, seed=11))
+    y1 = torch.from_numpy(synth.bank(B, seed=12)) * 2.0
+    ref = orc.classifier(St, y1, _sd(C))
+    logits, pred, score = ops.fc_argmax(m.packs()[3], St.to(_dev()), y1.to(_dev()), C, "fp32")
+    assert rel_err(logits, ref) < TOL["fp32"]
+    # argmax / score are exact functions of OUR logits (first index on ties, EVAL:491-493)
+    p = torch.softmax(logits, dim=1)
+    s2, p2 = torch.max(p, 1)
+    assert torch.equal(pred, p2)
+    assert torch.allclose(score, s2, rtol=1e-6, atol=1e-7)
+
+
+def test_argmax_first_index_on_ties():
+    dev = _dev()
+    m = tb.resnet_lstm(num_class=7).to(dev).eval()
+    with torch.no_grad():
+        m.fc_c.weight.zero_()
+        m.fc_c.bias.copy_(torch.tensor([0.5, 2.0, 2.0, -1.0, 2.0, 0.0, 1.0]))
+        logits, pred, score = ops.fc_argmax(m.packs()[3], torch.zeros(5, 512, device=dev), torch.zeros(5, 512, device=dev), 7)
+    assert pred.tolist() == [1] * 5
+    assert torch.equal(logits[0].cpu(), torch.tensor([0.5, 2.0, 2.0, -1.0, 2.0, 0.0, 1.0]))
+
+
+# ------------------------------------------------------------------------------------------
+# a11: whole head
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("C", [7, 8])
+def test_head_matches_golden(golden_dir, mode, C):
+    _need_mode(mode)
+    z = np.load(os.path.join(golden_dir, "head_b4_l30.npz"))
+    seed, seq, L, B = (int(v) for v in z["meta"])
+    feats = synth.features(int(z["lengths"].sum()), seed=seed)
+    x = torch.from_numpy(np.stack([feats[s:s + seq] for s in z["pick"]])).to(_dev())
+    lf = torch.from_numpy(z["long_feature"]).to(_dev())
+    m = _model(C)
+    m.math_mode = mode
+    with torch.no_grad():
+        logits = m(x, lf)
+        l2, pred, score = m.predict(x.reshape(-1, 2048), lf)
+    assert torch.equal(logits, l2)
+    assert rel_err(logits, z[f"logits_c{C}"]) < TOL[mode]
+    assert np.array_equal(pred.cpu().numpy(), z[f"pred_c{C}"])
+    assert np.allclose(score.cpu().numpy(), z[f"score_c{C}"], atol=2e-3 if mode == "tf32" else 1e-5)
+    mn = _model(C, use_timeconv=False)
+    mn.math_mode = mode
+    with torch.no_grad():
+        ln = mn(x, lf)
+    assert rel_err(ln, z[f"logits_nlonly_c{C}"]) < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_head_batch_vs_oracle_with_margin_aware_argmax(mode):
+    """Config-4-shaped batch: logits within tolerance; argmax identical wherever the oracle's
+    top-2 margin exceeds twice the tolerance."""
+    _need_mode(mode)
+    B, seq, L = 256, 10, 30
+    lengths = [400, 350]
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    starts_all = synth.clip_starts(lengths, seq)
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(starts_all, size=B, replace=False))
+    feats = synth.features(sum(lengths), seed=21)
+    bank = synth.bank(len(starts_all), seed=21)
+    x = np.stack([feats[s:s + seq] for s in pick])
+    lf_ref = orc.get_long_feature(pick, orc.build_start_dict(starts_all.tolist()), bank, L)
+    ref_logits = orc.head(x, lf_ref, _sd(7))[0]
+    m = _model(7)
+    m.math_mode = mode
+    dev = _dev()
+    with torch.no_grad():
+        lf = tb.get_long_feature(pick, idx, torch.from_numpy(bank).to(dev), L)
+        assert np.array_equal(lf.cpu().numpy(), lf_ref)
+        logits, pred, score = m.predict(torch.from_numpy(x).to(dev), lf)
+    assert rel_err(logits, ref_logits) < TOL[mode]
+    top2 = torch.topk(ref_logits, 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    safe = margin > 2 * TOL[mode] * float(ref_logits.abs().max())
+    ref_pred = ref_logits.argmax(1)
+    assert torch.equal(pred.cpu()[safe], ref_pred[safe])
+    assert int(safe.sum()) > B * 0.9
+
+
+def test_empty_batch_is_a_noop():
+    m = _model(7)
+    dev = _dev()
+    with torch.no_grad():
+        logits, pred, score = m.predict(torch.zeros(0, 10, 2048, device=dev), torch.zeros(0, 30, 512, device=dev))
+    assert logits.shape == (0, 7) and pred.shape == (0,)
+
+
+def test_linear_generic():
+    dev = _dev()
+    rng = np.random.default_rng(0)
+    for M, N, K in [(1, 7, 512), (130, 512, 1024), (257, 2048, 2048), (5, 300, 16)]:
+        a = torch.from_numpy(rng.standard_normal((M, K), dtype=np.float32))
+        w = torch.from_numpy(rng.standard_normal((N, K), dtype=np.float32))
+        b = torch.from_numpy(rng.standard_normal((N,), dtype=np.float32))
+        ref = torch.relu(a.double() @ w.double().T + b.double())
+        got = ops.linear(a.to(dev), w.to(dev), b.to(dev), relu=True, math_mode="fp32")
+        assert rel_err(got, ref) < 1e-5

@@ -1,0 +1,408 @@
+// extern "C" entry points of libtmr_b200.so (see include/tmr_b200.h for the contract and the
+// reference code each one replaces).  Orchestration only: argument checks, workspace carving and
+// kernel sequencing on the caller's stream.  No allocation, no synchronisation, no global state.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "tmr_internal.h"
+
+namespace tmr {
+
+std::string& last_error_ref() {
+  static thread_local std::string e;
+  return e;
+}
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+static int check_mode(int math_mode) {
+  TMR_CHECK_ARG(math_mode == TMR_MATH_FP32 || math_mode == TMR_MATH_TF32, "unknown math_mode %d", math_mode);
+  if (math_mode == TMR_MATH_TF32 && !umma_available())
+    return set_error(TMR_ERR_UNSUPPORTED, "TMR_MATH_TF32 needs the tcgen05 kernels (sm_100a device + build)");
+  return TMR_OK;
+}
+static int check_dims(int D, int F = kF) {
+  TMR_CHECK_ARG(D == kD, "D=%d unsupported: the head is built for D=%d (reference hard-codes 512)", D, kD);
+  TMR_CHECK_ARG(F == kF, "F=%d unsupported: the head is built for F=%d", F, kF);
+  return TMR_OK;
+}
+static int do_linear(const LinearArgs& g, int mode, cudaStream_t st) {
+  return mode == TMR_MATH_TF32 ? umma_linear(g, st) : simt_linear(g, st);
+}
+
+struct Carver {
+  char* p; size_t left;
+  Carver(void* ws, size_t bytes) : p((char*)ws), left(bytes) {}
+  float* take(size_t n_floats) {
+    const size_t b = align_up(n_floats * sizeof(float), 256);
+    if (b > left) return nullptr;
+    float* r = (float*)p; p += b; left -= b; return r;
+  }
+};
+static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof(float), 256); }
+
+// ---- stage implementations on carved workspaces -------------------------------------------------
+static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
+                        float* w0, float* w1, int mode, cudaStream_t st) {
+  LinearArgs g;
+  // q = St W1^T + b1                                   (NLB:26-27)
+  g = LinearArgs(); g.a = St; g.lda = kD; g.w = pk + NLBlockPacked::w1_off; g.ldw = kD;
+  g.bias = pk + NLBlockPacked::b1_off; g.out = w0; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  TMR_TRY(do_linear(g, mode, st));
+  // u = W2^T q  (phi folded onto the query; b2 cancels in the softmax)     (NLB:28-30)
+  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w2t_off; g.ldw = kD;
+  g.out = w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  TMR_TRY(do_linear(g, mode, st));
+  // a = sum_k softmax(scale u.Lt_k) Lt_k                                   (NLB:30-34)
+  TMR_TRY(launch_attention(w1, Lt, B, L, w0, st));
+  // v = W3 a + b3  (g folded after the weighted sum: sum_k p_k = 1)         (NLB:33-34)
+  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w3_off; g.ldw = kD;
+  g.bias = pk + NLBlockPacked::b3_off; g.out = w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  TMR_TRY(do_linear(g, mode, st));
+  // r = relu(LayerNorm(v))                                                 (NLB:35-36)
+  TMR_TRY(launch_layernorm_relu(w1, pk + NLBlockPacked::lnw_off, pk + NLBlockPacked::lnb_off, B, w0, st));
+  // out = St + W4 r + b4   (dropout is the identity in eval)               (NLB:37-40)
+  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w4_off; g.ldw = kD;
+  g.bias = pk + NLBlockPacked::b4_off; g.residual = St; g.ldr = kD; g.out = out; g.ldo = kD;
+  g.M = B; g.N = kD; g.K = kD;
+  return do_linear(g, mode, st);
+}
+
+static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
+                     int seq, float* out, float* xp_buf, float* h0, float* h1, float* c, int mode,
+                     cudaStream_t st, int64_t frame0 = 0) {
+  float* xp = xp_buf;
+  // input projection for every row of x once: xp = x Wih'^T + (b_ih + b_hh)', gate-interleaved
+  LinearArgs g;
+  g.a = x; g.lda = kF; g.w = pk + LstmPacked::wih_off; g.ldw = kF; g.bias = pk + LstmPacked::bias_off;
+  g.out = xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
+  TMR_TRY(do_linear(g, mode, st));
+  xp -= frame0 * 4 * kD;   // rows are addressed by GLOBAL frame id (starts[m] + t) from here on
+  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out`
+  float* hcur = (seq == 1) ? out : h0;
+  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, c, B, st));
+  for (int t = 1; t < seq; ++t) {
+    float* hnext = (t == seq - 1) ? out : (hcur == h0 ? h1 : h0);
+    if (mode == TMR_MATH_TF32)
+      TMR_TRY(umma_lstm_step(pk + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, c, B, st));
+    else
+      TMR_TRY(simt_lstm_step(pk + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, c, B, st));
+    hcur = hnext;
+  }
+  return TMR_OK;
+}
+
+static int classifier_impl(const float* pk, const float* St, const float* y1, int B, int C,
+                           float* logits, int64_t* pred, float* score, float* z, int mode,
+                           cudaStream_t st) {
+  LinearArgs g;   // z = relu(fc_h_c([St || y1]))   (TRAIN:249-251, eval: dropout = identity)
+  g.a = St; g.lda = kD; g.a2 = y1; g.lda2 = kD; g.k_split = kD; g.w = pk + ClassifierPacked::wh_off;
+  g.ldw = 2 * kD; g.bias = pk + ClassifierPacked::bh_off; g.out = z; g.ldo = kD; g.M = B; g.N = kD;
+  g.K = 2 * kD; g.relu = 1;
+  TMR_TRY(do_linear(g, mode, st));
+  return launch_fc_argmax(z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
+                          pred, score, st);
+}
+
+}  // namespace tmr
+
+using namespace tmr;
+
+extern "C" {
+
+const char* tmr_last_error(void) { return last_error_ref().c_str(); }
+int tmr_version(void) { return 100; }
+
+int tmr_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error(TMR_ERR_CUDA, "no CUDA device"); return -1; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+int tmr_build_frame2row(const int64_t* lens_host, int V, int seq, int32_t* frame2row_host,
+                        int32_t* frame2vstart_host, int64_t* n_rows_out) {
+  TMR_CHECK_ARG(lens_host && frame2row_host && V >= 0 && seq >= 1, "build_frame2row: bad arguments");
+  int64_t total = 0, rows = 0;
+  for (int v = 0; v < V; ++v) {
+    TMR_CHECK_ARG(lens_host[v] >= 0, "build_frame2row: negative video length");
+    total += lens_host[v];
+  }
+  TMR_CHECK_ARG(total < (int64_t)INT32_MAX, "build_frame2row: more than 2^31 frames");
+  // forward pass: rows of valid starts, -1 elsewhere
+  int64_t g = 0;
+  for (int v = 0; v < V; ++v) {
+    const int64_t n = lens_host[v];
+    const int64_t n_valid = n - seq + 1 > 0 ? n - seq + 1 : 0;
+    for (int64_t j = 0; j < n; ++j, ++g) {
+      frame2row_host[g] = (j < n_valid) ? (int32_t)(rows + j) : -1;
+      if (frame2vstart_host) frame2vstart_host[g] = (int32_t)(g - j);
+    }
+    rows += n_valid;
+  }
+  // backward pass: an invalid frame takes the row of the smallest valid start above it — the row
+  // the reference walk is still "remembering" when it reaches that key (TRAIN:312-323)
+  int32_t nxt = -1;
+  for (int64_t i = total - 1; i >= 0; --i) {
+    if (frame2row_host[i] >= 0) nxt = frame2row_host[i];
+    else frame2row_host[i] = nxt;
+  }
+  if (n_rows_out) *n_rows_out = rows;
+  return TMR_OK;
+}
+
+int tmr_gather_windows(const float* bank, int64_t n_rows, const int32_t* frame2row,
+                       const int32_t* frame2vstart, int64_t n_frames, const int64_t* starts, int B,
+                       int L, int D, int pad_mode, float* out, int32_t* rows_out, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_CHECK_ARG(B >= 0 && L >= 1, "gather: bad B=%d L=%d", B, L);
+  TMR_CHECK_ARG(pad_mode == TMR_PAD_REPEAT || pad_mode == TMR_PAD_ZERO, "gather: bad pad_mode %d", pad_mode);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(bank && frame2row && starts && out, "gather: null pointer");
+  TMR_CHECK_ARG(pad_mode != TMR_PAD_ZERO || frame2vstart, "gather: TMR_PAD_ZERO needs frame2vstart");
+  TMR_CHECK_ARG(aligned16(bank) && aligned16(out), "gather: bank/out must be 16-byte aligned");
+  TMR_CHECK_ARG(n_rows > 0 && n_frames > 0, "gather: empty bank");
+  return launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames, starts, B, L, pad_mode, out,
+                       rows_out, (cudaStream_t)stream);
+}
+
+size_t tmr_timeconv_packed_bytes(int D) { return D == kD ? TimeConvPacked::total * sizeof(float) : 0; }
+int tmr_timeconv_pack(const float* w3, const float* b3, const float* w5, const float* b5,
+                      const float* w7, const float* b7, int D, void* packed, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_CHECK_ARG(w3 && b3 && w5 && b5 && w7 && b7 && packed, "timeconv_pack: null pointer");
+  return launch_pack_timeconv(w3, b3, w5, b5, w7, b7, (float*)packed, (cudaStream_t)stream);
+}
+
+size_t tmr_nlblock_packed_bytes(int D) { return D == kD ? NLBlockPacked::total * sizeof(float) : 0; }
+int tmr_nlblock_pack(const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* w3, const float* b3, const float* w4, const float* b4,
+                     const float* ln_w, const float* ln_b, int D, void* packed, void* stream) {
+  TMR_TRY(check_dims(D));
+  (void)b2;  // cancels inside the softmax over L
+  TMR_CHECK_ARG(w1 && b1 && w2 && w3 && b3 && w4 && b4 && ln_w && ln_b && packed, "nlblock_pack: null pointer");
+  return launch_pack_nlblock(w1, b1, w2, w3, b3, w4, b4, ln_w, ln_b, (float*)packed, (cudaStream_t)stream);
+}
+
+size_t tmr_lstm_packed_bytes(int F, int D) { return (D == kD && F == kF) ? LstmPacked::total * sizeof(float) : 0; }
+int tmr_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int F,
+                  int D, void* packed, void* stream) {
+  TMR_TRY(check_dims(D, F));
+  TMR_CHECK_ARG(w_ih && w_hh && b_ih && b_hh && packed, "lstm_pack: null pointer");
+  return launch_pack_lstm(w_ih, w_hh, b_ih, b_hh, (float*)packed, (cudaStream_t)stream);
+}
+
+size_t tmr_classifier_packed_bytes(int D, int C) {
+  return (D == kD && C >= 1 && C <= ClassifierPacked::kMaxC) ? ClassifierPacked::total * sizeof(float) : 0;
+}
+int tmr_classifier_pack(const float* w_h, const float* b_h, const float* w_c, const float* b_c,
+                        int D, int C, void* packed, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "classifier_pack: C=%d out of range [1,%d]", C, ClassifierPacked::kMaxC);
+  TMR_CHECK_ARG(w_h && b_h && w_c && b_c && packed, "classifier_pack: null pointer");
+  return launch_pack_classifier(w_h, b_h, w_c, b_c, C, (float*)packed, (cudaStream_t)stream);
+}
+
+int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D, float* out,
+                         int math_mode, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && L >= 1, "timeconv: bad B=%d L=%d", B, L);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(packed && x && out, "timeconv: null pointer");
+  TMR_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(packed), "timeconv: pointers must be 16-byte aligned");
+  TMR_CHECK_ARG(x != out, "timeconv: in-place not supported");
+  if (math_mode == TMR_MATH_TF32)
+    return umma_timeconv((const float*)packed, x, B, L, out, (cudaStream_t)stream);
+  return simt_timeconv((const float*)packed, x, B, L, out, (cudaStream_t)stream);
+}
+
+size_t tmr_nlblock_workspace_bytes(int B, int D) { return 2 * fbytes((size_t)(B > 0 ? B : 1) * D); }
+int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B, int L, int D,
+                    float* out, void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && L >= 1, "nlblock: bad B=%d L=%d", B, L);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(packed && St && Lt && out && workspace, "nlblock: null pointer");
+  TMR_CHECK_ARG(aligned16(St) && aligned16(Lt) && aligned16(out) && aligned16(workspace) && aligned16(packed),
+                "nlblock: pointers must be 16-byte aligned");
+  Carver cv(workspace, workspace_bytes);
+  float* w0 = cv.take((size_t)B * kD);
+  float* w1 = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(w0 && w1, "nlblock: workspace too small (%zu < %zu)", workspace_bytes, tmr_nlblock_workspace_bytes(B, D));
+  return nlblock_impl((const float*)packed, St, Lt, B, L, out, w0, w1, math_mode, (cudaStream_t)stream);
+}
+
+size_t tmr_lstm_workspace_bytes(int64_t n_rows_x, int B, int D) {
+  return fbytes((size_t)(n_rows_x > 0 ? n_rows_x : 1) * 4 * D) + 3 * fbytes((size_t)(B > 0 ? B : 1) * D);
+}
+static int lstm_entry(const void* packed, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
+                      int seq, int F, int D, float* out, void* workspace, size_t workspace_bytes,
+                      int math_mode, void* stream) {
+  TMR_TRY(check_dims(D, F));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && seq >= 1 && n_rows_x >= 0, "lstm: bad B=%d seq=%d", B, seq);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(packed && x && out && workspace, "lstm: null pointer");
+  TMR_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(workspace) && aligned16(packed), "lstm: pointers must be 16-byte aligned");
+  Carver cv(workspace, workspace_bytes);
+  float* xp = cv.take((size_t)n_rows_x * 4 * kD);
+  float* h0 = cv.take((size_t)B * kD);
+  float* h1 = cv.take((size_t)B * kD);
+  float* c = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(xp && h0 && h1 && c, "lstm: workspace too small (%zu < %zu)", workspace_bytes,
+                tmr_lstm_workspace_bytes(n_rows_x, B, D));
+  return lstm_impl((const float*)packed, x, n_rows_x, starts, B, seq, out, xp, h0, h1, c, math_mode,
+                   (cudaStream_t)stream);
+}
+int tmr_lstm_last_fwd(const void* packed, const float* x, int B, int seq, int F, int D, float* out,
+                      void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
+  return lstm_entry(packed, x, (int64_t)B * seq, nullptr, B, seq, F, D, out, workspace, workspace_bytes,
+                    math_mode, stream);
+}
+int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_frames,
+                             const int64_t* starts, int B, int seq, int F, int D, float* out,
+                             void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
+  TMR_CHECK_ARG(B == 0 || starts, "lstm_frames: starts is null");
+  return lstm_entry(packed, feats, n_frames, starts, B, seq, F, D, out, workspace, workspace_bytes,
+                    math_mode, stream);
+}
+
+size_t tmr_classifier_workspace_bytes(int B, int D) { return fbytes((size_t)(B > 0 ? B : 1) * D); }
+int tmr_fc_argmax_fwd(const void* packed, const float* St, const float* y1, int B, int D, int C,
+                      float* logits, int64_t* pred, float* score, void* workspace,
+                      size_t workspace_bytes, int math_mode, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "fc_argmax: C=%d out of range", C);
+  TMR_CHECK_ARG(B >= 0, "fc_argmax: bad B");
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(packed && St && y1 && logits && workspace, "fc_argmax: null pointer");
+  TMR_CHECK_ARG(aligned16(St) && aligned16(y1) && aligned16(workspace) && aligned16(packed), "fc_argmax: pointers must be 16-byte aligned");
+  Carver cv(workspace, workspace_bytes);
+  float* z = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(z, "fc_argmax: workspace too small");
+  return classifier_impl((const float*)packed, St, y1, B, C, logits, pred, score, z, math_mode,
+                         (cudaStream_t)stream);
+}
+
+size_t tmr_head_workspace_bytes(int B, int seq, int L, int D) {
+  const size_t b = (size_t)(B > 0 ? B : 1);
+  return tmr_lstm_workspace_bytes((int64_t)b * seq, (int)b, D) + fbytes(b * L * D) + 2 * fbytes(b * D) +
+         tmr_nlblock_workspace_bytes((int)b, D) + tmr_classifier_workspace_bytes((int)b, D);
+}
+int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const void* nlblock_packed,
+                 const void* classifier_packed, const float* x, const float* long_feature, int B,
+                 int seq, int L, int F, int D, int C, float* logits, int64_t* pred, float* score,
+                 void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
+  TMR_TRY(check_dims(D, F));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && seq >= 1 && L >= 1, "head: bad B=%d seq=%d L=%d", B, seq, L);
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "head: C=%d out of range", C);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(lstm_packed && nlblock_packed && classifier_packed && x && long_feature && logits && workspace,
+                "head: null pointer");
+  TMR_CHECK_ARG(aligned16(x) && aligned16(long_feature) && aligned16(workspace), "head: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace, workspace_bytes);
+  float* xp = cv.take((size_t)B * seq * 4 * kD);
+  float* h0 = cv.take((size_t)B * kD);
+  float* h1 = cv.take((size_t)B * kD);
+  float* c = cv.take((size_t)B * kD);
+  float* Lt = cv.take((size_t)B * L * kD);
+  float* St = cv.take((size_t)B * kD);
+  float* y1 = cv.take((size_t)B * kD);
+  float* n0 = cv.take((size_t)B * kD);
+  float* n1 = cv.take((size_t)B * kD);
+  float* z = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(xp && h0 && h1 && c && Lt && St && y1 && n0 && n1 && z, "head: workspace too small (%zu < %zu)",
+                workspace_bytes, tmr_head_workspace_bytes(B, seq, L, D));
+  TMR_TRY(lstm_impl((const float*)lstm_packed, x, (int64_t)B * seq, nullptr, B, seq, St, xp, h0, h1, c, math_mode, st));
+  const float* Lt_in = long_feature;     // NL-only wiring: Lt = long_feature
+  if (timeconv_packed) {
+    if (math_mode == TMR_MATH_TF32) TMR_TRY(umma_timeconv((const float*)timeconv_packed, long_feature, B, L, Lt, st));
+    else TMR_TRY(simt_timeconv((const float*)timeconv_packed, long_feature, B, L, Lt, st));
+    Lt_in = Lt;
+  }
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, y1, n0, n1, math_mode, st));
+  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, z, math_mode, st);
+}
+
+size_t tmr_head_frames_workspace_bytes(int64_t n_feat_frames, int B, int L, int D) {
+  const size_t b = (size_t)(B > 0 ? B : 1);
+  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + 2 * fbytes(b * L * D) + 2 * fbytes(b * D) +
+         tmr_nlblock_workspace_bytes((int)b, D) + tmr_classifier_workspace_bytes((int)b, D);
+}
+int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
+                        const void* nlblock_packed, const void* classifier_packed,
+                        const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                        int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
+                        int64_t n_frames_total, const int64_t* starts, int B, int seq, int L, int F,
+                        int D, int C, int pad_mode, float* logits, int64_t* pred, float* score,
+                        float* St_out, void* workspace, size_t workspace_bytes, int math_mode,
+                        void* stream) {
+  TMR_TRY(check_dims(D, F));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && seq >= 1 && L >= 1 && n_feat_frames >= 0 && frame0 >= 0, "head_frames: bad sizes");
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "head_frames: C=%d out of range", C);
+  TMR_CHECK_ARG(pad_mode == TMR_PAD_REPEAT || pad_mode == TMR_PAD_ZERO, "head_frames: bad pad_mode");
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(lstm_packed && nlblock_packed && classifier_packed && feats && bank && frame2row && starts &&
+                logits && workspace, "head_frames: null pointer");
+  TMR_CHECK_ARG(pad_mode != TMR_PAD_ZERO || frame2vstart, "head_frames: TMR_PAD_ZERO needs frame2vstart");
+  TMR_CHECK_ARG(aligned16(feats) && aligned16(bank) && aligned16(workspace), "head_frames: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace, workspace_bytes);
+  float* xp = cv.take((size_t)n_feat_frames * 4 * kD);
+  float* h0 = cv.take((size_t)B * kD);
+  float* h1 = cv.take((size_t)B * kD);
+  float* c = cv.take((size_t)B * kD);
+  float* win = cv.take((size_t)B * L * kD);
+  float* Lt = cv.take((size_t)B * L * kD);
+  float* St = cv.take((size_t)B * kD);
+  float* y1 = cv.take((size_t)B * kD);
+  float* n0 = cv.take((size_t)B * kD);
+  float* n1 = cv.take((size_t)B * kD);
+  float* z = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(xp && h0 && h1 && c && win && Lt && St && y1 && n0 && n1 && z,
+                "head_frames: workspace too small (%zu < %zu)", workspace_bytes,
+                tmr_head_frames_workspace_bytes(n_feat_frames, B, L, D));
+  if (St_out) St = St_out;
+  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, xp, h0, h1, c,
+                    math_mode, st, frame0));
+  TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, starts, B, L, pad_mode, win,
+                        nullptr, st));
+  const float* Lt_in = win;
+  if (timeconv_packed) {
+    if (math_mode == TMR_MATH_TF32) TMR_TRY(umma_timeconv((const float*)timeconv_packed, win, B, L, Lt, st));
+    else TMR_TRY(simt_timeconv((const float*)timeconv_packed, win, B, L, Lt, st));
+    Lt_in = Lt;
+  }
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, y1, n0, n1, math_mode, st));
+  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, z, math_mode, st);
+}
+
+int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,
+                   float* out, int relu, int math_mode, void* stream) {
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "linear: bad sizes");
+  if (M == 0) return TMR_OK;
+  TMR_CHECK_ARG(a && w && out, "linear: null pointer");
+  TMR_CHECK_ARG(aligned16(a) && aligned16(w) && aligned16(out), "linear: pointers must be 16-byte aligned");
+  LinearArgs g;
+  g.a = a; g.lda = K; g.w = w; g.ldw = K; g.bias = bias; g.out = out; g.ldo = N; g.M = M; g.N = N; g.K = K;
+  g.relu = relu;
+  return do_linear(g, math_mode, (cudaStream_t)stream);
+}
+
+}  // extern "C"

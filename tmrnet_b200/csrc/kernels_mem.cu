@@ -1,0 +1,383 @@
+// HBM-bound kernels of the head: window gather, attention over the L memory slots (warp-shuffle
+// online softmax), LayerNorm+ReLU, the 7-way FC + softmax score + argmax, the LSTM step-0 cell and
+// the one-off weight repacks.  All use 128-bit accesses with a warp per 512-float row.
+#include "tmr_internal.h"
+
+namespace tmr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// streaming 128-bit load/store: the bank is read through the read-only path; gathered windows are
+// written once and not re-read by this kernel.
+__device__ __forceinline__ float4 ldg_nc(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_na(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// -------------------------------------------------------------------------------------------
+// a3: window gather.  One warp per (clip, slot) row of 512 floats: 4 x 128-bit loads per lane.
+// row(b,k) = frame2row[starts[b]-k-1], 0 for negative keys (repeat-fill/leak semantics are baked
+// into frame2row, see tmr_build_frame2row); TMR_PAD_ZERO zeroes slots before the clip's video.
+// -------------------------------------------------------------------------------------------
+constexpr int kGatherWarps = 8;
+
+__global__ void __launch_bounds__(kGatherWarps * 32)
+gather_kernel(const float* __restrict__ bank, int64_t n_rows, const int32_t* __restrict__ f2r,
+              const int32_t* __restrict__ f2v, const int64_t* __restrict__ starts, int64_t total,
+              int L, int pad_mode, float* __restrict__ out, int32_t* __restrict__ rows_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid0 = (int64_t)blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * kGatherWarps;
+  for (int64_t w = wid0; w < total; w += stride) {
+    const int64_t b = w / L;
+    const int k = (int)(w - b * L);
+    const int64_t s = starts[b];
+    const int64_t key = s - k - 1;
+    int64_t row;
+    if (pad_mode == TMR_PAD_ZERO) {
+      row = (key >= (int64_t)f2v[s]) ? (int64_t)f2r[key] : -1;
+    } else {
+      row = (key >= 0) ? (int64_t)f2r[key] : 0;
+    }
+    float4 v[4];
+    if (row >= 0) {
+      const float4* src = reinterpret_cast<const float4*>(bank + row * kD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = ldg_nc(src + i * 32 + lane);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + w * kD);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) stg_na(dst + i * 32 + lane, v[i]);
+    if (rows_out && lane == 0) rows_out[w] = (int32_t)row;
+  }
+}
+
+int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
+                  int64_t n_frames, const int64_t* starts, int B, int L, int pad_mode, float* out,
+                  int32_t* rows_out, cudaStream_t st) {
+  const int64_t total = (int64_t)B * L;
+  if (total == 0) return TMR_OK;
+  // grid: enough warps to cover the rows, capped at a multiple of the 148 SMs (8 CTAs each)
+  int64_t blocks = (total + kGatherWarps - 1) / kGatherWarps;
+  const int64_t cap = 148 * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  gather_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, st>>>(bank, n_rows, f2r, f2v, starts, total,
+                                                               L, pad_mode, out, rows_out);
+  TMR_LAUNCH_CHECK("gather_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// LSTM step 0 from zero state: gates = xp row (bias already folded), c = sig(i) tanh(g).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+__global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* __restrict__ starts,
+                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (clip, unit)
+  if (idx >= total) return;
+  const int64_t m = idx / kD;
+  const int unit = (int)(idx - m * kD);
+  const int64_t xr = starts ? starts[m] : m * seq;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(xp + xr * (4 * kD) + unit * 4));
+  const float cn = sigmoidf_(p.x) * tanhf(p.z);     // f * 0 drops out
+  c[idx] = cn;
+  h[idx] = sigmoidf_(p.w) * tanhf(cn);
+}
+
+int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
+                      cudaStream_t st) {
+  const int64_t total = (int64_t)B * kD;
+  if (total == 0) return TMR_OK;
+  lstm_cell0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xp, starts, seq, h, c, total);
+  TMR_LAUNCH_CHECK("lstm_cell0_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Attention over the memory slots (NLB:30-34 with phi/g folded):
+//   s_k = scale * (u . Lt_k),  p = softmax_k(s),  a = sum_k p_k Lt_k.
+// One warp per clip; each lane owns 16 channels (4 float4); slots are streamed once in chunks of
+// KB rows with an online (running-max) softmax, dots reduced with warp shuffles.
+// -------------------------------------------------------------------------------------------
+constexpr int kAttnWarps = 4;
+constexpr int KB = 6;
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
+                 float* __restrict__ a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float4 uq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) uq[i] = __ldg(reinterpret_cast<const float4*>(u + (int64_t)b * kD) + i * 32 + lane);
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float run_max = -INFINITY, run_sum = 0.f;
+  const float4* base = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
+
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    float4 x[KB][4];
+    float d[KB];
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      if (k0 + kk < L) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[kk][i] = ldg_nc(base + (int64_t)(k0 + kk) * (kD / 4) + i * 32 + lane);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[kk][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p = fmaf(x[kk][i].x, uq[i].x, p); p = fmaf(x[kk][i].y, uq[i].y, p);
+        p = fmaf(x[kk][i].z, uq[i].z, p); p = fmaf(x[kk][i].w, uq[i].w, p);
+      }
+      d[kk] = p;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) d[kk] = warp_sum(d[kk]);
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      d[kk] = (k0 + kk < L) ? d[kk] * scale : -INFINITY;
+      cmax = fmaxf(cmax, d[kk]);
+    }
+    const float new_max = fmaxf(run_max, cmax);
+    const float corr = expf(run_max - new_max);          // 0 on the first chunk (run_max = -inf)
+    run_sum *= corr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      const float p = expf(d[kk] - new_max);             // exp(-inf) = 0 for masked slots
+      run_sum += p;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i].x = fmaf(p, x[kk][i].x, acc[i].x); acc[i].y = fmaf(p, x[kk][i].y, acc[i].y);
+        acc[i].z = fmaf(p, x[kk][i].z, acc[i].z); acc[i].w = fmaf(p, x[kk][i].w, acc[i].w);
+      }
+    }
+    run_max = new_max;
+  }
+  const float inv = 1.f / run_sum;
+  float4* dst = reinterpret_cast<float4*>(a + (int64_t)b * kD);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    dst[i * 32 + lane] = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+}
+
+int launch_attention(const float* u, const float* Lt, int B, int L, float* a, cudaStream_t st) {
+  if (B == 0) return TMR_OK;
+  const float scale = (float)0.044194173824159216;   // (1/512)**0.5 as python computes it (NLB:31)
+  attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a);
+  TMR_LAUNCH_CHECK("attention_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// LayerNorm([1,512]) (biased variance, eps 1e-5) + ReLU (NLB:35-36).  One warp per row.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
+                      const float* __restrict__ bsh, int B, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float4* src = reinterpret_cast<const float4*>(v + (int64_t)b * kD);
+  float4 x[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { x[i] = src[i * 32 + lane]; s += (x[i].x + x[i].y) + (x[i].z + x[i].w); }
+  const float mean = warp_sum(s) * (1.f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a0 = x[i].x - mean, a1 = x[i].y - mean, a2 = x[i].z - mean, a3 = x[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / kD) + 1e-5f);
+  float4* dst = reinterpret_cast<float4*>(y + (int64_t)b * kD);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(bsh) + i * 32 + lane);
+    float4 o;
+    o.x = fmaxf((x[i].x - mean) * rstd * g.x + be.x, 0.f);
+    o.y = fmaxf((x[i].y - mean) * rstd * g.y + be.y, 0.f);
+    o.z = fmaxf((x[i].z - mean) * rstd * g.z + be.z, 0.f);
+    o.w = fmaxf((x[i].w - mean) * rstd * g.w + be.w, 0.f);
+    dst[i * 32 + lane] = o;
+  }
+}
+
+int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y, cudaStream_t st) {
+  if (B == 0) return TMR_OK;
+  layernorm_relu_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, w, b, B, y);
+  TMR_LAUNCH_CHECK("layernorm_relu_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// fc_c (512 -> C) + Softmax + torch.max (TRAIN:252, EVAL:491-493).  One warp per clip.
+// pred = first index of the maximum logit (ties -> lowest index); score = 1 / sum exp(l - lmax).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fc_argmax_kernel(const float* __restrict__ z, const float* __restrict__ wc, const float* __restrict__ bc,
+                 int B, int C, float* __restrict__ logits, int64_t* __restrict__ pred,
+                 float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)b * kD) + i * 32 + lane);
+  float mine = -INFINITY;                    // lane c keeps logit c (C <= 32)
+  for (int c = 0; c < C; ++c) {
+    const float4* wr = reinterpret_cast<const float4*>(wc + (int64_t)c * kD);
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 w = __ldg(wr + i * 32 + lane);
+      p = fmaf(x[i].x, w.x, p); p = fmaf(x[i].y, w.y, p); p = fmaf(x[i].z, w.z, p); p = fmaf(x[i].w, w.w, p);
+    }
+    p = warp_sum(p) + __ldg(bc + c);
+    if (lane == c) mine = p;
+  }
+  if (lane < C) logits[(int64_t)b * C + lane] = mine;
+  const float mx = warp_max(mine);
+  const unsigned hit = __ballot_sync(0xffffffffu, lane < C && mine == mx);
+  const float e = (lane < C) ? expf(mine - mx) : 0.f;
+  const float den = warp_sum(e);
+  if (lane == 0) {
+    if (pred) pred[b] = (int64_t)(__ffs(hit) - 1);
+    if (score) score[b] = 1.f / den;
+  }
+}
+
+int launch_fc_argmax(const float* z, const float* wc, const float* bc, int B, int C, float* logits,
+                     int64_t* pred, float* score, cudaStream_t st) {
+  if (B == 0) return TMR_OK;
+  fc_argmax_kernel<<<(B + 3) / 4, 128, 0, st>>>(z, wc, bc, B, C, logits, pred, score);
+  TMR_LAUNCH_CHECK("fc_argmax_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// weight repacks (run once per weight update)
+// -------------------------------------------------------------------------------------------
+__global__ void pack_conv_kernel(const float* __restrict__ w, int taps, float* __restrict__ dst) {
+  // dst[o][tap][c] = w[o][c][tap]
+  const int64_t total = (int64_t)kD * taps * kD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kD);
+    const int tap = (int)((i / kD) % taps);
+    const int o = (int)(i / ((int64_t)kD * taps));
+    dst[i] = w[((int64_t)o * kD + c) * taps + tap];
+  }
+}
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  // dst[j][i] = src[i][j], n x n
+  __shared__ float t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) t[r][threadIdx.x] = src[(int64_t)(by + r) * n + bx + threadIdx.x];
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) dst[(int64_t)(bx + r) * n + by + threadIdx.x] = t[threadIdx.x][r];
+}
+// dst row (unit*4+gate) = src row (gate*D+unit); cols wide
+__global__ void interleave_gates_kernel(const float* __restrict__ src, float* __restrict__ dst, int cols) {
+  const int64_t total = (int64_t)4 * kD * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % cols);
+    const int r = (int)(i / cols);
+    const int unit = r >> 2, gate = r & 3;
+    dst[i] = src[((int64_t)gate * kD + unit) * cols + col];
+  }
+}
+__global__ void interleave_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 4 * kD) return;
+  const int unit = r >> 2, gate = r & 3;
+  dst[r] = bih[gate * kD + unit] + bhh[gate * kD + unit];
+}
+
+static inline unsigned blocks_for(int64_t n) { int64_t b = (n + 255) / 256; return (unsigned)(b > 4096 ? 4096 : b); }
+
+int launch_pack_timeconv(const float* w3, const float* b3, const float* w5, const float* b5,
+                         const float* w7, const float* b7, float* packed, cudaStream_t st) {
+  pack_conv_kernel<<<blocks_for((int64_t)kD * 3 * kD), 256, 0, st>>>(w3, 3, packed + TimeConvPacked::w3_off);
+  pack_conv_kernel<<<blocks_for((int64_t)kD * 5 * kD), 256, 0, st>>>(w5, 5, packed + TimeConvPacked::w5_off);
+  pack_conv_kernel<<<blocks_for((int64_t)kD * 7 * kD), 256, 0, st>>>(w7, 7, packed + TimeConvPacked::w7_off);
+  copy_kernel<<<2, 256, 0, st>>>(b3, packed + TimeConvPacked::b3_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(b5, packed + TimeConvPacked::b5_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(b7, packed + TimeConvPacked::b7_off, kD);
+  TMR_LAUNCH_CHECK("pack_timeconv");
+  return TMR_OK;
+}
+
+int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const float* w3,
+                        const float* b3, const float* w4, const float* b4, const float* lnw,
+                        const float* lnb, float* packed, cudaStream_t st) {
+  const int64_t n2 = (int64_t)kD * kD;
+  copy_kernel<<<blocks_for(n2), 256, 0, st>>>(w1, packed + NLBlockPacked::w1_off, n2);
+  transpose_kernel<<<dim3(kD / 32, kD / 32), dim3(32, 8), 0, st>>>(w2, packed + NLBlockPacked::w2t_off, kD);
+  copy_kernel<<<blocks_for(n2), 256, 0, st>>>(w3, packed + NLBlockPacked::w3_off, n2);
+  copy_kernel<<<blocks_for(n2), 256, 0, st>>>(w4, packed + NLBlockPacked::w4_off, n2);
+  copy_kernel<<<2, 256, 0, st>>>(b1, packed + NLBlockPacked::b1_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(b3, packed + NLBlockPacked::b3_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(b4, packed + NLBlockPacked::b4_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(lnw, packed + NLBlockPacked::lnw_off, kD);
+  copy_kernel<<<2, 256, 0, st>>>(lnb, packed + NLBlockPacked::lnb_off, kD);
+  TMR_LAUNCH_CHECK("pack_nlblock");
+  return TMR_OK;
+}
+
+int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const float* bhh,
+                     float* packed, cudaStream_t st) {
+  interleave_gates_kernel<<<blocks_for((int64_t)4 * kD * kF), 256, 0, st>>>(wih, packed + LstmPacked::wih_off, kF);
+  interleave_gates_kernel<<<blocks_for((int64_t)4 * kD * kD), 256, 0, st>>>(whh, packed + LstmPacked::whh_off, kD);
+  interleave_bias_kernel<<<(4 * kD + 255) / 256, 256, 0, st>>>(bih, bhh, packed + LstmPacked::bias_off);
+  TMR_LAUNCH_CHECK("pack_lstm");
+  return TMR_OK;
+}
+
+int launch_pack_classifier(const float* wh, const float* bh, const float* wc, const float* bc, int C,
+                           float* packed, cudaStream_t st) {
+  TMR_CUDA(cudaMemsetAsync(packed + ClassifierPacked::wc_off, 0,
+                           sizeof(float) * (ClassifierPacked::total - ClassifierPacked::wc_off), st));
+  const int64_t nh = (int64_t)kD * 2 * kD;
+  copy_kernel<<<blocks_for(nh), 256, 0, st>>>(wh, packed + ClassifierPacked::wh_off, nh);
+  copy_kernel<<<2, 256, 0, st>>>(bh, packed + ClassifierPacked::bh_off, kD);
+  copy_kernel<<<blocks_for((int64_t)C * kD), 256, 0, st>>>(wc, packed + ClassifierPacked::wc_off, (int64_t)C * kD);
+  copy_kernel<<<1, 256, 0, st>>>(bc, packed + ClassifierPacked::bc_off, C);
+  TMR_LAUNCH_CHECK("pack_classifier");
+  return TMR_OK;
+}
+
+}  // namespace tmr

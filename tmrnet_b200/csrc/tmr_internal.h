@@ -1,0 +1,59 @@
+// Internal launcher prototypes shared by api.cu and the kernel translation units.
+#pragma once
+#include "tmr_common.cuh"
+
+namespace tmr {
+
+// out[M,N] (ldo) = [a | a2][M,K] . w[N,K]^T (+bias[N]) (+residual[M,N]) (relu).  Columns k < k_split
+// come from a (lda), the rest from a2 (lda2); a2 == nullptr means k_split == K.
+struct LinearArgs {
+  const float* a = nullptr;  int64_t lda = 0;
+  const float* a2 = nullptr; int64_t lda2 = 0; int k_split = 0;
+  const float* w = nullptr;  int64_t ldw = 0;
+  const float* bias = nullptr;
+  const float* residual = nullptr; int64_t ldr = 0;
+  float* out = nullptr; int64_t ldo = 0;
+  int64_t M = 0; int N = 0; int K = 0; int relu = 0;
+};
+
+// ---- fp32 CUDA-core path (kernels_simt.cu) ----
+int simt_linear(const LinearArgs& g, cudaStream_t st);
+int simt_timeconv(const float* packed, const float* x, int B, int L, float* out, cudaStream_t st);
+// One recurrent step t >= 1: gates = h_prev . Whh'^T + xp[row(m,t)], cell update into (h_out, c).
+// row(m,t) = (starts ? starts[m] : m*seq) + t.
+int simt_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
+                   const float* h_prev, float* h_out, float* c, int B, cudaStream_t st);
+
+// ---- tcgen05 TF32 path (umma_*.cu); same contracts ----
+int umma_linear(const LinearArgs& g, cudaStream_t st);
+int umma_timeconv(const float* packed, const float* x, int B, int L, float* out, cudaStream_t st);
+int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
+                   const float* h_prev, float* h_out, float* c, int B, cudaStream_t st);
+bool umma_available();
+
+// ---- memory-bound kernels (kernels_mem.cu) ----
+int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
+                  int64_t n_frames, const int64_t* starts, int B, int L, int pad_mode, float* out,
+                  int32_t* rows_out, cudaStream_t st);
+// step 0 of the LSTM from zero state: c = sig(i)*tanh(g), h = sig(o)*tanh(c) from xp rows.
+int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
+                      cudaStream_t st);
+// a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]
+int launch_attention(const float* u, const float* Lt, int B, int L, float* a, cudaStream_t st);
+// y = relu(layer_norm(v) * w + b) over rows of 512
+int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y,
+                          cudaStream_t st);
+// logits = z . Wc^T + bc ; score = max softmax prob ; pred = first argmax
+int launch_fc_argmax(const float* z, const float* wc, const float* bc, int B, int C, float* logits,
+                     int64_t* pred, float* score, cudaStream_t st);
+int launch_pack_timeconv(const float* w3, const float* b3, const float* w5, const float* b5,
+                         const float* w7, const float* b7, float* packed, cudaStream_t st);
+int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const float* w3,
+                        const float* b3, const float* w4, const float* b4, const float* lnw,
+                        const float* lnb, float* packed, cudaStream_t st);
+int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const float* bhh,
+                     float* packed, cudaStream_t st);
+int launch_pack_classifier(const float* wh, const float* bh, const float* wc, const float* bc, int C,
+                           float* packed, cudaStream_t st);
+
+}  // namespace tmr

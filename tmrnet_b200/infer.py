@@ -1,0 +1,154 @@
+"""Bank-level inference of the TMRNet head: the reference's test loop body
+(code/eval/python/test_singlenet_phase_non-local_pretrained_2fc_copy_mutiConv6_resnest.py:470-499)
+over per-frame backbone features and a memory bank that are both resident in HBM, plus the
+video-sharding plan for multi-GPU inference: videos are independent units, each GPU
+holds its own videos' features and bank rows (+ a halo of the previous video's tail, because the
+reference window leaks across the video boundary), and no collective is needed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .lfb import LFBIndex
+from .ops import D, F, _dev, _mode, _ptr, _stream, _ws, check
+
+
+class BankInference:
+    """Runs the head over every clip of a (shard of a) feature bank in clip batches.
+
+    model: tmrnet_b200.resnet_lstm (eval).  feats: CUDA (n_frames, 2048).  bank: CUDA (n_rows, 512).
+    index: LFBIndex.from_lengths(video_lengths, seq) for the same frames/rows.
+    """
+
+    def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 8192,
+                 pad_mode: str = "repeat", math_mode=None, starts=None):
+        self.model = model
+        self.index = index
+        self.seq, self.L = int(seq), int(L)
+        self.batch_clips = int(batch_clips)
+        self.pad_mode = {"repeat": ops.TMR_PAD_REPEAT, "zero": ops.TMR_PAD_ZERO}[pad_mode]
+        self.math_mode = math_mode
+        if starts is None:       # every clip of the index; a VideoShard passes its owned clips only
+            starts = np.fromiter(index.keys(), dtype=np.int64, count=len(index))
+        self.starts_host = np.sort(np.asarray(starts, dtype=np.int64))
+        self._ws = None
+        self._starts_dev = None
+
+    def plan(self):
+        """[(clip_lo, clip_hi, frame_lo, frame_hi)] per batch; frames cover every clip of the batch."""
+        out = []
+        n = len(self.starts_host)
+        for lo in range(0, n, self.batch_clips):
+            hi = min(n, lo + self.batch_clips)
+            out.append((lo, hi, int(self.starts_host[lo]), int(self.starts_host[hi - 1]) + self.seq))
+        return out
+
+    def run(self, feats, bank, starts_dev=None, out=None, want_st=False):
+        """All clips of the index in global clip order.  Returns dict(logits, pred, score[, St])."""
+        feats = _dev(feats, "feats")
+        bank = _dev(bank, "bank")
+        dev = feats.device
+        n = len(self.starts_host)
+        Cn = self.model.num_class
+        if starts_dev is None:
+            if self._starts_dev is None or self._starts_dev.device != dev:
+                self._starts_dev = torch.from_numpy(self.starts_host).to(dev)
+            starts_dev = self._starts_dev
+        if out is None:
+            out = dict(logits=torch.empty((n, Cn), dtype=torch.float32, device=dev),
+                       pred=torch.empty((n,), dtype=torch.int64, device=dev),
+                       score=torch.empty((n,), dtype=torch.float32, device=dev))
+            if want_st:
+                out["St"] = torch.empty((n, D), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        packs = self.model.packs()
+        f2r, f2v = self.index.device_tables(dev)
+        plan = self.plan()
+        need = max((lib.tmr_head_frames_workspace_bytes(fh - fl, hi - lo, self.L, D) for lo, hi, fl, fh in plan),
+                   default=256)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = _ws(need, dev)
+        ws = self._ws
+        mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
+        st = out.get("St")
+        with torch.cuda.device(dev):
+            stream = _stream()
+            for lo, hi, fl, fh in plan:
+                check(lib.tmr_head_frames_fwd(
+                    _ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
+                    C.c_void_p(feats.data_ptr() + fl * F * 4), fh - fl, fl,
+                    _ptr(bank), bank.shape[0], _ptr(f2r), _ptr(f2v), f2r.numel(),
+                    C.c_void_p(starts_dev.data_ptr() + lo * 8), hi - lo, self.seq, self.L, F, D, Cn,
+                    self.pad_mode,
+                    C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
+                    C.c_void_p(out["pred"].data_ptr() + lo * 8),
+                    C.c_void_p(out["score"].data_ptr() + lo * 4),
+                    C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
+                    _ptr(ws), ws.numel(), mode, stream))
+        return out
+
+    def launches_per_run(self) -> int:
+        """Kernel launches of one run() (for bench.py's gpu_launches): per batch
+        1 projection + 1 cell0 + (seq-1) steps + 1 gather + [1 timeconv] + 4 linears + attention +
+        layernorm + fc_h_c + fc_c."""
+        per = 1 + 1 + (self.seq - 1) + 1 + (1 if self.model.time_conv is not None else 0) + 4 + 1 + 1 + 1 + 1
+        return per * len(self.plan())
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: shard by video, no data-path collective
+# ---------------------------------------------------------------------------------------------
+def shard_videos(list_each_length, world_size: int):
+    """Contiguous, frame-balanced partition of the videos: returns [(v_lo, v_hi)] per rank."""
+    lens = np.asarray(list_each_length, dtype=np.int64)
+    V = len(lens)
+    cum = np.concatenate([[0], np.cumsum(lens)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        v = int(np.searchsorted(cum, target, side="left"))
+        v = min(max(v, bounds[-1]), V)
+        bounds.append(v)
+    bounds.append(V)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+class VideoShard:
+    """What one rank holds: the frames/rows of videos [v_lo, v_hi) plus the HALO needed for
+    bit-exact reference windows — the first clips of video v_lo read rows from the tail of the
+    previous videos (TRAIN:298-326 leak).  The halo is expressed as whole extra
+    frames/rows in front of the shard so the same closed-form index applies locally."""
+
+    def __init__(self, list_each_length, seq: int, L: int, v_lo: int, v_hi: int):
+        lens = [int(v) for v in list_each_length]
+        self.seq, self.L, self.v_lo, self.v_hi = seq, L, v_lo, v_hi
+        cum = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        # walk back over previous videos until the keys s-1 .. s-L of the shard's first clips are covered
+        h = v_lo
+        need = L
+        while h > 0 and need > 0:
+            h -= 1
+            need -= lens[h]
+        self.h_lo = h                                   # first halo video
+        self.frame_lo, self.frame_hi = int(cum[h]), int(cum[v_hi])
+        self.own_frame_lo = int(cum[v_lo])
+        self.local_lengths = lens[h:v_hi]
+        rows_before = lambda v: int(sum(max(0, n - seq + 1) for n in lens[:v]))
+        self.row_lo, self.row_hi = rows_before(h), rows_before(v_hi)
+        self.own_row_lo = rows_before(v_lo)
+        self.index = None
+
+    def build_index(self):
+        self.index = LFBIndex.from_lengths(self.local_lengths, self.seq)
+        return self.index
+
+    def own_local_starts(self):
+        """Local (shard-relative) start frame ids of the clips this rank owns (halo clips excluded)."""
+        from .lfb import get_useful_start_idx
+        s = np.asarray(get_useful_start_idx(self.seq, self.local_lengths), dtype=np.int64)
+        return s[s >= self.own_frame_lo - self.frame_lo]
