@@ -50,7 +50,9 @@ _models = {}
 def _model(C=7, seed=1234, use_timeconv=True):
     key = (C, seed, use_timeconv)
     if key not in _models:
-        sd = synth.head_state_dict(num_class=C, seed=seed, with_timeconv=use_timeconv)
+        sd = synth.head_state_dict(num_class=C, seed=seed)          # same weights with or without TimeConv
+        if not use_timeconv:
+            sd = {k: v for k, v in sd.items() if not k.startswith("time_conv.")}
         m = tb.resnet_lstm(num_class=C, use_timeconv=use_timeconv)
         m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         _models[key] = (m.to(_dev()).eval(), sd)
