@@ -374,3 +374,36 @@ def test_linear_generic():
         ref = torch.relu(a.double() @ w.double().T + b.double())
         got = ops.linear(a.to(dev), w.to(dev), b.to(dev), relu=True, math_mode="fp32")
         assert rel_err(got, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 GEMM engine in isolation
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 512), (1, 8, 32), (4, 512, 512), (130, 512, 1024),
+                                   (300, 2048, 2048), (1000, 260, 64), (20000, 512, 512)])
+def test_tf32_gemm_exact_on_small_integers(M, N, K):
+    """Integer-valued operands are exact in TF32 and their dot products exact in fp32, so any
+    layout / swizzle / descriptor / pipeline mistake shows up as a bit mismatch."""
+    _need_mode("tf32")
+    dev = _dev()
+    rng = np.random.default_rng(M + N + K)
+    a = torch.from_numpy(rng.integers(-4, 5, size=(M, K)).astype(np.float32))
+    w = torch.from_numpy(rng.integers(-4, 5, size=(N, K)).astype(np.float32))
+    b = torch.from_numpy(rng.integers(-9, 10, size=(N,)).astype(np.float32))
+    ref = (a.double() @ w.double().T + b.double()).float()
+    got = ops.linear(a.to(dev), w.to(dev), b.to(dev), math_mode="tf32").cpu()
+    bad = (got != ref).nonzero()
+    assert bad.numel() == 0, f"{bad.shape[0]} mismatches, first at {bad[0].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
+
+
+def test_tf32_gemm_random_precision():
+    _need_mode("tf32")
+    dev = _dev()
+    rng = np.random.default_rng(1)
+    a = torch.from_numpy(rng.standard_normal((513, 2048), dtype=np.float32))
+    w = torch.from_numpy(rng.standard_normal((512, 2048), dtype=np.float32))
+    ref = a.double() @ w.double().T
+    got = ops.linear(a.to(dev), w.to(dev), None, math_mode="tf32")
+    assert rel_err(got, ref) < 2e-3
+    got32 = ops.linear(a.to(dev), w.to(dev), None, math_mode="fp32")
+    assert rel_err(got32, ref) < 1e-5

@@ -1,0 +1,301 @@
+// TMR_MATH_TF32 GEMM engine: persistent, warp-specialised tcgen05 kernel.
+//   C[M,N] = A[M,K] . W[N,K]^T   (both K-major fp32 in HBM, consumed as TF32, fp32 accumulate in TMEM)
+// Tile 128 x 256 x 32: TMA (SWIZZLE_128B) stages A (16 KB) + W (32 KB) per k-block through a 4-deep
+// mbarrier ring; one elected thread issues four tcgen05.mma.kind::tf32 (K=8) per stage; accumulators
+// are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (tcgen05.ld).
+// Epilogues: EPI_LINEAR (bias / residual / relu -> out) and EPI_LSTM (gate-interleaved LSTM cell).
+#define TMR_HAVE_UMMA 1
+#include "tmr_internal.h"
+#include "umma_common.cuh"
+
+namespace tmr {
+namespace umma {
+
+int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return set_error(TMR_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    encode = (EncodeFn)fn;
+  }
+  cuuint64_t gdims[3] = {1, 1, 1};
+  cuuint64_t gstr[2] = {0, 0};
+  cuuint32_t gbox[3] = {1, 1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdims, gstr, gbox, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TMR_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu box %u,%u,%u)",
+                     (int)r, rank, (unsigned long long)gdims[0], (unsigned long long)gdims[1],
+                     (unsigned long long)gdims[2], gbox[0], gbox[1], gbox[2]);
+  return TMR_OK;
+}
+
+constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
+constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
+
+struct GemmParams {
+  int64_t M; int N; int K; int k_split;
+  // EPI_LINEAR
+  const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu;
+  // EPI_LSTM (N = 4*512 gate-interleaved columns)
+  const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c;
+};
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
+                 const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int64_t m_tiles = (p.M + BM - 1) / BM;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int k_blocks = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_a2); tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (int)(tile / n_tiles) * BM;
+        const int n0 = (int)(tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (k0 < p.k_split) tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+          else tma_load_2d(sa, &tma_a2, &full_bar[stage], k0 - p.k_split, m0);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)              // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+            mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          mma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&acc_full[acc]);                     // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;                             // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int64_t m = (tile / n_tiles) * BM + q * 32 + lane;
+      const int n0 = (int)(tile % n_tiles) * BN;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      int64_t xr = 0;
+      if (EPI == EPI_LSTM && m < p.M) xr = (p.starts ? p.starts[m] : m * p.seq) + p.t;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + cc, r);
+        tmem_ld_wait();
+        const int n = n0 + cc;
+        if (m < p.M && n < p.N) {
+          if (EPI == EPI_LINEAR) {
+            float* dst = p.out + m * p.ldo + n;
+            const float* res = p.residual ? p.residual + m * p.ldr + n : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n + j < p.N) {                        // N % 4 == 0
+                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                if (p.bias) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (res) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(res + j));
+                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                *reinterpret_cast<float4*>(dst + j) = v;
+              }
+            }
+          } else {
+            // 32 gate columns = 8 hidden units x (i,f,g,o)
+            const float* xrow = p.xp + xr * (4 * kD) + n;
+            const int unit0 = n >> 2;
+            float* crow = p.c + m * kD + unit0;
+            float* hrow = p.h_out + m * kD + unit0;
+            float cn[8], hn[8];
+            const float4 c0 = *reinterpret_cast<const float4*>(crow);
+            const float4 c1 = *reinterpret_cast<const float4*>(crow + 4);
+            const float cold[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 x4 = __ldg(reinterpret_cast<const float4*>(xrow + 4 * u));
+              const float gi = __uint_as_float(r[4 * u + 0]) + x4.x;
+              const float gf = __uint_as_float(r[4 * u + 1]) + x4.y;
+              const float gg = __uint_as_float(r[4 * u + 2]) + x4.z;
+              const float go = __uint_as_float(r[4 * u + 3]) + x4.w;
+              cn[u] = sigmoidf_(gf) * cold[u] + sigmoidf_(gi) * tanhf(gg);
+              hn[u] = sigmoidf_(go) * tanhf(cn[u]);
+            }
+            *reinterpret_cast<float4*>(crow) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(crow + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            *reinterpret_cast<float4*>(hrow) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(hrow + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int EPI>
+static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, const float* w,
+                       int64_t ldw, const GemmParams& p, cudaStream_t st) {
+  CUtensorMap ta, ta2, tb;
+  {
+    const int ka = a2 ? k_split : p.K;
+    uint64_t dims[2] = {(uint64_t)ka, (uint64_t)p.M};
+    uint64_t str[1] = {(uint64_t)lda * 4};
+    uint32_t box[2] = {BK, BM};
+    TMR_TRY(make_tmap(&ta, a, 2, dims, str, box));
+    if (a2) {
+      uint64_t d2[2] = {(uint64_t)(p.K - k_split), (uint64_t)p.M};
+      uint64_t s2[1] = {(uint64_t)lda2 * 4};
+      TMR_TRY(make_tmap(&ta2, a2, 2, d2, s2, box));
+    } else {
+      ta2 = ta;
+    }
+    uint64_t dw[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t sw[1] = {(uint64_t)ldw * 4};
+    uint32_t bw[2] = {BK, BN};
+    TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
+  }
+  TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  umma_gemm_kernel<EPI><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, ta2, tb, p);
+  TMR_LAUNCH_CHECK("umma_gemm_kernel");
+  return TMR_OK;
+}
+
+}  // namespace umma
+
+bool umma_available() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10) ? 1 : 0;
+  }
+  return ok == 1;
+}
+
+int umma_linear(const LinearArgs& g, cudaStream_t st) {
+  TMR_CHECK_ARG(g.K % umma::BK == 0 && g.K > 0, "tf32 linear: K=%d must be a multiple of %d", g.K, umma::BK);
+  TMR_CHECK_ARG(g.N % 4 == 0, "tf32 linear: N=%d must be a multiple of 4", g.N);
+  TMR_CHECK_ARG(g.lda % 4 == 0 && g.ldw % 4 == 0 && g.ldo % 4 == 0, "tf32 linear: leading dims must be multiples of 4");
+  TMR_CHECK_ARG(!g.a2 || (g.k_split % umma::BK == 0 && g.lda2 % 4 == 0), "tf32 linear: bad split");
+  TMR_CHECK_ARG(g.M < (int64_t)INT32_MAX, "tf32 linear: M too large");
+  if (g.M == 0) return TMR_OK;
+  umma::GemmParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.a2 ? g.k_split : g.K;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu;
+  return umma::launch_gemm<umma::EPI_LINEAR>(g.a, g.lda, g.a2, g.lda2, g.k_split, g.w, g.ldw, p, st);
+}
+
+int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t, const float* h_prev,
+                   float* h_out, float* c, int B, cudaStream_t st) {
+  if (B == 0) return TMR_OK;
+  umma::GemmParams p{};
+  p.M = B; p.N = 4 * kD; p.K = kD; p.k_split = kD;
+  p.xp = xp; p.starts = starts; p.seq = seq; p.t = t; p.h_out = h_out; p.c = c;
+  return umma::launch_gemm<umma::EPI_LSTM>(h_prev, kD, nullptr, 0, 0, whh, kD, p, st);
+}
+
+}  // namespace tmr
