@@ -38,7 +38,9 @@ extern "C" {
 
 /* math mode of the GEMM-shaped stages */
 #define TMR_MATH_FP32 0  /* fp32 FFMA on CUDA cores (exact-order reference path)          */
-#define TMR_MATH_TF32 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (default fast) */
+#define TMR_MATH_TF32 1  /* tcgen05.mma kind::tf32 on operands rounded to TF32 (round-to-nearest) by
+                            their producers, fp32 accumulate in TMEM; softmax / LayerNorm / gates /
+                            max / final 512->C FC stay fp32                                     */
 
 /* window padding at the start of the bank / of a video */
 #define TMR_PAD_REPEAT 0 /* reference semantics (TRAIN:298-326): repeat-fill, leaks into previous video */
@@ -94,9 +96,12 @@ int tmr_classifier_pack(const float* w_h, const float* b_h, const float* w_c, co
 
 /* ---- a5: TimeConv.forward (NLB:43-79) ---------------------------------------------------------
  * x (B,L,D) -> out (B,L,D): out[b,k,c] = max(x[k], k>0 ? max(x[k],x[k-1]) : max(x[k],0),
- * conv3, conv5, conv7) with zero "same" padding inside each window.  Any L >= 1. */
+ * conv3, conv5, conv7) with zero "same" padding inside each window.  Any L >= 1.
+ * workspace >= tmr_timeconv_workspace_bytes(B,L,D) (used by TMR_MATH_TF32 for the TF32-rounded copy
+ * of x that feeds the tensor cores; may be NULL in TMR_MATH_FP32). */
+size_t tmr_timeconv_workspace_bytes(int B, int L, int D);
 int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D, float* out,
-                         int math_mode, void* stream);
+                         void* workspace, size_t workspace_bytes, int math_mode, void* stream);
 
 /* ---- a6: NLBlock.forward, eval mode (NLB:25-40) -----------------------------------------------
  * St (B,D), Lt (B,L,D) -> out (B,D).  workspace >= tmr_nlblock_workspace_bytes(B,D). */

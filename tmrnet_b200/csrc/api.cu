@@ -35,7 +35,13 @@ static int check_dims(int D, int F = kF) {
   return TMR_OK;
 }
 static int do_linear(const LinearArgs& g, int mode, cudaStream_t st) {
-  return mode == TMR_MATH_TF32 ? umma_linear(g, st) : simt_linear(g, st);
+  if (mode != TMR_MATH_TF32) return simt_linear(g, st);
+  LinearArgs h = g;
+  if (g.a_scratch) {       // A operand is raw fp32: round it to TF32 (RN) once, then feed the MMA
+    TMR_TRY(launch_round_concat(g.a, g.lda, g.a2, g.lda2, g.k_split, g.K, g.M, g.a_scratch, st));
+    h.a = g.a_scratch; h.lda = g.K; h.a2 = nullptr; h.lda2 = 0; h.k_split = 0;
+  }
+  return umma_linear(h, st);
 }
 
 struct Carver {
@@ -50,66 +56,87 @@ struct Carver {
 static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof(float), 256); }
 
 // ---- stage implementations on carved workspaces -------------------------------------------------
+// In TF32 mode every tensor that feeds a tensor-core GEMM is rounded to TF32 (round-to-nearest) by
+// its producer (epilogue flag) or by a rounding pass into `scratch`; weights come from the rounded
+// mirror of the pack.  fp32 mode touches neither.
+struct NLWs { float* w0; float* w1; float* s; };
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
-                        float* w0, float* w1, int mode, cudaStream_t st) {
+                        NLWs ws, int mode, cudaStream_t st) {
+  const bool tc = mode == TMR_MATH_TF32;
+  const float* w = pk + (tc ? NLBlockPacked::fp32_total : 0);
   LinearArgs g;
   // q = St W1^T + b1                                   (NLB:26-27)
-  g = LinearArgs(); g.a = St; g.lda = kD; g.w = pk + NLBlockPacked::w1_off; g.ldw = kD;
-  g.bias = pk + NLBlockPacked::b1_off; g.out = w0; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  g = LinearArgs(); g.a = St; g.lda = kD; g.w = w + NLBlockPacked::w1_off; g.ldw = kD;
+  g.bias = pk + NLBlockPacked::b1_off; g.out = ws.w0; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  g.a_scratch = tc ? ws.s : nullptr; g.round_out = tc;
   TMR_TRY(do_linear(g, mode, st));
   // u = W2^T q  (phi folded onto the query; b2 cancels in the softmax)     (NLB:28-30)
-  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w2t_off; g.ldw = kD;
-  g.out = w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w2t_off; g.ldw = kD;
+  g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
   TMR_TRY(do_linear(g, mode, st));
   // a = sum_k softmax(scale u.Lt_k) Lt_k                                   (NLB:30-34)
-  TMR_TRY(launch_attention(w1, Lt, B, L, w0, st));
+  TMR_TRY(launch_attention(ws.w1, Lt, B, L, ws.w0, tc, st));
   // v = W3 a + b3  (g folded after the weighted sum: sum_k p_k = 1)         (NLB:33-34)
-  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w3_off; g.ldw = kD;
-  g.bias = pk + NLBlockPacked::b3_off; g.out = w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+  g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w3_off; g.ldw = kD;
+  g.bias = pk + NLBlockPacked::b3_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
   TMR_TRY(do_linear(g, mode, st));
   // r = relu(LayerNorm(v))                                                 (NLB:35-36)
-  TMR_TRY(launch_layernorm_relu(w1, pk + NLBlockPacked::lnw_off, pk + NLBlockPacked::lnb_off, B, w0, st));
+  TMR_TRY(launch_layernorm_relu(ws.w1, pk + NLBlockPacked::lnw_off, pk + NLBlockPacked::lnb_off, B, ws.w0, tc, st));
   // out = St + W4 r + b4   (dropout is the identity in eval)               (NLB:37-40)
-  g = LinearArgs(); g.a = w0; g.lda = kD; g.w = pk + NLBlockPacked::w4_off; g.ldw = kD;
+  g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w4_off; g.ldw = kD;
   g.bias = pk + NLBlockPacked::b4_off; g.residual = St; g.ldr = kD; g.out = out; g.ldo = kD;
   g.M = B; g.N = kD; g.K = kD;
   return do_linear(g, mode, st);
 }
 
+struct LstmWs { float* xp; float* xr; float* h0; float* h1; float* c; };
 static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
-                     int seq, float* out, float* xp_buf, float* h0, float* h1, float* c, int mode,
-                     cudaStream_t st, int64_t frame0 = 0) {
-  float* xp = xp_buf;
+                     int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0) {
+  const bool tc = mode == TMR_MATH_TF32;
+  const float* w = pk + (tc ? LstmPacked::fp32_total : 0);
   // input projection for every row of x once: xp = x Wih'^T + (b_ih + b_hh)', gate-interleaved
   LinearArgs g;
-  g.a = x; g.lda = kF; g.w = pk + LstmPacked::wih_off; g.ldw = kF; g.bias = pk + LstmPacked::bias_off;
-  g.out = xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
+  g.a = x; g.lda = kF; g.w = w + LstmPacked::wih_off; g.ldw = kF; g.bias = pk + LstmPacked::bias_off;
+  g.out = ws.xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
+  g.a_scratch = tc ? ws.xr : nullptr;
   TMR_TRY(do_linear(g, mode, st));
-  xp -= frame0 * 4 * kD;   // rows are addressed by GLOBAL frame id (starts[m] + t) from here on
-  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out`
-  float* hcur = (seq == 1) ? out : h0;
-  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, c, B, st));
+  const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
+  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
+  float* hcur = (seq == 1) ? out : ws.h0;
+  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, ws.c, B, tc && seq > 1, st));
   for (int t = 1; t < seq; ++t) {
-    float* hnext = (t == seq - 1) ? out : (hcur == h0 ? h1 : h0);
-    if (mode == TMR_MATH_TF32)
-      TMR_TRY(umma_lstm_step(pk + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, c, B, st));
+    const bool last = (t == seq - 1);
+    float* hnext = last ? out : (hcur == ws.h0 ? ws.h1 : ws.h0);
+    if (tc)
+      TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, !last, st));
     else
-      TMR_TRY(simt_lstm_step(pk + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, c, B, st));
+      TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, st));
     hcur = hnext;
   }
   return TMR_OK;
 }
 
+struct ClsWs { float* z; float* s; };
 static int classifier_impl(const float* pk, const float* St, const float* y1, int B, int C,
-                           float* logits, int64_t* pred, float* score, float* z, int mode,
+                           float* logits, int64_t* pred, float* score, ClsWs ws, int mode,
                            cudaStream_t st) {
+  const bool tc = mode == TMR_MATH_TF32;
+  const float* w = pk + (tc ? ClassifierPacked::fp32_total : 0);
   LinearArgs g;   // z = relu(fc_h_c([St || y1]))   (TRAIN:249-251, eval: dropout = identity)
-  g.a = St; g.lda = kD; g.a2 = y1; g.lda2 = kD; g.k_split = kD; g.w = pk + ClassifierPacked::wh_off;
-  g.ldw = 2 * kD; g.bias = pk + ClassifierPacked::bh_off; g.out = z; g.ldo = kD; g.M = B; g.N = kD;
-  g.K = 2 * kD; g.relu = 1;
+  g.a = St; g.lda = kD; g.a2 = y1; g.lda2 = kD; g.k_split = kD; g.w = w + ClassifierPacked::wh_off;
+  g.ldw = 2 * kD; g.bias = pk + ClassifierPacked::bh_off; g.out = ws.z; g.ldo = kD; g.M = B; g.N = kD;
+  g.K = 2 * kD; g.relu = 1; g.a_scratch = tc ? ws.s : nullptr;
   TMR_TRY(do_linear(g, mode, st));
-  return launch_fc_argmax(z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
+  // fc_c (512 -> C) + softmax score + argmax stay fp32 on CUDA cores
+  return launch_fc_argmax(ws.z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
                           pred, score, st);
+}
+
+static int timeconv_impl(const float* pk, const float* x, int B, int L, float* out, float* xr, int mode,
+                         cudaStream_t st) {
+  if (mode != TMR_MATH_TF32) return simt_timeconv(pk, x, B, L, out, st);
+  TMR_TRY(launch_round_tf32(x, xr, (int64_t)B * L * kD, st));
+  return umma_timeconv(pk, x, xr, B, L, out, st);
 }
 
 }  // namespace tmr
@@ -212,8 +239,9 @@ int tmr_classifier_pack(const float* w_h, const float* b_h, const float* w_c, co
   return launch_pack_classifier(w_h, b_h, w_c, b_c, C, (float*)packed, (cudaStream_t)stream);
 }
 
+size_t tmr_timeconv_workspace_bytes(int B, int L, int D) { return fbytes((size_t)(B > 0 ? B : 1) * L * D); }
 int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D, float* out,
-                         int math_mode, void* stream) {
+                         void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
   TMR_TRY(check_dims(D));
   TMR_TRY(check_mode(math_mode));
   TMR_CHECK_ARG(B >= 0 && L >= 1, "timeconv: bad B=%d L=%d", B, L);
@@ -221,12 +249,17 @@ int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D
   TMR_CHECK_ARG(packed && x && out, "timeconv: null pointer");
   TMR_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(packed), "timeconv: pointers must be 16-byte aligned");
   TMR_CHECK_ARG(x != out, "timeconv: in-place not supported");
-  if (math_mode == TMR_MATH_TF32)
-    return umma_timeconv((const float*)packed, x, B, L, out, (cudaStream_t)stream);
-  return simt_timeconv((const float*)packed, x, B, L, out, (cudaStream_t)stream);
+  float* xr = nullptr;
+  if (math_mode == TMR_MATH_TF32) {
+    TMR_CHECK_ARG(workspace && aligned16(workspace), "timeconv: TF32 mode needs a workspace");
+    Carver cv(workspace, workspace_bytes);
+    xr = cv.take((size_t)B * L * kD);
+    TMR_CHECK_ARG(xr, "timeconv: workspace too small (%zu < %zu)", workspace_bytes, tmr_timeconv_workspace_bytes(B, L, D));
+  }
+  return timeconv_impl((const float*)packed, x, B, L, out, xr, math_mode, (cudaStream_t)stream);
 }
 
-size_t tmr_nlblock_workspace_bytes(int B, int D) { return 2 * fbytes((size_t)(B > 0 ? B : 1) * D); }
+size_t tmr_nlblock_workspace_bytes(int B, int D) { return 3 * fbytes((size_t)(B > 0 ? B : 1) * D); }
 int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B, int L, int D,
                     float* out, void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
   TMR_TRY(check_dims(D));
@@ -237,14 +270,21 @@ int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B,
   TMR_CHECK_ARG(aligned16(St) && aligned16(Lt) && aligned16(out) && aligned16(workspace) && aligned16(packed),
                 "nlblock: pointers must be 16-byte aligned");
   Carver cv(workspace, workspace_bytes);
-  float* w0 = cv.take((size_t)B * kD);
-  float* w1 = cv.take((size_t)B * kD);
-  TMR_CHECK_ARG(w0 && w1, "nlblock: workspace too small (%zu < %zu)", workspace_bytes, tmr_nlblock_workspace_bytes(B, D));
-  return nlblock_impl((const float*)packed, St, Lt, B, L, out, w0, w1, math_mode, (cudaStream_t)stream);
+  NLWs ws;
+  ws.w0 = cv.take((size_t)B * kD); ws.w1 = cv.take((size_t)B * kD); ws.s = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(ws.w0 && ws.w1 && ws.s, "nlblock: workspace too small (%zu < %zu)", workspace_bytes, tmr_nlblock_workspace_bytes(B, D));
+  return nlblock_impl((const float*)packed, St, Lt, B, L, out, ws, math_mode, (cudaStream_t)stream);
 }
 
 size_t tmr_lstm_workspace_bytes(int64_t n_rows_x, int B, int D) {
-  return fbytes((size_t)(n_rows_x > 0 ? n_rows_x : 1) * 4 * D) + 3 * fbytes((size_t)(B > 0 ? B : 1) * D);
+  const size_t r = (size_t)(n_rows_x > 0 ? n_rows_x : 1);
+  return fbytes(r * 4 * D) + fbytes(r * kF) + 3 * fbytes((size_t)(B > 0 ? B : 1) * D);
+}
+static bool carve_lstm(Carver& cv, int64_t n_rows_x, int B, LstmWs& ws) {
+  ws.xp = cv.take((size_t)n_rows_x * 4 * kD);
+  ws.xr = cv.take((size_t)n_rows_x * kF);
+  ws.h0 = cv.take((size_t)B * kD); ws.h1 = cv.take((size_t)B * kD); ws.c = cv.take((size_t)B * kD);
+  return ws.xp && ws.xr && ws.h0 && ws.h1 && ws.c;
 }
 static int lstm_entry(const void* packed, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
                       int seq, int F, int D, float* out, void* workspace, size_t workspace_bytes,
@@ -256,14 +296,10 @@ static int lstm_entry(const void* packed, const float* x, int64_t n_rows_x, cons
   TMR_CHECK_ARG(packed && x && out && workspace, "lstm: null pointer");
   TMR_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(workspace) && aligned16(packed), "lstm: pointers must be 16-byte aligned");
   Carver cv(workspace, workspace_bytes);
-  float* xp = cv.take((size_t)n_rows_x * 4 * kD);
-  float* h0 = cv.take((size_t)B * kD);
-  float* h1 = cv.take((size_t)B * kD);
-  float* c = cv.take((size_t)B * kD);
-  TMR_CHECK_ARG(xp && h0 && h1 && c, "lstm: workspace too small (%zu < %zu)", workspace_bytes,
+  LstmWs ws;
+  TMR_CHECK_ARG(carve_lstm(cv, n_rows_x, B, ws), "lstm: workspace too small (%zu < %zu)", workspace_bytes,
                 tmr_lstm_workspace_bytes(n_rows_x, B, D));
-  return lstm_impl((const float*)packed, x, n_rows_x, starts, B, seq, out, xp, h0, h1, c, math_mode,
-                   (cudaStream_t)stream);
+  return lstm_impl((const float*)packed, x, n_rows_x, starts, B, seq, out, ws, math_mode, (cudaStream_t)stream);
 }
 int tmr_lstm_last_fwd(const void* packed, const float* x, int B, int seq, int F, int D, float* out,
                       void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
@@ -278,7 +314,11 @@ int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_f
                     math_mode, stream);
 }
 
-size_t tmr_classifier_workspace_bytes(int B, int D) { return fbytes((size_t)(B > 0 ? B : 1) * D); }
+size_t tmr_classifier_workspace_bytes(int B, int D) { return 3 * fbytes((size_t)(B > 0 ? B : 1) * D); }
+static bool carve_cls(Carver& cv, int B, ClsWs& ws) {
+  ws.z = cv.take((size_t)B * kD); ws.s = cv.take((size_t)B * 2 * kD);
+  return ws.z && ws.s;
+}
 int tmr_fc_argmax_fwd(const void* packed, const float* St, const float* y1, int B, int D, int C,
                       float* logits, int64_t* pred, float* score, void* workspace,
                       size_t workspace_bytes, int math_mode, void* stream) {
@@ -290,16 +330,39 @@ int tmr_fc_argmax_fwd(const void* packed, const float* St, const float* y1, int 
   TMR_CHECK_ARG(packed && St && y1 && logits && workspace, "fc_argmax: null pointer");
   TMR_CHECK_ARG(aligned16(St) && aligned16(y1) && aligned16(workspace) && aligned16(packed), "fc_argmax: pointers must be 16-byte aligned");
   Carver cv(workspace, workspace_bytes);
-  float* z = cv.take((size_t)B * kD);
-  TMR_CHECK_ARG(z, "fc_argmax: workspace too small");
-  return classifier_impl((const float*)packed, St, y1, B, C, logits, pred, score, z, math_mode,
+  ClsWs ws;
+  TMR_CHECK_ARG(carve_cls(cv, B, ws), "fc_argmax: workspace too small");
+  return classifier_impl((const float*)packed, St, y1, B, C, logits, pred, score, ws, math_mode,
                          (cudaStream_t)stream);
+}
+
+// shared tail of the two head entry points: St, window -> logits
+struct HeadWs { float* Lt; float* xr; float* St; float* y1; NLWs nl; ClsWs cls; };
+static bool carve_head(Carver& cv, int B, int L, HeadWs& ws) {
+  ws.Lt = cv.take((size_t)B * L * kD); ws.xr = cv.take((size_t)B * L * kD);
+  ws.St = cv.take((size_t)B * kD); ws.y1 = cv.take((size_t)B * kD);
+  ws.nl.w0 = cv.take((size_t)B * kD); ws.nl.w1 = cv.take((size_t)B * kD); ws.nl.s = cv.take((size_t)B * kD);
+  return ws.Lt && ws.xr && ws.St && ws.y1 && ws.nl.w0 && ws.nl.w1 && ws.nl.s && carve_cls(cv, B, ws.cls);
+}
+static size_t head_tail_bytes(size_t b, int L, int D) {
+  return 2 * fbytes(b * L * D) + 2 * fbytes(b * D) + tmr_nlblock_workspace_bytes((int)b, D) +
+         tmr_classifier_workspace_bytes((int)b, D);
+}
+static int head_tail(const void* timeconv_packed, const void* nlblock_packed, const void* classifier_packed,
+                     const float* St, const float* window, int B, int L, int C, float* logits, int64_t* pred,
+                     float* score, HeadWs& ws, int mode, cudaStream_t st) {
+  const float* Lt_in = window;     // NL-only wiring: Lt = long_feature
+  if (timeconv_packed) {
+    TMR_TRY(timeconv_impl((const float*)timeconv_packed, window, B, L, ws.Lt, ws.xr, mode, st));
+    Lt_in = ws.Lt;
+  }
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st));
+  return classifier_impl((const float*)classifier_packed, St, ws.y1, B, C, logits, pred, score, ws.cls, mode, st);
 }
 
 size_t tmr_head_workspace_bytes(int B, int seq, int L, int D) {
   const size_t b = (size_t)(B > 0 ? B : 1);
-  return tmr_lstm_workspace_bytes((int64_t)b * seq, (int)b, D) + fbytes(b * L * D) + 2 * fbytes(b * D) +
-         tmr_nlblock_workspace_bytes((int)b, D) + tmr_classifier_workspace_bytes((int)b, D);
+  return tmr_lstm_workspace_bytes((int64_t)b * seq, (int)b, D) + head_tail_bytes(b, L, D);
 }
 int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const void* nlblock_packed,
                  const void* classifier_packed, const float* x, const float* long_feature, int B,
@@ -315,33 +378,17 @@ int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const voi
   TMR_CHECK_ARG(aligned16(x) && aligned16(long_feature) && aligned16(workspace), "head: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv(workspace, workspace_bytes);
-  float* xp = cv.take((size_t)B * seq * 4 * kD);
-  float* h0 = cv.take((size_t)B * kD);
-  float* h1 = cv.take((size_t)B * kD);
-  float* c = cv.take((size_t)B * kD);
-  float* Lt = cv.take((size_t)B * L * kD);
-  float* St = cv.take((size_t)B * kD);
-  float* y1 = cv.take((size_t)B * kD);
-  float* n0 = cv.take((size_t)B * kD);
-  float* n1 = cv.take((size_t)B * kD);
-  float* z = cv.take((size_t)B * kD);
-  TMR_CHECK_ARG(xp && h0 && h1 && c && Lt && St && y1 && n0 && n1 && z, "head: workspace too small (%zu < %zu)",
-                workspace_bytes, tmr_head_workspace_bytes(B, seq, L, D));
-  TMR_TRY(lstm_impl((const float*)lstm_packed, x, (int64_t)B * seq, nullptr, B, seq, St, xp, h0, h1, c, math_mode, st));
-  const float* Lt_in = long_feature;     // NL-only wiring: Lt = long_feature
-  if (timeconv_packed) {
-    if (math_mode == TMR_MATH_TF32) TMR_TRY(umma_timeconv((const float*)timeconv_packed, long_feature, B, L, Lt, st));
-    else TMR_TRY(simt_timeconv((const float*)timeconv_packed, long_feature, B, L, Lt, st));
-    Lt_in = Lt;
-  }
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, y1, n0, n1, math_mode, st));
-  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, z, math_mode, st);
+  LstmWs lw; HeadWs hw;
+  TMR_CHECK_ARG(carve_lstm(cv, (int64_t)B * seq, B, lw) && carve_head(cv, B, L, hw),
+                "head: workspace too small (%zu < %zu)", workspace_bytes, tmr_head_workspace_bytes(B, seq, L, D));
+  TMR_TRY(lstm_impl((const float*)lstm_packed, x, (int64_t)B * seq, nullptr, B, seq, hw.St, lw, math_mode, st));
+  return head_tail(timeconv_packed, nlblock_packed, classifier_packed, hw.St, long_feature, B, L, C, logits, pred,
+                   score, hw, math_mode, st);
 }
 
 size_t tmr_head_frames_workspace_bytes(int64_t n_feat_frames, int B, int L, int D) {
   const size_t b = (size_t)(B > 0 ? B : 1);
-  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + 2 * fbytes(b * L * D) + 2 * fbytes(b * D) +
-         tmr_nlblock_workspace_bytes((int)b, D) + tmr_classifier_workspace_bytes((int)b, D);
+  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + fbytes(b * L * D) + head_tail_bytes(b, L, D);
 }
 int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
                         const void* nlblock_packed, const void* classifier_packed,
@@ -363,37 +410,23 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
   TMR_CHECK_ARG(aligned16(feats) && aligned16(bank) && aligned16(workspace), "head_frames: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv(workspace, workspace_bytes);
-  float* xp = cv.take((size_t)n_feat_frames * 4 * kD);
-  float* h0 = cv.take((size_t)B * kD);
-  float* h1 = cv.take((size_t)B * kD);
-  float* c = cv.take((size_t)B * kD);
-  float* win = cv.take((size_t)B * L * kD);
-  float* Lt = cv.take((size_t)B * L * kD);
-  float* St = cv.take((size_t)B * kD);
-  float* y1 = cv.take((size_t)B * kD);
-  float* n0 = cv.take((size_t)B * kD);
-  float* n1 = cv.take((size_t)B * kD);
-  float* z = cv.take((size_t)B * kD);
-  TMR_CHECK_ARG(xp && h0 && h1 && c && win && Lt && St && y1 && n0 && n1 && z,
-                "head_frames: workspace too small (%zu < %zu)", workspace_bytes,
+  LstmWs lw; HeadWs hw;
+  float* win = nullptr;
+  const bool ok = carve_lstm(cv, n_feat_frames, B, lw) && (win = cv.take((size_t)B * L * kD)) && carve_head(cv, B, L, hw);
+  TMR_CHECK_ARG(ok, "head_frames: workspace too small (%zu < %zu)", workspace_bytes,
                 tmr_head_frames_workspace_bytes(n_feat_frames, B, L, D));
-  if (St_out) St = St_out;
-  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, xp, h0, h1, c,
-                    math_mode, st, frame0));
+  float* St = St_out ? St_out : hw.St;
+  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, math_mode, st, frame0));
   TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, starts, B, L, pad_mode, win,
                         nullptr, st));
-  const float* Lt_in = win;
-  if (timeconv_packed) {
-    if (math_mode == TMR_MATH_TF32) TMR_TRY(umma_timeconv((const float*)timeconv_packed, win, B, L, Lt, st));
-    else TMR_TRY(simt_timeconv((const float*)timeconv_packed, win, B, L, Lt, st));
-    Lt_in = Lt;
-  }
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, y1, n0, n1, math_mode, st));
-  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, z, math_mode, st);
+  return head_tail(timeconv_packed, nlblock_packed, classifier_packed, St, win, B, L, C, logits, pred, score, hw,
+                   math_mode, st);
 }
 
 int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,
                    float* out, int relu, int math_mode, void* stream) {
+  // Exposed for tests of the GEMM engines: in TF32 mode the operands are consumed as given (the
+  // tensor core ignores the low 13 mantissa bits); callers wanting RN semantics pre-round them.
   TMR_TRY(check_mode(math_mode));
   TMR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "linear: bad sizes");
   if (M == 0) return TMR_OK;

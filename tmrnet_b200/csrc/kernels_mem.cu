@@ -90,7 +90,7 @@ int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const i
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
 __global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* __restrict__ starts,
-                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total) {
+                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total, int round_h) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (clip, unit)
   if (idx >= total) return;
   const int64_t m = idx / kD;
@@ -99,14 +99,15 @@ __global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* _
   const float4 p = __ldg(reinterpret_cast<const float4*>(xp + xr * (4 * kD) + unit * 4));
   const float cn = sigmoidf_(p.x) * tanhf(p.z);     // f * 0 drops out
   c[idx] = cn;
-  h[idx] = sigmoidf_(p.w) * tanhf(cn);
+  const float hn = sigmoidf_(p.w) * tanhf(cn);
+  h[idx] = round_h ? round_tf32(hn) : hn;
 }
 
 int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      cudaStream_t st) {
+                      int round_h, cudaStream_t st) {
   const int64_t total = (int64_t)B * kD;
   if (total == 0) return TMR_OK;
-  lstm_cell0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xp, starts, seq, h, c, total);
+  lstm_cell0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xp, starts, seq, h, c, total, round_h);
   TMR_LAUNCH_CHECK("lstm_cell0_kernel");
   return TMR_OK;
 }
@@ -122,7 +123,7 @@ constexpr int KB = 6;
 
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
-                 float* __restrict__ a) {
+                 float* __restrict__ a, int round_out) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -186,14 +187,17 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
   const float inv = 1.f / run_sum;
   float4* dst = reinterpret_cast<float4*>(a + (int64_t)b * kD);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    dst[i * 32 + lane] = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+  for (int i = 0; i < 4; ++i) {
+    float4 o = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    dst[i * 32 + lane] = o;
+  }
 }
 
-int launch_attention(const float* u, const float* Lt, int B, int L, float* a, cudaStream_t st) {
+int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   const float scale = (float)0.044194173824159216;   // (1/512)**0.5 as python computes it (NLB:31)
-  attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a);
+  attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a, round_out);
   TMR_LAUNCH_CHECK("attention_kernel");
   return TMR_OK;
 }
@@ -203,7 +207,7 @@ int launch_attention(const float* u, const float* Lt, int B, int L, float* a, cu
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
-                      const float* __restrict__ bsh, int B, float* __restrict__ y) {
+                      const float* __restrict__ bsh, int B, float* __restrict__ y, int round_out) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -230,13 +234,15 @@ layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
     o.y = fmaxf((x[i].y - mean) * rstd * g.y + be.y, 0.f);
     o.z = fmaxf((x[i].z - mean) * rstd * g.z + be.z, 0.f);
     o.w = fmaxf((x[i].w - mean) * rstd * g.w + be.w, 0.f);
+    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
     dst[i * 32 + lane] = o;
   }
 }
 
-int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y, cudaStream_t st) {
+int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y, int round_out,
+                          cudaStream_t st) {
   if (B == 0) return TMR_OK;
-  layernorm_relu_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, w, b, B, y);
+  layernorm_relu_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, w, b, B, y, round_out);
   TMR_LAUNCH_CHECK("layernorm_relu_kernel");
   return TMR_OK;
 }
@@ -327,6 +333,44 @@ __global__ void interleave_bias_kernel(const float* __restrict__ bih, const floa
   dst[r] = bih[gate * kD + unit] + bhh[gate * kD + unit];
 }
 
+__global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(src + i);
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    dst[i] = v;
+  }
+}
+int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return TMR_OK;
+  TMR_CHECK_ARG(n % 4 == 0, "round_tf32: n must be a multiple of 4");
+  int64_t b = (n / 4 + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  round_tf32_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n / 4);
+  TMR_LAUNCH_CHECK("round_tf32_kernel");
+  return TMR_OK;
+}
+__global__ void round_concat_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ a2, int64_t lda2,
+                                    int k_split, int K, int64_t M, float* __restrict__ dst) {
+  const int64_t n4 = M * (K / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / (K / 4);
+    const int k = (int)(i - m * (K / 4)) * 4;
+    const float* src = (k < k_split) ? a + m * lda + k : a2 + m * lda2 + (k - k_split);
+    float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    *reinterpret_cast<float4*>(dst + m * K + k) = v;
+  }
+}
+int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
+                        int64_t M, float* dst, cudaStream_t st) {
+  if (M == 0) return TMR_OK;
+  int64_t b = (M * (K / 4) + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  round_concat_kernel<<<(unsigned)b, 256, 0, st>>>(a, lda, a2, lda2, a2 ? k_split : K, K, M, dst);
+  TMR_LAUNCH_CHECK("round_concat_kernel");
+  return TMR_OK;
+}
+
 static inline unsigned blocks_for(int64_t n) { int64_t b = (n + 255) / 256; return (unsigned)(b > 4096 ? 4096 : b); }
 
 int launch_pack_timeconv(const float* w3, const float* b3, const float* w5, const float* b5,
@@ -338,7 +382,7 @@ int launch_pack_timeconv(const float* w3, const float* b3, const float* w5, cons
   copy_kernel<<<2, 256, 0, st>>>(b5, packed + TimeConvPacked::b5_off, kD);
   copy_kernel<<<2, 256, 0, st>>>(b7, packed + TimeConvPacked::b7_off, kD);
   TMR_LAUNCH_CHECK("pack_timeconv");
-  return TMR_OK;
+  return launch_round_tf32(packed, packed + TimeConvPacked::fp32_total, TimeConvPacked::fp32_total, st);
 }
 
 int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const float* w3,
@@ -355,7 +399,7 @@ int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const
   copy_kernel<<<2, 256, 0, st>>>(lnw, packed + NLBlockPacked::lnw_off, kD);
   copy_kernel<<<2, 256, 0, st>>>(lnb, packed + NLBlockPacked::lnb_off, kD);
   TMR_LAUNCH_CHECK("pack_nlblock");
-  return TMR_OK;
+  return launch_round_tf32(packed, packed + NLBlockPacked::fp32_total, NLBlockPacked::fp32_total, st);
 }
 
 int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const float* bhh,
@@ -364,20 +408,20 @@ int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const
   interleave_gates_kernel<<<blocks_for((int64_t)4 * kD * kD), 256, 0, st>>>(whh, packed + LstmPacked::whh_off, kD);
   interleave_bias_kernel<<<(4 * kD + 255) / 256, 256, 0, st>>>(bih, bhh, packed + LstmPacked::bias_off);
   TMR_LAUNCH_CHECK("pack_lstm");
-  return TMR_OK;
+  return launch_round_tf32(packed, packed + LstmPacked::fp32_total, LstmPacked::fp32_total, st);
 }
 
 int launch_pack_classifier(const float* wh, const float* bh, const float* wc, const float* bc, int C,
                            float* packed, cudaStream_t st) {
   TMR_CUDA(cudaMemsetAsync(packed + ClassifierPacked::wc_off, 0,
-                           sizeof(float) * (ClassifierPacked::total - ClassifierPacked::wc_off), st));
+                           sizeof(float) * (ClassifierPacked::fp32_total - ClassifierPacked::wc_off), st));
   const int64_t nh = (int64_t)kD * 2 * kD;
   copy_kernel<<<blocks_for(nh), 256, 0, st>>>(wh, packed + ClassifierPacked::wh_off, nh);
   copy_kernel<<<2, 256, 0, st>>>(bh, packed + ClassifierPacked::bh_off, kD);
   copy_kernel<<<blocks_for((int64_t)C * kD), 256, 0, st>>>(wc, packed + ClassifierPacked::wc_off, (int64_t)C * kD);
   copy_kernel<<<1, 256, 0, st>>>(bc, packed + ClassifierPacked::bc_off, C);
   TMR_LAUNCH_CHECK("pack_classifier");
-  return TMR_OK;
+  return launch_round_tf32(packed, packed + ClassifierPacked::fp32_total, ClassifierPacked::fp32_total, st);
 }
 
 }  // namespace tmr

@@ -45,7 +45,18 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int kD = 512;   // bank row width / LSTM hidden (reference hard-codes 512, NLB:26,17)
 constexpr int kF = 2048;  // backbone feature width
 
+// Round-to-nearest fp32 -> TF32 (10-bit mantissa).  tcgen05.mma.kind::tf32 ignores the low 13
+// mantissa bits of its operands (truncation, a systematic shrink of every product); operands of
+// the tensor-core path are therefore rounded once, by their producer, with cvt.rna.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 // ---- packed weight layouts (floats) ---------------------------------------------------------
+// Every pack holds the fp32 layout below followed by a mirror of it rounded to TF32 (same offsets
+// + fp32_total) that the tcgen05 path reads.
 // TimeConv: Wp_K[o][tap][c] = w_K[o][c][tap]  (K-major rows of length K*D), then biases.
 struct TimeConvPacked {
   static constexpr size_t w3_off = 0;
@@ -54,7 +65,8 @@ struct TimeConvPacked {
   static constexpr size_t b3_off = w7_off + (size_t)kD * 7 * kD;
   static constexpr size_t b5_off = b3_off + kD;
   static constexpr size_t b7_off = b5_off + kD;
-  static constexpr size_t total = b7_off + kD;
+  static constexpr size_t fp32_total = b7_off + kD;
+  static constexpr size_t total = 2 * fp32_total;   // + TF32-rounded (RN) mirror for the tensor-core path
 };
 // NLBlock: W1[n][k], W2T[n][k] = W2[k][n], W3[n][k], W4[n][k], b1, b3, b4, ln_w, ln_b.
 // (b2 cancels inside the softmax over L: q.(W2 l_k + b2) = (W2^T q).l_k + const.)
@@ -68,7 +80,8 @@ struct NLBlockPacked {
   static constexpr size_t b4_off = b3_off + kD;
   static constexpr size_t lnw_off = b4_off + kD;
   static constexpr size_t lnb_off = lnw_off + kD;
-  static constexpr size_t total = lnb_off + kD;
+  static constexpr size_t fp32_total = lnb_off + kD;
+  static constexpr size_t total = 2 * fp32_total;
 };
 // LSTM: gate-interleaved rows r' = unit*4 + gate (gate order i,f,g,o) so one float4 of the
 // projected row holds the four gates of a hidden unit.  Wih'[4D][F], Whh'[4D][D], bias'[4D] = bih+bhh.
@@ -76,7 +89,8 @@ struct LstmPacked {
   static constexpr size_t wih_off = 0;
   static constexpr size_t whh_off = wih_off + (size_t)4 * kD * kF;
   static constexpr size_t bias_off = whh_off + (size_t)4 * kD * kD;
-  static constexpr size_t total = bias_off + 4 * kD;
+  static constexpr size_t fp32_total = bias_off + 4 * kD;
+  static constexpr size_t total = 2 * fp32_total;
 };
 // Classifier: Wh[D][2D], bh[D], Wc[C][D], bc[C] (C padded to 32 rows for alignment).
 struct ClassifierPacked {
@@ -85,7 +99,8 @@ struct ClassifierPacked {
   static constexpr size_t bh_off = wh_off + (size_t)kD * 2 * kD;
   static constexpr size_t wc_off = bh_off + kD;
   static constexpr size_t bc_off = wc_off + (size_t)kMaxC * kD;
-  static constexpr size_t total = bc_off + kMaxC;
+  static constexpr size_t fp32_total = bc_off + kMaxC;
+  static constexpr size_t total = 2 * fp32_total;
 };
 
 }  // namespace tmr

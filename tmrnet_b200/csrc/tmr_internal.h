@@ -14,6 +14,8 @@ struct LinearArgs {
   const float* residual = nullptr; int64_t ldr = 0;
   float* out = nullptr; int64_t ldo = 0;
   int64_t M = 0; int N = 0; int K = 0; int relu = 0;
+  int round_out = 0;            // round outputs to TF32 (they only feed another tensor-core GEMM)
+  float* a_scratch = nullptr;   // TF32 path: [M,K] buffer; A (|a2) is RN-rounded into it first
 };
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) ----
@@ -26,9 +28,10 @@ int simt_lstm_step(const float* whh, const float* xp, const int64_t* starts, int
 
 // ---- tcgen05 TF32 path (umma_*.cu); same contracts ----
 int umma_linear(const LinearArgs& g, cudaStream_t st);
-int umma_timeconv(const float* packed, const float* x, int B, int L, float* out, cudaStream_t st);
+// x_r = x rounded to TF32 (MMA operand); x = exact values for the identity / pool branches
+int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, int L, float* out, cudaStream_t st);
 int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
-                   const float* h_prev, float* h_out, float* c, int B, cudaStream_t st);
+                   const float* h_prev, float* h_out, float* c, int B, int round_h, cudaStream_t st);
 bool umma_available();
 
 // ---- memory-bound kernels (kernels_mem.cu) ----
@@ -37,12 +40,17 @@ int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const i
                   int32_t* rows_out, cudaStream_t st);
 // step 0 of the LSTM from zero state: c = sig(i)*tanh(g), h = sig(o)*tanh(c) from xp rows.
 int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      cudaStream_t st);
+                      int round_h, cudaStream_t st);
 // a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]
-int launch_attention(const float* u, const float* Lt, int B, int L, float* a, cudaStream_t st);
+int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st);
 // y = relu(layer_norm(v) * w + b) over rows of 512
 int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y,
-                          cudaStream_t st);
+                          int round_out, cudaStream_t st);
+// dst[n] = round_tf32(src[n])
+int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st);
+// dst[M,K] = round_tf32([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))
+int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
+                        int64_t M, float* dst, cudaStream_t st);
 // logits = z . Wc^T + bc ; score = max softmax prob ; pred = first argmax
 int launch_fc_argmax(const float* z, const float* wc, const float* bc, int B, int C, float* logits,
                      int64_t* pred, float* score, cudaStream_t st);

@@ -56,9 +56,9 @@ enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
   // EPI_LINEAR
-  const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu;
+  const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
-  const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c;
+  const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
 };
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
@@ -181,6 +181,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                 }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                 *reinterpret_cast<float4*>(dst + j) = v;
               }
             }
@@ -203,6 +204,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               const float go = __uint_as_float(r[4 * u + 3]) + x4.w;
               cn[u] = sigmoidf_(gf) * cold[u] + sigmoidf_(gi) * tanhf(gg);
               hn[u] = sigmoidf_(go) * tanhf(cn[u]);
+              if (p.round_h) hn[u] = round_tf32(hn[u]);   // only feeds the next step's MMA
             }
             *reinterpret_cast<float4*>(crow) = make_float4(cn[0], cn[1], cn[2], cn[3]);
             *reinterpret_cast<float4*>(crow + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
@@ -285,14 +287,15 @@ int umma_linear(const LinearArgs& g, cudaStream_t st) {
   if (g.M == 0) return TMR_OK;
   umma::GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.a2 ? g.k_split : g.K;
-  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu; p.round_out = g.round_out;
   return umma::launch_gemm<umma::EPI_LINEAR>(g.a, g.lda, g.a2, g.lda2, g.k_split, g.w, g.ldw, p, st);
 }
 
 int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t, const float* h_prev,
-                   float* h_out, float* c, int B, cudaStream_t st) {
+                   float* h_out, float* c, int B, int round_h, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   umma::GemmParams p{};
+  p.round_h = round_h;
   p.M = B; p.N = 4 * kD; p.K = kD; p.k_split = kD;
   p.xp = xp; p.starts = starts; p.seq = seq; p.t = t; p.h_out = h_out; p.c = c;
   return umma::launch_gemm<umma::EPI_LSTM>(h_prev, kD, nullptr, 0, 0, whh, kD, p, st);

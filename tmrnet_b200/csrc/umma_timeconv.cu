@@ -168,7 +168,7 @@ umma_timeconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
 }  // namespace umma
 
-int umma_timeconv(const float* packed, const float* x, int B, int L, float* out, cudaStream_t st) {
+int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, int L, float* out, cudaStream_t st) {
   using namespace umma;
   if (B == 0) return TMR_OK;
   TimeConvParams p{};
@@ -185,8 +185,9 @@ int umma_timeconv(const float* packed, const float* x, int B, int L, float* out,
     uint64_t dims[3] = {(uint64_t)kD, (uint64_t)L, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)kD * 4, (uint64_t)L * kD * 4};
     uint32_t box[3] = {TC_BK, (uint32_t)p.box_l, (uint32_t)p.nb};
-    TMR_TRY(make_tmap(&tx, x, 3, dims, str, box));
-    const float* w[3] = {packed + TimeConvPacked::w3_off, packed + TimeConvPacked::w5_off, packed + TimeConvPacked::w7_off};
+    TMR_TRY(make_tmap(&tx, x_r, 3, dims, str, box));
+    const float* pr = packed + TimeConvPacked::fp32_total;      // TF32-rounded weight mirror
+    const float* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
     CUtensorMap* tw[3] = {&tw3, &tw5, &tw7};
     for (int i = 0; i < 3; ++i) {
       const int taps = 3 + 2 * i;

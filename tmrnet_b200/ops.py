@@ -143,8 +143,12 @@ def timeconv_max(packed, x, math_mode=None):
         raise ValueError(f"TimeConv input must be (B,L,{D}), got {tuple(x.shape)}")
     B, L, _ = x.shape
     out = torch.empty_like(x)
+    lib = _lib.load()
+    mode = _mode(math_mode)
+    ws = _ws(lib.tmr_timeconv_workspace_bytes(B, L, D), x.device) if mode == TMR_MATH_TF32 else None
     with torch.cuda.device(x.device):
-        check(_lib.load().tmr_timeconv_max_fwd(_ptr(packed), _ptr(x), B, L, D, _ptr(out), _mode(math_mode), _stream()))
+        check(lib.tmr_timeconv_max_fwd(_ptr(packed), _ptr(x), B, L, D, _ptr(out), _ptr(ws),
+                                       ws.numel() if ws is not None else 0, mode, _stream()))
     return out
 
 
