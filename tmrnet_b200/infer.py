@@ -92,10 +92,14 @@ class BankInference:
         return out
 
     def launches_per_run(self) -> int:
-        """Kernel launches of one run() (for bench.py's gpu_launches): per batch
-        1 projection + 1 cell0 + (seq-1) steps + 1 gather + [1 timeconv] + 4 linears + attention +
-        layernorm + fc_h_c + fc_c."""
-        per = 1 + 1 + (self.seq - 1) + 1 + (1 if self.model.time_conv is not None else 0) + 4 + 1 + 1 + 1 + 1
+        """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
+        projection + cell0 + (seq-1) steps | gather | timeconv | q, u, attention, v, layernorm, out |
+        fc_h_c, fc_c; TF32 mode adds the four TF32 rounding passes (features, window, St, [St|y1])."""
+        mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
+        tc = 1 if self.model.time_conv is not None else 0
+        per = (1 + 1 + (self.seq - 1)) + 1 + tc + 6 + 2
+        if mode == ops.TMR_MATH_TF32:
+            per += 3 + tc
         return per * len(self.plan())
 
 

@@ -14,7 +14,7 @@ from ._lib import TMR_MATH_FP32, TMR_MATH_TF32, TMR_PAD_REPEAT, TMR_PAD_ZERO, ch
 D = 512
 F = 2048
 
-_default_math = [TMR_MATH_FP32]
+_default_math = [TMR_MATH_TF32]      # tensor cores by default; 'fp32' = CUDA-core exact-order mode
 _MATH_NAMES = {"fp32": TMR_MATH_FP32, "tf32": TMR_MATH_TF32}
 
 
