@@ -160,6 +160,33 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
                         float* St_out, void* workspace, size_t workspace_bytes, int math_mode,
                         void* stream);
 
+/* ---- bank-level head with the TimeConv deduplicated per bank ROW (TMR_MATH_TF32 only) ----------
+ * Same contract and results (up to fp32 summation order) as tmr_head_frames_fwd, for clip batches
+ * sorted by start frame.  A clip is REGULAR when its window is a contiguous run of bank rows, i.e.
+ * it lies at least L clips into its video (starts[b] - frame2vstart[starts[b]] >= L); then slot k of
+ * its window is bank row frame2row[starts[b]] - 1 - k and the TimeConv output of that slot depends
+ * only on the row and on the slot's distance to the window edges, so the convolutions run once per
+ * row (7.9 MFLOP/row instead of 236 MFLOP/clip) into PB[row][7 variants][D].  IRREGULAR clips (the
+ * first L of every video, where the reference window repeat-fills / leaks into the previous video)
+ * go through the per-clip gather + TimeConv.  The caller supplies the split, computed once per batch
+ * plan on the host (tmrnet_b200.infer.BankInference does):
+ *   src_idx          device int32[B]: regular clip -> (frame2row[starts[b]] - 1) - pb_row_base (>= L-1);
+ *                    irregular clip -> -1 - j, j its position in irregular_starts;
+ *   irregular_starts device int64[n_irregular] global start frames of the irregular clips;
+ *   pb_row_base, pb_rows  bank row range covering slot L-1 of the first regular clip .. slot 0 of the
+ *                    last one (pb_rows = 0 when the batch has no regular clip).  Needs L >= 6. */
+size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
+                                             int L, int D);
+int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
+                              const void* nlblock_packed, const void* classifier_packed,
+                              const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                              int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
+                              int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
+                              const int64_t* irregular_starts, int n_irregular, int64_t pb_row_base,
+                              int64_t pb_rows, int seq, int L, int F, int D, int C, int pad_mode,
+                              float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- generic fp32 linear used by the stages above (exposed for tests) --------------------------
  * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N. */
 int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,

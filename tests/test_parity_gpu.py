@@ -429,7 +429,7 @@ def test_bank_inference_matches_oracle_and_module_path(mode):
     lengths, seq, L, feats, bank = _small_job()
     m = _model(7)
     idx = tb.LFBIndex.from_lengths(lengths, seq)
-    eng = BankInference(m, idx, seq, L, batch_clips=100, math_mode=mode)
+    eng = BankInference(m, idx, seq, L, batch_clips=100, math_mode=mode, dedup=False)
     out = eng.run(torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev), want_st=True)
     starts = synth.clip_starts(lengths, seq)
     x = np.stack([feats[s:s + seq] for s in starts])
@@ -454,16 +454,49 @@ def test_video_sharded_inference_is_bit_identical_to_unsharded(mode):
     dev = _dev()
     lengths, seq, L, feats, bank = _small_job(seed=8)
     m = _model(7)
-    full = BankInference(m, tb.LFBIndex.from_lengths(lengths, seq), seq, L, batch_clips=128, math_mode=mode)
+    full = BankInference(m, tb.LFBIndex.from_lengths(lengths, seq), seq, L, batch_clips=128, math_mode=mode, dedup=False)
     ref = full.run(torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev))
     for world in (2, 3):
         parts = []
         for lo, hi in shard_videos(lengths, world):
             sh = VideoShard(lengths, seq, L, lo, hi)
             idx = sh.build_index()
-            eng = BankInference(m, idx, seq, L, batch_clips=128, math_mode=mode, starts=sh.own_local_starts())
+            eng = BankInference(m, idx, seq, L, batch_clips=128, math_mode=mode, starts=sh.own_local_starts(), dedup=False)
             f = torch.from_numpy(feats[sh.frame_lo:sh.frame_hi]).to(dev)
             b = torch.from_numpy(bank[sh.row_lo:sh.row_hi]).to(dev)
             parts.append(eng.run(f, b))
         for key in ("logits", "pred", "score"):
             assert torch.equal(torch.cat([p[key] for p in parts]), ref[key]), (world, key)
+
+
+@pytest.mark.parametrize("L", [6, 7, 10, 30, 60])
+@pytest.mark.parametrize("pad_mode", ["repeat", "zero"])
+def test_bank_level_timeconv_dedup_matches_per_clip_path(L, pad_mode):
+    """tmr_head_frames_dedup_fwd (convolutions once per bank row, 7 edge variants) against the
+    per-clip path on the same clips, and against the oracle."""
+    _need_mode("tf32")
+    from tmrnet_b200.infer import BankInference
+    dev = _dev()
+    lengths, seq, _, feats, bank = _small_job(seed=11)
+    lengths = lengths + [400]
+    feats = synth.features(sum(lengths), seed=11)
+    bank = synth.bank(len(synth.clip_starts(lengths, seq)), seed=11)
+    m = _model(7)
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    f, b = torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)
+    ref = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=False, pad_mode=pad_mode).run(f, b)
+    eng = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=True, pad_mode=pad_mode)
+    assert eng._use_dedup()
+    n_irr = sum(len(d["irr"]) for d in eng.dedup_plan())
+    assert 0 < n_irr < len(idx)
+    got = eng.run(f, b)
+    assert rel_err(got["logits"], ref["logits"]) < 2e-5
+    if pad_mode == "repeat":
+        starts = synth.clip_starts(lengths, seq)
+        x = np.stack([feats[s:s + seq] for s in starts])
+        lf = orc.get_long_feature(starts, orc.build_start_dict(starts.tolist()), bank, L)
+        ref_logits = orc.head(x, lf, _sd(7))[0]
+        assert rel_err(got["logits"], ref_logits) < TOL["tf32"]
+        top2 = torch.topk(ref_logits, 2, dim=1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL["tf32"] * float(ref_logits.abs().max())
+        assert torch.equal(got["pred"].cpu()[safe], ref_logits.argmax(1)[safe])

@@ -60,8 +60,9 @@ static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof
 // its producer (epilogue flag) or by a rounding pass into `scratch`; weights come from the rounded
 // mirror of the pack.  fp32 mode touches neither.
 struct NLWs { float* w0; float* w1; float* s; };
+struct PbSrc { const float* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
-                        NLWs ws, int mode, cudaStream_t st) {
+                        NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr) {
   const bool tc = mode == TMR_MATH_TF32;
   const float* w = pk + (tc ? NLBlockPacked::fp32_total : 0);
   LinearArgs g;
@@ -75,7 +76,8 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
   g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
   TMR_TRY(do_linear(g, mode, st));
   // a = sum_k softmax(scale u.Lt_k) Lt_k                                   (NLB:30-34)
-  TMR_TRY(launch_attention(ws.w1, Lt, B, L, ws.w0, tc, st));
+  if (pbs) TMR_TRY(launch_attention_pb(ws.w1, pbs->pb, pbs->lt_irr, pbs->src, B, L, ws.w0, tc, st));
+  else TMR_TRY(launch_attention(ws.w1, Lt, B, L, ws.w0, tc, st));
   // v = W3 a + b3  (g folded after the weighted sum: sum_k p_k = 1)         (NLB:33-34)
   g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w3_off; g.ldw = kD;
   g.bias = pk + NLBlockPacked::b3_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
@@ -421,6 +423,76 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
                         nullptr, st));
   return head_tail(timeconv_packed, nlblock_packed, classifier_packed, St, win, B, L, C, logits, pred, score, hw,
                    math_mode, st);
+}
+
+size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
+                                             int L, int D) {
+  const size_t b = (size_t)(B > 0 ? B : 1);
+  const size_t ni = (size_t)(n_irregular > 0 ? n_irregular : 1);
+  const size_t pr = (size_t)(pb_rows > 0 ? pb_rows : 1);
+  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + fbytes((pr + 8) * D) + fbytes(pr * 7 * D) +
+         3 * fbytes(ni * L * D) + 2 * fbytes(b * D) + tmr_nlblock_workspace_bytes((int)b, D) +
+         tmr_classifier_workspace_bytes((int)b, D);
+}
+int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
+                              const void* nlblock_packed, const void* classifier_packed,
+                              const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                              int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
+                              int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
+                              const int64_t* irregular_starts, int n_irregular, int64_t pb_row_base,
+                              int64_t pb_rows, int seq, int L, int F, int D, int C, int pad_mode,
+                              float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  const int mode = TMR_MATH_TF32;
+  TMR_TRY(check_dims(D, F));
+  TMR_TRY(check_mode(mode));
+  TMR_CHECK_ARG(B >= 0 && seq >= 1 && n_feat_frames >= 0 && frame0 >= 0 && n_irregular >= 0 && pb_rows >= 0,
+                "head_frames_dedup: bad sizes");
+  TMR_CHECK_ARG(L >= 6, "head_frames_dedup: L=%d < 6 has no interior slots; use tmr_head_frames_fwd", L);
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "head_frames_dedup: C=%d out of range", C);
+  TMR_CHECK_ARG(pad_mode == TMR_PAD_REPEAT || pad_mode == TMR_PAD_ZERO, "head_frames_dedup: bad pad_mode");
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(lstm_packed && timeconv_packed && nlblock_packed && classifier_packed && feats && bank && frame2row &&
+                starts && src_idx && logits && workspace, "head_frames_dedup: null pointer");
+  TMR_CHECK_ARG(n_irregular == 0 || irregular_starts, "head_frames_dedup: irregular_starts is null");
+  TMR_CHECK_ARG(pad_mode != TMR_PAD_ZERO || frame2vstart, "head_frames_dedup: TMR_PAD_ZERO needs frame2vstart");
+  TMR_CHECK_ARG(pb_row_base >= 0 && pb_row_base + pb_rows <= n_rows, "head_frames_dedup: PB row range outside the bank");
+  TMR_CHECK_ARG(aligned16(feats) && aligned16(bank) && aligned16(workspace), "head_frames_dedup: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace, workspace_bytes);
+  LstmWs lw;
+  bool ok = carve_lstm(cv, n_feat_frames, B, lw);
+  const int64_t r_lo = pb_row_base - 3 > 0 ? pb_row_base - 3 : 0;                       // rounded-bank slice
+  const int64_t r_hi = pb_row_base + pb_rows + 4 < n_rows ? pb_row_base + pb_rows + 4 : n_rows;
+  float* bank_r = cv.take((size_t)(pb_rows + 8) * kD);
+  float* pb = cv.take((size_t)(pb_rows > 0 ? pb_rows : 1) * 7 * kD);
+  const size_t ni = (size_t)(n_irregular > 0 ? n_irregular : 1);
+  float* win_i = cv.take(ni * L * kD);
+  float* lt_i = cv.take(ni * L * kD);
+  float* xr_i = cv.take(ni * L * kD);
+  float* St_ws = cv.take((size_t)B * kD);
+  float* y1 = cv.take((size_t)B * kD);
+  NLWs nl; nl.w0 = cv.take((size_t)B * kD); nl.w1 = cv.take((size_t)B * kD); nl.s = cv.take((size_t)B * kD);
+  ClsWs cls;
+  ok = ok && bank_r && pb && win_i && lt_i && xr_i && St_ws && y1 && nl.w0 && nl.w1 && nl.s && carve_cls(cv, B, cls);
+  TMR_CHECK_ARG(ok, "head_frames_dedup: workspace too small (%zu < %zu)", workspace_bytes,
+                tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, pb_rows, L, D));
+  float* St = St_out ? St_out : St_ws;
+  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0));
+  if (pb_rows > 0) {
+    // TF32 (RN) copy of the bank rows the convolutions touch, then one pass of tap products per row
+    TMR_TRY(launch_round_tf32(bank + r_lo * kD, bank_r, (r_hi - r_lo) * kD, st));
+    TMR_TRY(umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, pb_row_base,
+                          pb_rows, pb, st));
+  }
+  if (n_irregular > 0) {      // clips whose window crosses a video start: per-clip gather + TimeConv
+    TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, irregular_starts, n_irregular, L,
+                          pad_mode, win_i, nullptr, st));
+    TMR_TRY(timeconv_impl((const float*)timeconv_packed, win_i, n_irregular, L, lt_i, xr_i, mode, st));
+  }
+  PbSrc pbs{pb, lt_i, src_idx};
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs));
+  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, mode, st);
 }
 
 int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,

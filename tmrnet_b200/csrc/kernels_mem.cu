@@ -121,12 +121,11 @@ int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h,
 constexpr int kAttnWarps = 4;
 constexpr int KB = 6;
 
-__global__ void __launch_bounds__(kAttnWarps * 32)
-attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
-                 float* __restrict__ a, int round_out) {
+// Body shared by the two attention kernels; rowptr(k) yields the 512-float row of memory slot k.
+template <class RowPtr>
+__device__ __forceinline__ void attention_body(const float* __restrict__ u, int b, int L, float scale,
+                                               float* __restrict__ a, int round_out, RowPtr rowptr) {
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
-  if (b >= B) return;
   float4 uq[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) uq[i] = __ldg(reinterpret_cast<const float4*>(u + (int64_t)b * kD) + i * 32 + lane);
@@ -134,7 +133,6 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float run_max = -INFINITY, run_sum = 0.f;
-  const float4* base = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
 
   for (int k0 = 0; k0 < L; k0 += KB) {
     float4 x[KB][4];
@@ -142,8 +140,9 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
 #pragma unroll
     for (int kk = 0; kk < KB; ++kk) {
       if (k0 + kk < L) {
+        const float4* row = rowptr(k0 + kk);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) x[kk][i] = ldg_nc(base + (int64_t)(k0 + kk) * (kD / 4) + i * 32 + lane);
+        for (int i = 0; i < 4; ++i) x[kk][i] = ldg_nc(row + i * 32 + lane);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) x[kk][i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,11 +193,52 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
   }
 }
 
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
+                 float* __restrict__ a, int round_out) {
+  const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float4* base = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
+  attention_body(u, b, L, scale, a, round_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
+}
+
+// Attention over the bank-level TimeConv output PB[row][7][512] (umma_bankconv.cu).  src[b] >= 0:
+// the clip's window is the contiguous run of bank rows whose slot 0 is PB row src[b]; slot k reads
+// PB row src[b]-k in the variant its distance to the window edges selects.  src[b] < 0: an
+// irregular clip (window crosses a video start) whose TimeConv output lt_irr[-1-src[b]] was computed
+// per clip by the general kernel.
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attention_pb_kernel(const float* __restrict__ u, const float* __restrict__ pb, const float* __restrict__ lt_irr,
+                    const int32_t* __restrict__ src, int B, int L, float scale, float* __restrict__ a,
+                    int round_out) {
+  const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int s = src[b];
+  if (s >= 0) {
+    attention_body(u, b, L, scale, a, round_out, [&](int k) {
+      const int v = (k <= 2) ? k + 1 : ((L - 1 - k <= 2) ? 4 + (L - 1 - k) : 0);
+      return reinterpret_cast<const float4*>(pb + ((int64_t)(s - k) * 7 + v) * kD);
+    });
+  } else {
+    const float4* base = reinterpret_cast<const float4*>(lt_irr + (int64_t)(-1 - s) * L * kD);
+    attention_body(u, b, L, scale, a, round_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
+  }
+}
+
 int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   const float scale = (float)0.044194173824159216;   // (1/512)**0.5 as python computes it (NLB:31)
   attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a, round_out);
   TMR_LAUNCH_CHECK("attention_kernel");
+  return TMR_OK;
+}
+
+int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
+                        float* a, int round_out, cudaStream_t st) {
+  if (B == 0) return TMR_OK;
+  const float scale = (float)0.044194173824159216;
+  attention_pb_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, pb, lt_irr, src, B, L, scale, a, round_out);
+  TMR_LAUNCH_CHECK("attention_pb_kernel");
   return TMR_OK;
 }
 

@@ -33,6 +33,9 @@ int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, 
 int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
                    const float* h_prev, float* h_out, float* c, int B, int round_h, cudaStream_t st);
 bool umma_available();
+// bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
+int umma_bankconv(const float* packed, const float* bank, const float* bank_r, int64_t n_rows, int64_t r_lo,
+                  int64_t r_cnt, int64_t row_base, int64_t pb_rows, float* pb, cudaStream_t st);
 
 // ---- memory-bound kernels (kernels_mem.cu) ----
 int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
@@ -43,6 +46,9 @@ int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h,
                       int round_h, cudaStream_t st);
 // a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]
 int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st);
+// same attention over the bank-level TimeConv output (see umma_bankconv.cu)
+int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
+                        float* a, int round_out, cudaStream_t st);
 // y = relu(layer_norm(v) * w + b) over rows of 512
 int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y,
                           int round_out, cudaStream_t st);

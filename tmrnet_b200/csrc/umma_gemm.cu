@@ -3,7 +3,9 @@
 // Tile 128 x 256 x 32: TMA (SWIZZLE_128B) stages A (16 KB) + W (32 KB) per k-block through a 4-deep
 // mbarrier ring; one elected thread issues four tcgen05.mma.kind::tf32 (K=8) per stage; accumulators
 // are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
-// tile i+1.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (tcgen05.ld).
+// tile i+1.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (tcgen05.ld; two
+// warps per TMEM lane quarter, one per 128-column half, so every SM sub-partition has two warps to
+// hide the epilogue's load / MUFU latencies behind each other).
 // Epilogues: EPI_LINEAR (bias / residual / relu -> out) and EPI_LSTM (gate-interleaved LSTM cell).
 #define TMR_HAVE_UMMA 1
 #include "tmr_internal.h"
@@ -48,7 +50,8 @@ constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;                        // 2 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
@@ -61,7 +64,10 @@ struct GemmParams {
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
 };
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+// Gate non-linearities of the tensor-core path: ex2.approx based, ~1e-7 absolute error, ~6
+// instructions each (the precise expf/tanhf versions made the LSTM epilogue the bottleneck).
+__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * v)); }
 
 template <int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -86,7 +92,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_a2); tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -144,27 +150,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                   // which 128-column half of the accumulator
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m = (tile / n_tiles) * BM + q * 32 + lane;
-      const int n0 = (int)(tile % n_tiles) * BN;
+      const int n0 = (int)(tile % n_tiles) * BN + half * (BN / 2);
+      const bool row_ok = m < p.M;
+      int64_t xr = 0;
+      if (EPI == EPI_LSTM && row_ok) xr = (p.starts ? p.starts[m] : m * p.seq) + p.t;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      int64_t xr = 0;
-      if (EPI == EPI_LSTM && m < p.M) xr = (p.starts ? p.starts[m] : m * p.seq) + p.t;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + cc, r);
-        tmem_ld_wait();
+      for (int cc = 0; cc < BN / 2; cc += 32) {
         const int n = n0 + cc;
-        if (m < p.M && n < p.N) {
-          if (EPI == EPI_LINEAR) {
+        const bool ok = row_ok && n < p.N;
+        uint32_t r[32];
+        if (EPI == EPI_LINEAR) {
+          tmem_ld32(t_row + cc, r);
+          tmem_ld_wait();
+          if (ok) {
             float* dst = p.out + m * p.ldo + n;
             const float* res = p.residual ? p.residual + m * p.ldr + n : nullptr;
 #pragma unroll
@@ -185,25 +194,35 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 *reinterpret_cast<float4*>(dst + j) = v;
               }
             }
-          } else {
-            // 32 gate columns = 8 hidden units x (i,f,g,o)
-            const float* xrow = p.xp + xr * (4 * kD) + n;
-            const int unit0 = n >> 2;
-            float* crow = p.c + m * kD + unit0;
-            float* hrow = p.h_out + m * kD + unit0;
-            float cn[8], hn[8];
-            const float4 c0 = *reinterpret_cast<const float4*>(crow);
-            const float4 c1 = *reinterpret_cast<const float4*>(crow + 4);
+          }
+        } else {
+          // 32 gate columns = 8 hidden units x (i,f,g,o).  Issue the global loads (projected row,
+          // cell state) before waiting on TMEM so their latency overlaps the tcgen05.ld.
+          const int unit0 = n >> 2;
+          float4 x4[8];
+          float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+          float* crow = p.c + m * kD + unit0;
+          float* hrow = p.h_out + m * kD + unit0;
+          if (ok) {
+            const float4* xrow = reinterpret_cast<const float4*>(p.xp + xr * (4 * kD) + n);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x4[u] = __ldg(xrow + u);
+            c0 = *reinterpret_cast<const float4*>(crow);
+            c1 = *reinterpret_cast<const float4*>(crow + 4);
+          }
+          tmem_ld32(t_row + cc, r);
+          tmem_ld_wait();
+          if (ok) {
             const float cold[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float cn[8], hn[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const float4 x4 = __ldg(reinterpret_cast<const float4*>(xrow + 4 * u));
-              const float gi = __uint_as_float(r[4 * u + 0]) + x4.x;
-              const float gf = __uint_as_float(r[4 * u + 1]) + x4.y;
-              const float gg = __uint_as_float(r[4 * u + 2]) + x4.z;
-              const float go = __uint_as_float(r[4 * u + 3]) + x4.w;
-              cn[u] = sigmoidf_(gf) * cold[u] + sigmoidf_(gi) * tanhf(gg);
-              hn[u] = sigmoidf_(go) * tanhf(cn[u]);
+              const float gi = __uint_as_float(r[4 * u + 0]) + x4[u].x;
+              const float gf = __uint_as_float(r[4 * u + 1]) + x4[u].y;
+              const float gg = __uint_as_float(r[4 * u + 2]) + x4[u].z;
+              const float go = __uint_as_float(r[4 * u + 3]) + x4[u].w;
+              cn[u] = fast_sigmoid(gf) * cold[u] + fast_sigmoid(gi) * fast_tanh(gg);
+              hn[u] = fast_sigmoid(go) * fast_tanh(cn[u]);
               if (p.round_h) hn[u] = round_tf32(hn[u]);   // only feeds the next step's MMA
             }
             *reinterpret_cast<float4*>(crow) = make_float4(cn[0], cn[1], cn[2], cn[3]);

@@ -25,7 +25,7 @@ class BankInference:
     """
 
     def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 8192,
-                 pad_mode: str = "repeat", math_mode=None, starts=None):
+                 pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True):
         self.model = model
         self.index = index
         self.seq, self.L = int(seq), int(L)
@@ -37,6 +37,48 @@ class BankInference:
         self.starts_host = np.sort(np.asarray(starts, dtype=np.int64))
         self._ws = None
         self._starts_dev = None
+        # bank-level TimeConv dedup (tmr_head_frames_dedup_fwd): tensor-core mode, TimeConv present, L >= 6
+        self.dedup = bool(dedup) and self.L >= 6 and model.time_conv is not None
+        self._dedup_plan = None
+        self._dedup_dev = {}
+
+    def _use_dedup(self):
+        mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
+        return self.dedup and mode == ops.TMR_MATH_TF32
+
+    def dedup_plan(self):
+        """Per batch: which clips are regular (window = contiguous run of bank rows), the PB row range
+        and the per-clip source index the attention kernel reads (see include/tmr_b200.h)."""
+        if self._dedup_plan is None:
+            f2r = self.index.frame2row_host.astype(np.int64)
+            f2v = self.index.frame2vstart_host
+            if f2v is None:
+                raise ValueError("dedup needs an LFBIndex built with from_lengths() (video boundaries)")
+            f2v = f2v.astype(np.int64)
+            out = []
+            for lo, hi, fl, fh in self.plan():
+                s = self.starts_host[lo:hi]
+                regular = (s - f2v[s]) >= self.L
+                r0 = f2r[s] - 1                                   # bank row of slot 0
+                src = np.empty(hi - lo, dtype=np.int32)
+                irr = s[~regular]
+                src[~regular] = -1 - np.arange(len(irr), dtype=np.int32)
+                if regular.any():
+                    row_base = int(r0[regular].min()) - (self.L - 1)
+                    pb_rows = int(r0[regular].max()) - row_base + 1
+                    src[regular] = (r0[regular] - row_base).astype(np.int32)
+                else:
+                    row_base, pb_rows = 0, 0
+                out.append(dict(src=src, irr=irr.astype(np.int64), row_base=row_base, pb_rows=pb_rows))
+            self._dedup_plan = out
+        return self._dedup_plan
+
+    def _dedup_tensors(self, dev):
+        if dev not in self._dedup_dev:
+            self._dedup_dev[dev] = [(torch.from_numpy(d["src"]).to(dev),
+                                     torch.from_numpy(d["irr"]).to(dev) if len(d["irr"]) else None)
+                                    for d in self.dedup_plan()]
+        return self._dedup_dev[dev]
 
     def plan(self):
         """[(clip_lo, clip_hi, frame_lo, frame_hi)] per batch; frames cover every clip of the batch."""
@@ -68,8 +110,14 @@ class BankInference:
         packs = self.model.packs()
         f2r, f2v = self.index.device_tables(dev)
         plan = self.plan()
-        need = max((lib.tmr_head_frames_workspace_bytes(fh - fl, hi - lo, self.L, D) for lo, hi, fl, fh in plan),
-                   default=256)
+        dedup = self._use_dedup()
+        if dedup:
+            dplan, dten = self.dedup_plan(), self._dedup_tensors(dev)
+            need = max((lib.tmr_head_frames_dedup_workspace_bytes(fh - fl, hi - lo, len(d["irr"]), d["pb_rows"], self.L, D)
+                        for (lo, hi, fl, fh), d in zip(plan, dplan)), default=256)
+        else:
+            need = max((lib.tmr_head_frames_workspace_bytes(fh - fl, hi - lo, self.L, D) for lo, hi, fl, fh in plan),
+                       default=256)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = _ws(need, dev)
         ws = self._ws
@@ -77,30 +125,44 @@ class BankInference:
         st = out.get("St")
         with torch.cuda.device(dev):
             stream = _stream()
-            for lo, hi, fl, fh in plan:
-                check(lib.tmr_head_frames_fwd(
-                    _ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
-                    C.c_void_p(feats.data_ptr() + fl * F * 4), fh - fl, fl,
-                    _ptr(bank), bank.shape[0], _ptr(f2r), _ptr(f2v), f2r.numel(),
-                    C.c_void_p(starts_dev.data_ptr() + lo * 8), hi - lo, self.seq, self.L, F, D, Cn,
-                    self.pad_mode,
-                    C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
-                    C.c_void_p(out["pred"].data_ptr() + lo * 8),
-                    C.c_void_p(out["score"].data_ptr() + lo * 4),
-                    C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
-                    _ptr(ws), ws.numel(), mode, stream))
+            for i, (lo, hi, fl, fh) in enumerate(plan):
+                common_in = (_ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
+                             C.c_void_p(feats.data_ptr() + fl * F * 4), fh - fl, fl,
+                             _ptr(bank), bank.shape[0], _ptr(f2r), _ptr(f2v), f2r.numel(),
+                             C.c_void_p(starts_dev.data_ptr() + lo * 8), hi - lo)
+                common_out = (C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
+                              C.c_void_p(out["pred"].data_ptr() + lo * 8),
+                              C.c_void_p(out["score"].data_ptr() + lo * 4),
+                              C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
+                              _ptr(ws), ws.numel())
+                if dedup:
+                    d, (src_dev, irr_dev) = dplan[i], dten[i]
+                    check(lib.tmr_head_frames_dedup_fwd(*common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
+                                                        d["row_base"], d["pb_rows"], self.seq, self.L, F, D, Cn,
+                                                        self.pad_mode, *common_out, stream))
+                else:
+                    check(lib.tmr_head_frames_fwd(*common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
+                                                  *common_out, mode, stream))
         return out
 
     def launches_per_run(self) -> int:
         """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
         projection + cell0 + (seq-1) steps | gather | timeconv | q, u, attention, v, layernorm, out |
-        fc_h_c, fc_c; TF32 mode adds the four TF32 rounding passes (features, window, St, [St|y1])."""
+        fc_h_c, fc_c; TF32 mode adds the TF32 rounding passes (features, window, St, [St|y1]); the
+        dedup path replaces gather+round+timeconv over all clips by round(bank rows) + bankconv and
+        runs gather+round+timeconv only when the batch has irregular clips."""
         mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
         tc = 1 if self.model.time_conv is not None else 0
-        per = (1 + 1 + (self.seq - 1)) + 1 + tc + 6 + 2
-        if mode == ops.TMR_MATH_TF32:
-            per += 3 + tc
-        return per * len(self.plan())
+        lstm = 1 + 1 + (self.seq - 1)
+        tail = 6 + 2
+        if mode != ops.TMR_MATH_TF32:
+            return (lstm + 1 + tc + tail) * len(self.plan())
+        if not self._use_dedup():
+            return (lstm + 1 + 1 + 2 * tc + tail + 2) * len(self.plan())
+        n = 0
+        for d in self.dedup_plan():
+            n += (lstm + 1) + (2 if d["pb_rows"] > 0 else 0) + (3 if len(d["irr"]) else 0) + tail + 2
+        return n
 
 
 # ---------------------------------------------------------------------------------------------
