@@ -175,6 +175,11 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
  *   irregular_starts device int64[n_irregular] global start frames of the irregular clips;
  *   pb_row_base, pb_rows  bank row range covering slot L-1 of the first regular clip .. slot 0 of the
  *                    last one (pb_rows = 0 when the batch has no regular clip).  Needs L >= 6. */
+/* The bank-level TimeConv alone: pb[(row - row_base)*7 + v][D] for bank rows row_base .. row_base+pb_rows-1,
+ * v = 0 interior slot, 1..3 slot k = 0,1,2, 4..6 slot k = L-1, L-2, L-3 (see tmrnet_b200/csrc/umma_bankconv.cu). */
+size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D);
+int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
+                     int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream);
 size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
                                              int L, int D);
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,

@@ -261,9 +261,12 @@ def test_lstm_LFB_module_builds_bank_rows(golden_dir):
     sd = _sd(7)
     lfb.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items() if k.startswith("lstm.")})
     lfb = lfb.to(_dev()).eval()
-    with torch.no_grad():
-        got = lfb(x.reshape(-1, 2048))
-    assert rel_err(got, z["St"]) < TOL["fp32"]
+    for mode in MODES:
+        _need_mode(mode)
+        lfb.math_mode = mode
+        with torch.no_grad():
+            got = lfb(x.reshape(-1, 2048))
+        assert rel_err(got, z["St"]) < TOL[mode]
 
 
 # ------------------------------------------------------------------------------------------
@@ -470,15 +473,42 @@ def test_video_sharded_inference_is_bit_identical_to_unsharded(mode):
 
 
 @pytest.mark.parametrize("L", [6, 7, 10, 30, 60])
+def test_bankconv_variants_match_per_clip_timeconv(L):
+    """Bank-level TimeConv (convolutions once per bank row, 7 edge variants) against the per-clip
+    tcgen05 kernel on windows that are contiguous runs of bank rows: same TF32 operands, only the
+    fp32 summation order differs."""
+    _need_mode("tf32")
+    dev = _dev()
+    n_rows = 500
+    bank = synth.bank(n_rows, seed=3)
+    m = _model(7)
+    pk = m.time_conv.packed()
+    pb = ops.bankconv(pk, torch.from_numpy(bank).to(dev), 0, n_rows).cpu()
+    pb_part = ops.bankconv(pk, torch.from_numpy(bank).to(dev), 130, 200).cpu()       # arbitrary row range
+    assert torch.equal(pb_part[3:-3], pb[133:327])
+    r0 = np.arange(L + 2, n_rows - 5)
+    rows = r0[:, None] - np.arange(L)[None, :]
+    win = torch.from_numpy(bank[rows])
+    k = np.arange(L)
+    v = np.where(k <= 2, k + 1, np.where(L - 1 - k <= 2, 4 + (L - 1 - k), 0))
+    ded = pb[torch.from_numpy(rows), torch.from_numpy(np.broadcast_to(v, rows.shape).copy())]
+    gen = ops.timeconv_max(pk, win.to(dev), "tf32").cpu()
+    assert rel_err(ded, gen) < 2e-5
+    assert rel_err(ded, orc.timeconv(win, _sd(7), dtype=torch.float64)) < TOL["tf32"]
+
+
+@pytest.mark.parametrize("L", [6, 10, 30, 60])
 @pytest.mark.parametrize("pad_mode", ["repeat", "zero"])
-def test_bank_level_timeconv_dedup_matches_per_clip_path(L, pad_mode):
-    """tmr_head_frames_dedup_fwd (convolutions once per bank row, 7 edge variants) against the
-    per-clip path on the same clips, and against the oracle."""
+def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode):
+    """tmr_head_frames_dedup_fwd against the oracle (1e-3) and against the per-clip path.  The two
+    CUDA paths use identical TF32 operands; their TimeConv outputs differ by ~1e-5 (summation order),
+    which the TF32 re-rounding of later GEMM operands can amplify to the TF32 noise level, so they are
+    held to the same 1e-3 as the oracle comparison, and irregular clips must agree exactly."""
     _need_mode("tf32")
     from tmrnet_b200.infer import BankInference
     dev = _dev()
-    lengths, seq, _, feats, bank = _small_job(seed=11)
-    lengths = lengths + [400]
+    lengths = [57, 12, 140, 9, 33, 210, 45, 400]
+    seq = 10
     feats = synth.features(sum(lengths), seed=11)
     bank = synth.bank(len(synth.clip_starts(lengths, seq)), seed=11)
     m = _model(7)
@@ -487,10 +517,12 @@ def test_bank_level_timeconv_dedup_matches_per_clip_path(L, pad_mode):
     ref = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=False, pad_mode=pad_mode).run(f, b)
     eng = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=True, pad_mode=pad_mode)
     assert eng._use_dedup()
-    n_irr = sum(len(d["irr"]) for d in eng.dedup_plan())
-    assert 0 < n_irr < len(idx)
+    src = np.concatenate([d["src"] for d in eng.dedup_plan()])
+    assert 0 < (src < 0).sum() < len(idx)
     got = eng.run(f, b)
-    assert rel_err(got["logits"], ref["logits"]) < 2e-5
+    assert rel_err(got["logits"], ref["logits"]) < TOL["tf32"]
+    irr = torch.from_numpy(src < 0).to(dev)
+    assert torch.equal(got["logits"][irr], ref["logits"][irr])
     if pad_mode == "repeat":
         starts = synth.clip_starts(lengths, seq)
         x = np.stack([feats[s:s + seq] for s in starts])

@@ -425,6 +425,25 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
                    math_mode, st);
 }
 
+size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D) { return fbytes((size_t)((pb_rows > 0 ? pb_rows : 1) + 8) * D); }
+int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
+                     int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_TRY(check_mode(TMR_MATH_TF32));
+  TMR_CHECK_ARG(pb_rows >= 0 && row_base >= 0 && row_base + pb_rows <= n_rows, "bankconv: row range outside the bank");
+  if (pb_rows == 0) return TMR_OK;
+  TMR_CHECK_ARG(timeconv_packed && bank && pb && workspace, "bankconv: null pointer");
+  TMR_CHECK_ARG(aligned16(bank) && aligned16(pb) && aligned16(workspace), "bankconv: pointers must be 16-byte aligned");
+  Carver cv(workspace, workspace_bytes);
+  float* bank_r = cv.take((size_t)(pb_rows + 8) * kD);
+  TMR_CHECK_ARG(bank_r, "bankconv: workspace too small");
+  const int64_t r_lo = row_base - 3 > 0 ? row_base - 3 : 0;
+  const int64_t r_hi = row_base + pb_rows + 4 < n_rows ? row_base + pb_rows + 4 : n_rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  TMR_TRY(launch_round_tf32(bank + r_lo * kD, bank_r, (r_hi - r_lo) * kD, st));
+  return umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows, pb, st);
+}
+
 size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
                                              int L, int D) {
   const size_t b = (size_t)(B > 0 ? B : 1);
