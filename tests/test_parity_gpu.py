@@ -532,3 +532,22 @@ def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode):
         top2 = torch.topk(ref_logits, 2, dim=1).values
         safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL["tf32"] * float(ref_logits.abs().max())
         assert torch.equal(got["pred"].cpu()[safe], ref_logits.argmax(1)[safe])
+
+
+def test_host_buffer_pass_equals_resident_pass():
+    """BankInference.run_host (double-buffered H2D of the features, D2H of preds/scores) must give
+    exactly what run() gives on resident features."""
+    from tmrnet_b200.infer import BankInference
+    dev = _dev()
+    lengths, seq, L, feats, bank = _small_job(seed=4)
+    m = _model(7)
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    eng = BankInference(m, idx, seq, L, batch_clips=64)
+    b = torch.from_numpy(bank).to(dev)
+    ref = eng.run(torch.from_numpy(feats).to(dev), b)
+    ref = {k: v.clone() for k, v in ref.items()}
+    out, (pred_h, score_h) = eng.run_host(torch.from_numpy(feats).pin_memory(), b)
+    torch.cuda.synchronize()
+    for k in ("logits", "pred", "score"):
+        assert torch.equal(out[k], ref[k]), k
+    assert torch.equal(pred_h, ref["pred"].cpu()) and torch.equal(score_h, ref["score"].cpu())

@@ -89,28 +89,23 @@ class BankInference:
             out.append((lo, hi, int(self.starts_host[lo]), int(self.starts_host[hi - 1]) + self.seq))
         return out
 
-    def run(self, feats, bank, starts_dev=None, out=None, want_st=False):
-        """All clips of the index in global clip order.  Returns dict(logits, pred, score[, St])."""
-        feats = _dev(feats, "feats")
-        bank = _dev(bank, "bank")
-        dev = feats.device
-        n = len(self.starts_host)
-        Cn = self.model.num_class
-        if starts_dev is None:
-            if self._starts_dev is None or self._starts_dev.device != dev:
-                self._starts_dev = torch.from_numpy(self.starts_host).to(dev)
-            starts_dev = self._starts_dev
-        if out is None:
-            out = dict(logits=torch.empty((n, Cn), dtype=torch.float32, device=dev),
-                       pred=torch.empty((n,), dtype=torch.int64, device=dev),
-                       score=torch.empty((n,), dtype=torch.float32, device=dev))
-            if want_st:
-                out["St"] = torch.empty((n, D), dtype=torch.float32, device=dev)
+    def _alloc_out(self, dev, want_st):
+        n, Cn = len(self.starts_host), self.model.num_class
+        out = dict(logits=torch.empty((n, Cn), dtype=torch.float32, device=dev),
+                   pred=torch.empty((n,), dtype=torch.int64, device=dev),
+                   score=torch.empty((n,), dtype=torch.float32, device=dev))
+        if want_st:
+            out["St"] = torch.empty((n, D), dtype=torch.float32, device=dev)
+        return out
+
+    def _prepare(self, dev, bank):
+        """Everything a pass needs that does not depend on the feature buffer."""
         lib = _lib.load()
-        packs = self.model.packs()
-        f2r, f2v = self.index.device_tables(dev)
+        if self._starts_dev is None or self._starts_dev.device != dev:
+            self._starts_dev = torch.from_numpy(self.starts_host).to(dev)
         plan = self.plan()
         dedup = self._use_dedup()
+        dplan = dten = None
         if dedup:
             dplan, dten = self.dedup_plan(), self._dedup_tensors(dev)
             need = max((lib.tmr_head_frames_dedup_workspace_bytes(fh - fl, hi - lo, len(d["irr"]), d["pb_rows"], self.L, D)
@@ -120,30 +115,91 @@ class BankInference:
                        default=256)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = _ws(need, dev)
-        ws = self._ws
+        f2r, f2v = self.index.device_tables(dev)
         mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
+        return dict(lib=lib, plan=plan, dedup=dedup, dplan=dplan, dten=dten, ws=self._ws, f2r=f2r, f2v=f2v, mode=mode,
+                    packs=self.model.packs(), bank=bank, starts=self._starts_dev)
+
+    def _launch_batch(self, ctx, i, feats_ptr, out, stream):
+        """Enqueue batch i; feats_ptr addresses the features of frame plan[i].frame_lo."""
+        lo, hi, fl, fh = ctx["plan"][i]
+        lib, packs, bank, ws = ctx["lib"], ctx["packs"], ctx["bank"], ctx["ws"]
+        Cn = self.model.num_class
         st = out.get("St")
+        common_in = (_ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
+                     C.c_void_p(feats_ptr), fh - fl, fl,
+                     _ptr(bank), bank.shape[0], _ptr(ctx["f2r"]), _ptr(ctx["f2v"]), ctx["f2r"].numel(),
+                     C.c_void_p(ctx["starts"].data_ptr() + lo * 8), hi - lo)
+        common_out = (C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
+                      C.c_void_p(out["pred"].data_ptr() + lo * 8),
+                      C.c_void_p(out["score"].data_ptr() + lo * 4),
+                      C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
+                      _ptr(ws), ws.numel())
+        if ctx["dedup"]:
+            d, (src_dev, irr_dev) = ctx["dplan"][i], ctx["dten"][i]
+            check(lib.tmr_head_frames_dedup_fwd(*common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
+                                                d["row_base"], d["pb_rows"], self.seq, self.L, F, D, Cn,
+                                                self.pad_mode, *common_out, stream))
+        else:
+            check(lib.tmr_head_frames_fwd(*common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
+                                          *common_out, ctx["mode"], stream))
+
+    def run(self, feats, bank, out=None, want_st=False):
+        """All clips of the index in global clip order, features resident on the device.
+        Returns dict(logits, pred, score[, St]) of device tensors."""
+        feats = _dev(feats, "feats")
+        bank = _dev(bank, "bank")
+        dev = feats.device
+        if out is None:
+            out = self._alloc_out(dev, want_st)
+        ctx = self._prepare(dev, bank)
         with torch.cuda.device(dev):
             stream = _stream()
-            for i, (lo, hi, fl, fh) in enumerate(plan):
-                common_in = (_ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
-                             C.c_void_p(feats.data_ptr() + fl * F * 4), fh - fl, fl,
-                             _ptr(bank), bank.shape[0], _ptr(f2r), _ptr(f2v), f2r.numel(),
-                             C.c_void_p(starts_dev.data_ptr() + lo * 8), hi - lo)
-                common_out = (C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
-                              C.c_void_p(out["pred"].data_ptr() + lo * 8),
-                              C.c_void_p(out["score"].data_ptr() + lo * 4),
-                              C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
-                              _ptr(ws), ws.numel())
-                if dedup:
-                    d, (src_dev, irr_dev) = dplan[i], dten[i]
-                    check(lib.tmr_head_frames_dedup_fwd(*common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
-                                                        d["row_base"], d["pb_rows"], self.seq, self.L, F, D, Cn,
-                                                        self.pad_mode, *common_out, stream))
-                else:
-                    check(lib.tmr_head_frames_fwd(*common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
-                                                  *common_out, mode, stream))
+            for i, (lo, hi, fl, fh) in enumerate(ctx["plan"]):
+                self._launch_batch(ctx, i, feats.data_ptr() + fl * F * 4, out, stream)
         return out
+
+    def run_host(self, feats_host, bank, out=None, host_out=None):
+        """Same pass with the per-frame features in (pinned) HOST memory: each batch's frames are
+        copied H2D on a side stream into one of two staging buffers while the previous batch
+        computes; predictions and scores are copied back D2H at the end.  Returns
+        (device outputs, (pred_host, score_host))."""
+        bank = _dev(bank, "bank")
+        dev = bank.device
+        if not (isinstance(feats_host, torch.Tensor) and not feats_host.is_cuda and feats_host.dtype == torch.float32
+                and feats_host.dim() == 2 and feats_host.shape[1] == F and feats_host.is_contiguous()):
+            raise TypeError(f"feats_host must be a contiguous CPU float32 tensor (n_frames,{F})")
+        if out is None:
+            out = self._alloc_out(dev, False)
+        ctx = self._prepare(dev, bank)
+        plan = ctx["plan"]
+        max_frames = max((fh - fl for _, _, fl, fh in plan), default=1)
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < max_frames or self._stage[0].device != dev:
+            self._stage = [torch.empty((max_frames, F), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if host_out is None:
+            n = len(self.starts_host)
+            host_out = (torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory())
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream()
+            stream = _stream()
+            copied = [torch.cuda.Event() for _ in plan]
+            freed = [None, None]
+            self._copy_stream.wait_stream(compute)          # staging buffers may still be in use by earlier work
+            for i, (lo, hi, fl, fh) in enumerate(plan):
+                buf = self._stage[i & 1]
+                with torch.cuda.stream(self._copy_stream):
+                    if freed[i & 1] is not None:
+                        self._copy_stream.wait_event(freed[i & 1])
+                    buf[:fh - fl].copy_(feats_host[fl:fh], non_blocking=True)
+                    copied[i].record(self._copy_stream)
+                compute.wait_event(copied[i])
+                self._launch_batch(ctx, i, buf.data_ptr(), out, stream)
+                freed[i & 1] = torch.cuda.Event()
+                freed[i & 1].record(compute)
+            host_out[0].copy_(out["pred"], non_blocking=True)
+            host_out[1].copy_(out["score"], non_blocking=True)
+        return out, host_out
 
     def launches_per_run(self) -> int:
         """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
