@@ -8,6 +8,8 @@
 // hide the epilogue's load / MUFU latencies behind each other).
 // Epilogues: EPI_LINEAR (bias / residual / relu -> out) and EPI_LSTM (gate-interleaved LSTM cell).
 #define TMR_HAVE_UMMA 1
+#include <stdlib.h>
+
 #include "tmr_internal.h"
 #include "umma_common.cuh"
 
@@ -69,7 +71,11 @@ struct GemmParams {
 __device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
 __device__ __forceinline__ float fast_tanh(float v) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * v)); }
 
-template <int EPI>
+// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs on adjacent M tiles of the same N tile; each
+// CTA loads its own A tile and HALF of the shared W tile and multicasts that half into both CTAs, so
+// weight traffic from L2 per CTA halves (48 -> 32 KB per k-block).  A stage may only be refilled when
+// BOTH consumers have released it: every tcgen05.commit on a stage arrives on both CTAs' empty barrier.
+template <int EPI, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                  const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
@@ -86,18 +92,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int64_t m_tiles = (p.M + BM - 1) / BM;
-  const int64_t num_tiles = m_tiles * n_tiles;
   const int k_blocks = p.K / BK;
+  // work items: CL consecutive M tiles x one N tile; CTA `crank` of the cluster takes M tile CL*mp + crank
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
+  const int64_t num_items = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const int64_t item0 = blockIdx.x / CL;
+  const int64_t item_stride = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_a2); tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -105,18 +117,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (int)(tile / n_tiles) * BM;
-        const int n0 = (int)(tile % n_tiles) * BN;
+      for (int64_t item = item0; item < num_items; item += item_stride) {
+        const int m0 = (int)((item / n_tiles) * CL + crank) * BM;
+        const int n0 = (int)(item % n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);       // CL > 1: released by BOTH CTAs' consumers
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int k0 = kb * BK;
           if (k0 < p.k_split) tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
           else tma_load_2d(sa, &tma_a2, &full_bar[stage], k0 - p.k_split, m0);
-          tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+          if (CL == 1) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+            tma_load_2d(sb + B_BYTES / 2, &tma_b, &full_bar[stage], k0, n0 + BN / 2);
+          } else {   // my half of the W tile, written into both CTAs
+            tma_load_2d_mcast(sb + crank * (B_BYTES / 2), &tma_b, &full_bar[stage], k0, n0 + (int)crank * (BN / 2), kMask);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -127,7 +144,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
@@ -143,7 +160,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)              // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
             mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          mma_commit(&empty_bar[stage]);                // frees the smem stage when these MMAs retire
+          if (CL == 1) mma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+          else mma_commit_mcast(&empty_bar[stage], kMask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit(&acc_full[acc]);                     // accumulator complete -> epilogue
@@ -154,23 +172,77 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                   // which 128-column half of the accumulator
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int64_t m = (tile / n_tiles) * BM + q * 32 + lane;
-      const int n0 = (int)(tile % n_tiles) * BN + half * (BN / 2);
+      const int64_t m = ((item / n_tiles) * CL + crank) * BM + q * 32 + lane;
+      const int n0 = (int)(item % n_tiles) * BN + half * (BN / 2);
       const bool row_ok = m < p.M;
       int64_t xr = 0;
       if (EPI == EPI_LSTM && row_ok) xr = (p.starts ? p.starts[m] : m * p.seq) + p.t;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+      if (EPI == EPI_LSTM) {
+        // ---- LSTM cell epilogue, software-pipelined: the projected-row and cell-state loads of chunk
+        // cc+1 are in flight while chunk cc is computed, and chunk 0's are issued BEFORE waiting for the
+        // accumulator, so their latency hides behind this tile's main loop. ----
+        const float4* xrow = reinterpret_cast<const float4*>(p.xp + xr * (4 * kD) + n0);
+        float* crow = p.c + m * kD + (n0 >> 2);
+        float* hrow = p.h_out + m * kD + (n0 >> 2);
+        float4 xa[8], xb[8], ca[2], cb[2];
+        auto prefetch = [&](int cc, float4 (&x4)[8], float4 (&c2)[2]) {
+          if (row_ok) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x4[u] = __ldg(xrow + (cc >> 2) + u);
+            c2[0] = *reinterpret_cast<const float4*>(crow + (cc >> 2));
+            c2[1] = *reinterpret_cast<const float4*>(crow + (cc >> 2) + 4);
+          }
+        };
+        auto compute = [&](int cc, const float4 (&x4)[8], const float4 (&c2)[2]) {
+          uint32_t r[32];
+          tmem_ld32(t_row + cc, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const float cold[8] = {c2[0].x, c2[0].y, c2[0].z, c2[0].w, c2[1].x, c2[1].y, c2[1].z, c2[1].w};
+            float cn[8], hn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float gi = __uint_as_float(r[4 * u + 0]) + x4[u].x;
+              const float gf = __uint_as_float(r[4 * u + 1]) + x4[u].y;
+              const float gg = __uint_as_float(r[4 * u + 2]) + x4[u].z;
+              const float go = __uint_as_float(r[4 * u + 3]) + x4[u].w;
+              cn[u] = fast_sigmoid(gf) * cold[u] + fast_sigmoid(gi) * fast_tanh(gg);
+              hn[u] = fast_sigmoid(go) * fast_tanh(cn[u]);
+              if (p.round_h) hn[u] = round_tf32(hn[u]);   // only feeds the next step's MMA
+            }
+            float* cw = crow + (cc >> 2);
+            float* hw = hrow + (cc >> 2);
+            *reinterpret_cast<float4*>(cw) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(cw + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            *reinterpret_cast<float4*>(hw) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(hw + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+          }
+        };
+        prefetch(0, xa, ca);
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        // BN/2 = 128 gate columns = 4 chunks of 32 (8 hidden units x i,f,g,o)
+        prefetch(32, xb, cb);  compute(0, xa, ca);
+        prefetch(64, xa, ca);  compute(32, xb, cb);
+        prefetch(96, xb, cb);  compute(64, xa, ca);
+        compute(96, xb, cb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        continue;
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 2; cc += 32) {
         const int n = n0 + cc;
         const bool ok = row_ok && n < p.N;
         uint32_t r[32];
-        if (EPI == EPI_LINEAR) {
+        {
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
           if (ok) {
@@ -195,41 +267,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               }
             }
           }
-        } else {
-          // 32 gate columns = 8 hidden units x (i,f,g,o).  Issue the global loads (projected row,
-          // cell state) before waiting on TMEM so their latency overlaps the tcgen05.ld.
-          const int unit0 = n >> 2;
-          float4 x4[8];
-          float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-          float* crow = p.c + m * kD + unit0;
-          float* hrow = p.h_out + m * kD + unit0;
-          if (ok) {
-            const float4* xrow = reinterpret_cast<const float4*>(p.xp + xr * (4 * kD) + n);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) x4[u] = __ldg(xrow + u);
-            c0 = *reinterpret_cast<const float4*>(crow);
-            c1 = *reinterpret_cast<const float4*>(crow + 4);
-          }
-          tmem_ld32(t_row + cc, r);
-          tmem_ld_wait();
-          if (ok) {
-            const float cold[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            float cn[8], hn[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float gi = __uint_as_float(r[4 * u + 0]) + x4[u].x;
-              const float gf = __uint_as_float(r[4 * u + 1]) + x4[u].y;
-              const float gg = __uint_as_float(r[4 * u + 2]) + x4[u].z;
-              const float go = __uint_as_float(r[4 * u + 3]) + x4[u].w;
-              cn[u] = fast_sigmoid(gf) * cold[u] + fast_sigmoid(gi) * fast_tanh(gg);
-              hn[u] = fast_sigmoid(go) * fast_tanh(cn[u]);
-              if (p.round_h) hn[u] = round_tf32(hn[u]);   // only feeds the next step's MMA
-            }
-            *reinterpret_cast<float4*>(crow) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(crow + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-            *reinterpret_cast<float4*>(hrow) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hrow + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-          }
         }
       }
       tc_fence_before();
@@ -240,6 +277,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's smem / barriers
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
@@ -273,13 +311,30 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     }
     uint64_t dw[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t sw[1] = {(uint64_t)ldw * 4};
-    uint32_t bw[2] = {BK, BN};
+    uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
     TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
   }
-  TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const int64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
+  const int64_t m_tiles = (p.M + BM - 1) / BM;
+  const int64_t n_tiles = (p.N + BN - 1) / BN;
+  if (cluster == 2 && m_tiles >= 2) {
+    TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int64_t items = ((m_tiles + 1) / 2) * n_tiles;
+    const int max_clusters = num_sms() / 2;
+    const int clusters = (int)(items < max_clusters ? items : max_clusters);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, p));
+    return TMR_OK;
+  }
+  TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int64_t tiles = m_tiles * n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  umma_gemm_kernel<EPI><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, ta2, tb, p);
+  umma_gemm_kernel<EPI, 1><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, ta2, tb, p);
   TMR_LAUNCH_CHECK("umma_gemm_kernel");
   return TMR_OK;
 }
