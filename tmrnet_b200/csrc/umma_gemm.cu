@@ -51,7 +51,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 8 * 4096;            // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 320;                        // 2 control warps + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
@@ -64,12 +65,18 @@ struct GemmParams {
   const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
+  int debug;   // experiments only (TMR_DEBUG_EPI): 1 = skip epilogue global I/O, 2 = skip TMEM loads too
 };
 
-// Gate non-linearities of the tensor-core path: ex2.approx based, ~1e-7 absolute error, ~6
-// instructions each (the precise expf/tanhf versions made the LSTM epilogue the bottleneck).
-__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * v)); }
+// Gate non-linearities of the tensor-core path: MUFU ex2/rcp approximations (2 ulp / 1 ulp), four
+// instructions per sigmoid.  The precise expf/tanhf versions — and even __expf + __frcp_rn, whose
+// round-to-nearest reciprocal expands to ~10 instructions and a slow-path branch — made the gate math
+// of the LSTM epilogue the bottleneck of the whole recurrence (measured: 1007 us -> 694 us per
+// 8192-clip batch with the math stubbed out).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float fast_tanh(float v) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * v)), -1.f); }
 
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs on adjacent M tiles of the same N tile; each
 // CTA loads its own A tile and HALF of the shared W tile and multicasts that half into both CTAs, so
@@ -81,7 +88,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                  const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
@@ -169,101 +176,120 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
+    // TMEM hands every thread one accumulator ROW (lane = row), but a row-per-thread global access
+    // pattern touches 32 different cache lines per warp instruction and made the epilogue, not the
+    // MMAs, bound these kernels (measured: recurrent GEMM 48 us with, 30 us without epilogue I/O).
+    // So each 32x32 chunk goes TMEM -> registers -> a 4 KB XOR-swizzled smem tile (phase A), and all
+    // element-wise work + global I/O happens in a COALESCED layout (phase B): per instruction 8 lanes
+    // cover the 128 contiguous bytes of one row, 4 rows per warp instruction.
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                   // which 128-column half of the accumulator
+    float* sbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * 1024;   // 32 rows x 32 floats
+    const int prow = lane >> 3;                         // phase B: row within a group of 4
+    const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
     int it = 0;
     for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int64_t m = ((item / n_tiles) * CL + crank) * BM + q * 32 + lane;
+      const int64_t m_base = ((item / n_tiles) * CL + crank) * BM + q * 32;     // first row of this warp
       const int n0 = (int)(item % n_tiles) * BN + half * (BN / 2);
-      const bool row_ok = m < p.M;
-      int64_t xr = 0;
-      if (EPI == EPI_LSTM && row_ok) xr = (p.starts ? p.starts[m] : m * p.seq) + p.t;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
-      if (EPI == EPI_LSTM) {
-        // ---- LSTM cell epilogue, software-pipelined: the projected-row and cell-state loads of chunk
-        // cc+1 are in flight while chunk cc is computed, and chunk 0's are issued BEFORE waiting for the
-        // accumulator, so their latency hides behind this tile's main loop. ----
-        const float4* xrow = reinterpret_cast<const float4*>(p.xp + xr * (4 * kD) + n0);
-        float* crow = p.c + m * kD + (n0 >> 2);
-        float* hrow = p.h_out + m * kD + (n0 >> 2);
-        float4 xa[8], xb[8], ca[2], cb[2];
-        auto prefetch = [&](int cc, float4 (&x4)[8], float4 (&c2)[2]) {
-          if (row_ok) {
+
+      // phase A helper: this thread's row of the chunk -> swizzled smem (conflict-free 128-bit stores)
+      auto stage_rows = [&](const uint32_t (&r)[32]) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) x4[u] = __ldg(xrow + (cc >> 2) + u);
-            c2[0] = *reinterpret_cast<const float4*>(crow + (cc >> 2));
-            c2[1] = *reinterpret_cast<const float4*>(crow + (cc >> 2) + 4);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      };
+      auto staged = [&](int i) -> float4 {     // phase B read: row 4i+prow, columns 4*pch..4*pch+3
+        const int row = 4 * i + prow;
+        return *reinterpret_cast<const float4*>(sbuf + row * 32 + ((pch ^ (row & 7)) << 2));
+      };
+
+      if (EPI == EPI_LSTM) {
+        // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
+        // step i.  Projected rows + cell state of chunk cc+1 are loaded while chunk cc is computed, and
+        // chunk 0's loads are issued before waiting for the accumulator.
+        int xr[8];                                      // projected-row index per phase-B step (-1: row >= M)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t mr = m_base + 4 * i + prow;
+          xr[i] = (mr < p.M) ? (int)((p.starts ? p.starts[mr] : mr * p.seq) + p.t) : -1;
+        }
+        const float* xp0 = p.xp + n0 + 4 * pch;
+        const int64_t c0 = (m_base + prow) * kD + (n0 >> 2) + pch;      // + 4*i*kD per step, + cc/4 per chunk
+        float4 xa[8], xb[8];
+        float ca[8], cb[8];
+        auto prefetch = [&](int cc, float4 (&x4)[8], float (&c1)[8]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (xr[i] >= 0 && !(p.debug & 4)) {
+              x4[i] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc));
+              c1[i] = p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)];
+            } else { x4[i] = make_float4(0.f, 0.f, 0.f, 0.f); c1[i] = 0.f; }
           }
         };
-        auto compute = [&](int cc, const float4 (&x4)[8], const float4 (&c2)[2]) {
+        auto compute = [&](int cc, const float4 (&x4)[8], const float (&c1)[8]) {
           uint32_t r[32];
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
-          if (row_ok) {
-            const float cold[8] = {c2[0].x, c2[0].y, c2[0].z, c2[0].w, c2[1].x, c2[1].y, c2[1].z, c2[1].w};
-            float cn[8], hn[8];
+          __syncwarp();                                   // previous chunk's phase B reads are done
+          stage_rows(r);
+          __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float gi = __uint_as_float(r[4 * u + 0]) + x4[u].x;
-              const float gf = __uint_as_float(r[4 * u + 1]) + x4[u].y;
-              const float gg = __uint_as_float(r[4 * u + 2]) + x4[u].z;
-              const float go = __uint_as_float(r[4 * u + 3]) + x4[u].w;
-              cn[u] = fast_sigmoid(gf) * cold[u] + fast_sigmoid(gi) * fast_tanh(gg);
-              hn[u] = fast_sigmoid(go) * fast_tanh(cn[u]);
-              if (p.round_h) hn[u] = round_tf32(hn[u]);   // only feeds the next step's MMA
+          for (int i = 0; i < 8; ++i) {
+            if (xr[i] >= 0) {
+              const float4 g = staged(i);
+              const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
+              float cn, hn;
+              if (p.debug & 16) { cn = gf * c1[i] + gi * gg; hn = go * cn; }
+              else { cn = fast_sigmoid(gf) * c1[i] + fast_sigmoid(gi) * fast_tanh(gg); hn = fast_sigmoid(go) * fast_tanh(cn); }
+              if (p.round_h) hn = round_tf32(hn);         // only feeds the next step's MMA
+              if (!(p.debug & 8) || hn == 123.456f) {
+                p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
+                p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = hn;
+              }
             }
-            float* cw = crow + (cc >> 2);
-            float* hw = hrow + (cc >> 2);
-            *reinterpret_cast<float4*>(cw) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(cw + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-            *reinterpret_cast<float4*>(hw) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hw + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
           }
         };
-        prefetch(0, xa, ca);
+        if (p.debug != 1) prefetch(0, xa, ca);
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
-        // BN/2 = 128 gate columns = 4 chunks of 32 (8 hidden units x i,f,g,o)
-        prefetch(32, xb, cb);  compute(0, xa, ca);
-        prefetch(64, xa, ca);  compute(32, xb, cb);
-        prefetch(96, xb, cb);  compute(64, xa, ca);
-        compute(96, xb, cb);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        continue;
-      }
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+        if (p.debug != 1) {
+          prefetch(32, xb, cb);  compute(0, xa, ca);
+          prefetch(64, xa, ca);  compute(32, xb, cb);
+          prefetch(96, xb, cb);  compute(64, xa, ca);
+          compute(96, xb, cb);
+        }
+      } else {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 2; cc += 32) {
-        const int n = n0 + cc;
-        const bool ok = row_ok && n < p.N;
-        uint32_t r[32];
-        {
+        for (int cc = 0; cc < BN / 2; cc += 32) {
+          if (p.debug == 1) break;
+          uint32_t r[32];
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
-          if (ok) {
-            float* dst = p.out + m * p.ldo + n;
-            const float* res = p.residual ? p.residual + m * p.ldr + n : nullptr;
+          __syncwarp();
+          stage_rows(r);
+          __syncwarp();
+          const int n = n0 + cc + 4 * pch;
+          if (n < p.N) {                                  // N % 4 == 0
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n + j < p.N) {                        // N % 4 == 0
-                float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                if (p.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                }
-                if (res) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(res + j));
-                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            for (int i = 0; i < 8; ++i) {
+              const int64_t mr = m_base + 4 * i + prow;
+              if (mr < p.M) {
+                float4 v = staged(i);
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                if (p.residual) {
+                  const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + mr * p.ldr + n));
+                  v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
                 }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-                *reinterpret_cast<float4*>(dst + j) = v;
+                *reinterpret_cast<float4*>(p.out + mr * p.ldo + n) = v;
               }
             }
           }
@@ -314,6 +340,8 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
     TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
   }
+  static const int dbg = [] { const char* e = getenv("TMR_DEBUG_EPI"); return e ? atoi(e) : 0; }();
+  const_cast<GemmParams&>(p).debug = dbg;
   static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
