@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("TMR_MATH", "tf32"), choices=["fp32", "tf32"])
-    ap.add_argument("--batch", type=int, default=8192, help="clips per head launch sequence")
+    ap.add_argument("--batch", type=int, default=14336, help="clips per head launch sequence")
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

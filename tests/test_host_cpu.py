@@ -100,3 +100,17 @@ def test_bank_pickle_roundtrip(tmp_path):
     raw = pickle.load(open(p, "rb"))
     assert raw.dtype == np.float64 and raw.shape == (17, 512)
     assert np.array_equal(raw.astype(np.float32), bank)
+
+
+def test_export_matches_reference_format(tmp_path):
+    from tmrnet_b200.export import export_phase_files, phase_lines
+    lengths, seq = [12, 15], 10
+    preds = torch.arange(1, 10) % 7                     # 3 + 6 clips
+    lines = phase_lines(preds, lengths, seq)
+    assert lines == orc.export_phase_lines(preds.tolist(), lengths, seq)
+    assert lines[0][:10] == [f"{25 * k}\t0" for k in range(9)] + ["225\t1"]
+    paths = export_phase_files(preds, lengths, tmp_path, seq)
+    assert [os.path.basename(p) for p in paths] == ["video41-phase.txt", "video42-phase.txt"]
+    assert open(paths[1]).read().splitlines() == lines[1]
+    with pytest.raises(ValueError, match="number error"):
+        phase_lines(preds[:-1], lengths, seq)

@@ -551,3 +551,27 @@ def test_host_buffer_pass_equals_resident_pass():
     for k in ("logits", "pred", "score"):
         assert torch.equal(out[k], ref[k]), k
     assert torch.equal(pred_h, ref["pred"].cpu()) and torch.equal(score_h, ref["score"].cpu())
+
+
+def test_bank_builder_is_self_consistent_with_the_head():
+    """Bank built from features by the LSTM kernels (reference resnet_lstm_LFB loop, TRAIN:684-756):
+    row r equals the oracle LSTM state of the r-th valid clip, and a head pass over that bank agrees
+    with the oracle end to end."""
+    from tmrnet_b200.infer import BankInference, build_bank
+    dev = _dev()
+    lengths, seq, L = [40, 25, 61], 10, 30
+    feats = synth.features(sum(lengths), seed=31)
+    m = _model(7)
+    for mode in MODES:
+        _need_mode(mode)
+        bank = build_bank(m, torch.from_numpy(feats).to(dev), lengths, seq, batch_clips=50, math_mode=mode)
+        starts = synth.clip_starts(lengths, seq)
+        x = np.stack([feats[s:s + seq] for s in starts])
+        ref_bank = orc.lstm_last(x, _sd(7))
+        assert bank.shape == (len(starts), 512)
+        assert rel_err(bank, ref_bank) < TOL[mode]
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    out = BankInference(m, idx, seq, L, batch_clips=64, math_mode="fp32").run(torch.from_numpy(feats).to(dev), bank)
+    lf = orc.get_long_feature(starts, orc.build_start_dict(starts.tolist()), ref_bank.numpy(), L)
+    ref_logits = orc.head(x, lf, _sd(7))[0]
+    assert rel_err(out["logits"], ref_logits) < 2e-3      # bank itself came from the TF32 path

@@ -15,8 +15,11 @@
 // each = max(bank[rho], pool, conv3, conv5, conv7) with pool = bank[rho+1] (slot k-1) or 0 for v1
 // (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512]; attention_pb_kernel consumes it.
 // 236 MFLOP/clip become 7.9 MFLOP/row; only summation order changes.
-#include <stdlib.h>
-
+//
+// Tried and dropped (round 1): loading the 134 rows of a chunk once and taking the seven shifts as
+// row-offset views of that smem tile (descriptor start + n*128 B with the matrix-base-offset field)
+// produced wrong products on B200 and was no faster — the kernel is bound by bytes in flight per SM
+// (TMA latency x smem ring), not by the L2 traffic of the shifted loads.
 #include "tmr_internal.h"
 #include "umma_common.cuh"
 
@@ -33,16 +36,6 @@ constexpr int BC_STAGE_BYTES = BC_A_BYTES + 3 * BC_W_BYTES;   // 28 KB
 constexpr int BC_SMEM_BYTES = BC_STAGES * BC_STAGE_BYTES + 1024 + 256;
 constexpr int BC_THREADS = 192;
 constexpr int BC_TMEM_COLS = 512;
-// Variant SHIFT: the 134 bank rows rho0-3 .. rho0+130 of a chunk are loaded ONCE into a ring of A
-// buffers and the seven time shifts are taken as row-offset views of that buffer (descriptor start
-// address + (3-t)*128 B, matrix base offset = row phase inside the 1024-byte swizzle atom), instead
-// of seven separate TMA loads: 7x less activation traffic from L2.
-constexpr int BCS_A_ROWS = BC_BM + 6;
-constexpr int BCS_A_BYTES = 18 * 1024;                  // 134 rows x 128 B = 17 152, padded to 1 KB multiple
-constexpr int BCS_A_STAGES = 3;
-constexpr int BCS_W_STAGE_BYTES = 3 * BC_W_BYTES;       // 12 KB
-constexpr int BCS_W_STAGES = 10;
-constexpr int BCS_SMEM_BYTES = BCS_A_STAGES * BCS_A_BYTES + BCS_W_STAGES * BCS_W_STAGE_BYTES + 1024 + 512;
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
   uint32_t u[8];
@@ -58,35 +51,22 @@ __host__ __device__ constexpr int group_col(int t) {
   return t == -3 ? 0 : t == -2 ? 32 : t == -1 ? 96 : t == 0 ? 192 : t == 1 ? 288 : t == 2 ? 384 : 448;
 }
 
-// SWIZZLE_128B K-major descriptor whose start is a whole number of 128-byte rows into a 1024-byte
-// aligned tile: the row phase goes into the matrix-base-offset field (bits 49..51).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_rowshift(uint32_t smem_addr) {
-  return make_smem_desc_sw128(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
-}
-
 struct BankConvParams {
   const float* bank; float* pb; const float* bias3; const float* bias5; const float* bias7;
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
 };
 
-template <bool SHIFT>
 __global__ void __launch_bounds__(BC_THREADS, 1)
 umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w3,
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
                      const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // !SHIFT: BC_STAGES x [A 16 KB | W 12 KB].  SHIFT: BCS_A_STAGES x A 18 KB, then BCS_W_STAGES x W 12 KB.
-  constexpr int W_STAGES = SHIFT ? BCS_W_STAGES : BC_STAGES;
-  uint8_t* smem_w = smem + (SHIFT ? BCS_A_STAGES * BCS_A_BYTES : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (SHIFT ? BCS_A_STAGES * BCS_A_BYTES + BCS_W_STAGES * BCS_W_STAGE_BYTES
-                                                              : BC_STAGES * BC_STAGE_BYTES));
-  uint64_t* full_bar = bars;                       // [W_STAGES]
-  uint64_t* empty_bar = bars + W_STAGES;           // [W_STAGES]
-  uint64_t* acc_full = bars + 2 * W_STAGES;        // [1]
-  uint64_t* a_full = bars + 2 * W_STAGES + 1;      // [BCS_A_STAGES] (SHIFT only)
-  uint64_t* a_empty = a_full + BCS_A_STAGES;       // [BCS_A_STAGES]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + BCS_A_STAGES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BC_STAGES * BC_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + BC_STAGES;
+  uint64_t* acc_full = bars + 2 * BC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * BC_STAGES + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,8 +76,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
-    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < BCS_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -110,62 +89,42 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      int a_stage = 0; uint32_t a_phase = 0;
       for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
         const int c0 = chunk * BC_BK;
-        if (SHIFT) {                                   // one activation load per chunk: rows rho0-3 .. rho0+130
-          mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-          mbar_expect_tx(&a_full[a_stage], BCS_A_ROWS * BC_BK * 4);
-          tma_load_2d(smem + a_stage * BCS_A_BYTES, &tma_x, &a_full[a_stage], c0, (int)(rho0 - 3 - p.r_lo));
-          if (++a_stage == BCS_A_STAGES) { a_stage = 0; a_phase ^= 1; }
-        }
         for (int t = -3; t <= 3; ++t) {
           const int at = t < 0 ? -t : t;
           const int n_w = (at <= 1) ? 3 : (at == 2 ? 2 : 1);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * BC_STAGE_BYTES;
-          uint8_t* sw = SHIFT ? smem_w + stage * BCS_W_STAGE_BYTES : sa + BC_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], (SHIFT ? 0 : BC_A_BYTES) + n_w * BC_W_BYTES);
-          if (!SHIFT) tma_load_2d(sa, &tma_x, &full_bar[stage], c0, (int)(rho0 - t - p.r_lo));   // rows rho - t (OOB -> 0)
+          uint8_t* sw = sa + BC_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], BC_A_BYTES + n_w * BC_W_BYTES);
+          tma_load_2d(sa, &tma_x, &full_bar[stage], c0, (int)(rho0 - t - p.r_lo));   // rows rho - t (OOB -> 0)
           tma_load_2d(sw + 0 * BC_W_BYTES, &tma_w7, &full_bar[stage], (t + 3) * kD + c0, n0);
           if (n_w >= 2) tma_load_2d(sw + 1 * BC_W_BYTES, &tma_w5, &full_bar[stage], (t + 2) * kD + c0, n0);
           if (n_w >= 3) tma_load_2d(sw + 2 * BC_W_BYTES, &tma_w3, &full_bar[stage], (t + 1) * kD + c0, n0);
-          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      int a_stage = 0; uint32_t a_phase = 0;
       for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
-        if (SHIFT) { mbar_wait(&a_full[a_stage], a_phase); tc_fence_after(); }
         for (int t = -3; t <= 3; ++t) {
           const int at = t < 0 ? -t : t;
           const int n_w = (at <= 1) ? 3 : (at == 2 ? 2 : 1);
           const uint32_t idesc = make_idesc_tf32(BC_BM, n_w * BC_NCH);           // one MMA covers every conv of the shift
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          uint64_t da, db;
-          if (SHIFT) {
-            // bank row rho0 - t is row (3 - t) of the 134-row buffer
-            da = make_smem_desc_sw128_rowshift(smem_u32(smem + a_stage * BCS_A_BYTES) + (uint32_t)(3 - t) * 128u);
-            db = make_smem_desc_sw128(smem_u32(smem_w + stage * BCS_W_STAGE_BYTES));
-          } else {
-            const uint32_t sa = smem_u32(smem + stage * BC_STAGE_BYTES);
-            da = make_smem_desc_sw128(sa);
-            db = make_smem_desc_sw128(sa + BC_A_BYTES);                          // tap tiles are stacked along N
-          }
+          const uint32_t sa = smem_u32(smem + stage * BC_STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + BC_A_BYTES);             // tap tiles are stacked along N
           const uint32_t d_tmem = tmem_base + (uint32_t)group_col(t);
 #pragma unroll
           for (int k = 0; k < BC_BK / 8; ++k)
             mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (chunk | k) != 0);
           mma_commit(&empty_bar[stage]);
-          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (SHIFT) {
-          mma_commit(&a_empty[a_stage]);                                         // all 7 shifts of the chunk issued
-          if (++a_stage == BCS_A_STAGES) { a_stage = 0; a_phase ^= 1; }
+          if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
       mma_commit(acc_full);
@@ -253,7 +212,6 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
   using namespace umma;
   if (pb_rows <= 0) return TMR_OK;
   TMR_CHECK_ARG(n_rows < (int64_t)INT32_MAX - 256, "bankconv: bank too large");
-  static const bool shift = [] { const char* e = getenv("TMR_BANKCONV_SHIFT"); return e ? atoi(e) != 0 : false; }();
   BankConvParams p{};
   p.bank = bank; p.pb = pb;
   p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
@@ -262,7 +220,7 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
     uint64_t str[1] = {(uint64_t)kD * 4};
-    uint32_t box[2] = {BC_BK, (uint32_t)(shift ? BCS_A_ROWS : BC_BM)};
+    uint32_t box[2] = {BC_BK, BC_BM};
     TMR_TRY(make_tmap(&tx, bank_r, 2, dims, str, box));
     const float* pr = packed + TimeConvPacked::fp32_total;
     const float* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
@@ -275,14 +233,9 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
       TMR_TRY(make_tmap(tw[i], w[i], 2, dw, sw, bw));
     }
   }
+  TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
   const int64_t tiles = ((pb_rows + BC_BM - 1) / BC_BM) * (kD / BC_NCH);
-  if (shift) {
-    TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BCS_SMEM_BYTES));
-    umma_bankconv_kernel<true><<<(unsigned)tiles, BC_THREADS, BCS_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, p);
-  } else {
-    TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
-    umma_bankconv_kernel<false><<<(unsigned)tiles, BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, p);
-  }
+  umma_bankconv_kernel<<<(unsigned)tiles, BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, p);
   TMR_LAUNCH_CHECK("umma_bankconv_kernel");
   return TMR_OK;
 }

@@ -65,7 +65,6 @@ struct GemmParams {
   const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
-  int debug;   // experiments only (TMR_DEBUG_EPI): 1 = skip epilogue global I/O, 2 = skip TMEM loads too
 };
 
 // Gate non-linearities of the tensor-core path: MUFU ex2/rcp approximations (2 ulp / 1 ulp), four
@@ -223,10 +222,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         auto prefetch = [&](int cc, float4 (&x4)[8], float (&c1)[8]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (xr[i] >= 0 && !(p.debug & 4)) {
+            if (xr[i] >= 0) {
               x4[i] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc));
               c1[i] = p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)];
-            } else { x4[i] = make_float4(0.f, 0.f, 0.f, 0.f); c1[i] = 0.f; }
+            }
           }
         };
         auto compute = [&](int cc, const float4 (&x4)[8], const float (&c1)[8]) {
@@ -241,21 +240,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (xr[i] >= 0) {
               const float4 g = staged(i);
               const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
-              float cn, hn;
-              if (p.debug & 16) { cn = gf * c1[i] + gi * gg; hn = go * cn; }
-              else { cn = fast_sigmoid(gf) * c1[i] + fast_sigmoid(gi) * fast_tanh(gg); hn = fast_sigmoid(go) * fast_tanh(cn); }
+              const float cn = fast_sigmoid(gf) * c1[i] + fast_sigmoid(gi) * fast_tanh(gg);
+              float hn = fast_sigmoid(go) * fast_tanh(cn);
               if (p.round_h) hn = round_tf32(hn);         // only feeds the next step's MMA
-              if (!(p.debug & 8) || hn == 123.456f) {
-                p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
-                p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = hn;
-              }
+              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
+              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = hn;
             }
           }
         };
-        if (p.debug != 1) prefetch(0, xa, ca);
+        prefetch(0, xa, ca);
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
-        if (p.debug != 1) {
+        {
           prefetch(32, xb, cb);  compute(0, xa, ca);
           prefetch(64, xa, ca);  compute(32, xb, cb);
           prefetch(96, xb, cb);  compute(64, xa, ca);
@@ -266,7 +262,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc_fence_after();
 #pragma unroll 1
         for (int cc = 0; cc < BN / 2; cc += 32) {
-          if (p.debug == 1) break;
           uint32_t r[32];
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
@@ -340,8 +335,6 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
     TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
   }
-  static const int dbg = [] { const char* e = getenv("TMR_DEBUG_EPI"); return e ? atoi(e) : 0; }();
-  const_cast<GemmParams&>(p).debug = dbg;
   static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;

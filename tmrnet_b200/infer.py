@@ -24,7 +24,7 @@ class BankInference:
     index: LFBIndex.from_lengths(video_lengths, seq) for the same frames/rows.
     """
 
-    def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 8192,
+    def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 14336,
                  pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True):
         self.model = model
         self.index = index
@@ -274,3 +274,39 @@ class VideoShard:
         from .lfb import get_useful_start_idx
         s = np.asarray(get_useful_start_idx(self.seq, self.local_lengths), dtype=np.int64)
         return s[s >= self.own_frame_lo - self.frame_lo]
+
+
+# ---------------------------------------------------------------------------------------------
+# upstream of the path: bank builder
+# ---------------------------------------------------------------------------------------------
+def build_bank(lfb_model, feats, list_each_length, seq: int = 10, batch_clips: int = 14336, math_mode=None):
+    """The reference's LFB construction loop (train_non-local_mutiConv_resnet.py:684-756) with the
+    backbone features precomputed: one LSTM pass per valid clip start, h at the last step written
+    straight into the device bank (row r = r-th valid start in global order) instead of growing a
+    numpy array with np.concatenate.  lfb_model: tmrnet_b200.resnet_lstm_LFB (or resnet_lstm)."""
+    from .lfb import get_useful_start_idx
+    feats = _dev(feats, "feats")
+    starts_host = np.asarray(get_useful_start_idx(seq, list_each_length), dtype=np.int64)
+    if feats.shape[0] != int(sum(int(v) for v in list_each_length)):
+        raise ValueError("feats rows must equal the total number of frames")
+    dev = feats.device
+    packed = lfb_model.packed() if hasattr(lfb_model, "packed") else lfb_model.packs()[0]
+    bank = torch.empty((len(starts_host), D), dtype=torch.float32, device=dev)
+    starts = torch.from_numpy(starts_host).to(dev)
+    lib = _lib.load()
+    mode = _mode(math_mode if math_mode is not None else getattr(lfb_model, "math_mode", None))
+    ws = None
+    with torch.cuda.device(dev):
+        for lo in range(0, len(starts_host), batch_clips):
+            hi = min(len(starts_host), lo + batch_clips)
+            fl, fh = int(starts_host[lo]), int(starts_host[hi - 1]) + seq
+            need = lib.tmr_lstm_workspace_bytes(fh - fl, hi - lo, D)
+            if ws is None or ws.numel() < need:
+                ws = _ws(need, dev)
+            # rows are addressed relative to frame fl: pass local starts through a shifted copy
+            local = starts[lo:hi] - fl
+            check(lib.tmr_lstm_last_frames_fwd(_ptr(packed), C.c_void_p(feats.data_ptr() + fl * F * 4), fh - fl,
+                                               _ptr(local), hi - lo, int(seq), F, D,
+                                               C.c_void_p(bank.data_ptr() + lo * D * 4), _ptr(ws), ws.numel(), mode,
+                                               _stream()))
+    return bank
