@@ -40,6 +40,11 @@ WORKLOAD = ("train_non-local_mutiConv_resnet.py head (LSTM 2048->512 x10 + TimeC
 FLOP_TIMECONV = 2 * 512 * 512 * 30 * 15          # 235.93 MFLOP
 BYTES_GATHER = 2 * 30 * 512 * 4                  # 122 880 B
 BYTES_RELATION = 30 * 512 * 4 + 2 * 512 * 4      # 65 536 B
+FLOP_LSTM_STEP = 2 * 4 * 512 * 512               # 2.097 MFLOP per clip per recurrent step
+FLOP_BANKCONV_ROW = 2 * 512 * 512 * 15           # 7.864 MFLOP per bank row (TimeConv deduplicated per row)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
+# ncu --set full capture (profiles/); None until that capture exists for the current kernel
+NCU_TRAFFIC_LSTM_STEP = None
 
 
 def peaks():
@@ -246,8 +251,7 @@ def run_ours(args):
             st = torch.from_numpy(eng.starts_host[:B]).to(dev)
             f2r, f2v = index.device_tables(dev)
             packs = model.packs()
-            win = ops.gather_windows(bank_dev, f2r, st, L)
-            St = torch.from_numpy(synth.bank(B, seed=5)).to(dev)
+            fr = feats_dev[: int(eng.starts_host[B - 1]) + SEQ]
 
             def timeit(fn, reps):
                 for _ in range(3):
@@ -261,13 +265,24 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 return a.elapsed_time(b) / reps
 
-            t_tc = timeit(lambda: ops.timeconv_max(packs[1], win), 5)
-            t_g = timeit(lambda: ops.gather_windows(bank_dev, f2r, st, L), 20)
-            t_nl = timeit(lambda: ops.nlblock(packs[2], St, win), 20)
+            # LSTM: full recurrence minus the seq=1 pass (projection + step 0) = 9 recurrent-step launches
+            t_l10 = timeit(lambda: ops.lstm_last_frames(packs[0], fr, st, SEQ), 10)
+            t_l1 = timeit(lambda: ops.lstm_last_frames(packs[0], fr, st, 1), 10)
+            t_step = (t_l10 - t_l1) / (SEQ - 1)
+            t_bc = timeit(lambda: ops.bankconv(packs[1], bank_dev, 0, B + L), 10)
+            # HBM-bound kernels on windows that do NOT dedupe in L2: random clip starts over the whole bank
+            rnd = torch.from_numpy(np.random.default_rng(0).permutation(eng.starts_host)[:B].copy()).to(dev)
+            t_g = timeit(lambda: ops.gather_windows(bank_dev, f2r, rnd, L), 20)
+            win = ops.gather_windows(bank_dev, f2r, rnd, L)
+            u = torch.from_numpy(synth.bank(B, seed=5)).to(dev)
+            t_at = timeit(lambda: ops.attention(u, win), 20)
+            t_tc = timeit(lambda: ops.timeconv_max(packs[1], win), 3)
             kern = {
-                "timeconv": {"ms": t_tc, "tflops": FLOP_TIMECONV * B / t_tc / 1e9, "clips": B},
+                "lstm_step": {"ms": t_step, "tflops": FLOP_LSTM_STEP * B / t_step / 1e9, "clips": B},
+                "bankconv": {"ms": t_bc, "tflops": FLOP_BANKCONV_ROW * (B + L) / t_bc / 1e9, "rows": B + L},
+                "timeconv_per_clip": {"ms": t_tc, "tflops": FLOP_TIMECONV * B / t_tc / 1e9, "clips": B},
                 "gather": {"ms": t_g, "gbs": BYTES_GATHER * B / t_g / 1e6, "clips": B},
-                "nlblock": {"ms": t_nl, "gbs": BYTES_RELATION * B / t_nl / 1e6, "clips": B},
+                "attention": {"ms": t_at, "gbs": BYTES_RELATION * B / t_at / 1e6, "clips": B},
             }
 
     # ---- max over ranks ----
@@ -285,16 +300,25 @@ def run_ours(args):
         pk = peaks()
         value = total_clips * args.steps / (ms / 1e3)
         e2e_v = total_clips * args.steps / (ms_e2e / 1e3)
-        tc = kern["timeconv"]
-        roof = {"kernel": "timeconv_max (3 temporal convs as implicit GEMM + 5-way max)", "bound": "tensor",
-                "achieved": tc["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tc["tflops"] / pk["tensor"],
-                "traffic": None, "peak_source": pk["source"] + " bf16 burst (TF32 issues at half that rate)",
-                "algorithmic_flop_per_clip": FLOP_TIMECONV, "clips_per_launch": tc["clips"], "ms_per_launch": tc["ms"],
-                "hbm_kernels": {
-                    "gather": {"achieved": kern["gather"]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                               "frac": kern["gather"]["gbs"] / pk["hbm"], "bytes_per_clip": BYTES_GATHER},
-                    "nlblock": {"achieved": kern["nlblock"]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                                "frac": kern["nlblock"]["gbs"] / pk["hbm"], "bytes_per_clip": BYTES_RELATION}}}
+        ls = kern["lstm_step"]
+        def hbm(k, bpc):
+            return {"achieved": kern[k]["gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": kern[k]["gbs"] / pk["hbm"],
+                    "bytes_per_clip": bpc, "ms_per_launch": kern[k]["ms"], "clips_per_launch": kern[k]["clips"],
+                    "inputs": "random clip starts over the whole bank (no L2 dedupe of window rows)"}
+        def tens(k, unit_flop, units):
+            return {"achieved": kern[k]["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": kern[k]["tflops"] / pk["tensor"], "algorithmic_flop_per_unit": unit_flop,
+                    "units_per_launch": units, "ms_per_launch": kern[k]["ms"]}
+        roof = {"kernel": "umma_gemm_kernel<EPI_LSTM> (recurrent step h.Whh^T + LSTM cell epilogue; 9 launches per batch, "
+                          "largest share of the step, see profiles/)",
+                "bound": "tensor", "achieved": ls["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ls["tflops"] / pk["tensor"], "traffic": NCU_TRAFFIC_LSTM_STEP,
+                "peak_source": pk["source"] + " bf16 burst (TF32 issues at half that rate: 0.5 is the TF32 ceiling)",
+                "algorithmic_flop_per_clip": FLOP_LSTM_STEP, "clips_per_launch": ls["clips"], "ms_per_launch": ls["ms"],
+                "how": "CUDA events: (10-step LSTM - 1-step LSTM) / 9 on one batch",
+                "tensor_kernels": {"bankconv": tens("bankconv", FLOP_BANKCONV_ROW, kern["bankconv"]["rows"]),
+                                   "timeconv_per_clip": tens("timeconv_per_clip", FLOP_TIMECONV, kern["timeconv_per_clip"]["clips"])},
+                "hbm_kernels": {"gather": hbm("gather", BYTES_GATHER), "attention": hbm("attention", BYTES_RELATION)}}
         cpu = None
         if world == 1 and not args.no_cpu:
             r = cpu_head_rate(256, iters=args.cpu_iters, warmup=1)

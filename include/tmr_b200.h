@@ -105,6 +105,9 @@ int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D
 
 /* ---- a6: NLBlock.forward, eval mode (NLB:25-40) -----------------------------------------------
  * St (B,D), Lt (B,L,D) -> out (B,D).  workspace >= tmr_nlblock_workspace_bytes(B,D). */
+/* The HBM-bound core of the relation block alone (NLB:30-34 with phi/g folded): for the folded query
+ * u (B,D) = W2^T (W1 St + b1): out[b] = sum_k softmax_k((1/512)**0.5 * u[b].Lt[b,k]) Lt[b,k]  (B,D). */
+int tmr_attention_fwd(const float* u, const float* Lt, int B, int L, int D, float* out, void* stream);
 size_t tmr_nlblock_workspace_bytes(int B, int D);
 int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B, int L, int D,
                     float* out, void* workspace, size_t workspace_bytes, int math_mode,

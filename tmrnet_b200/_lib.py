@@ -35,6 +35,7 @@ SIGNATURES = {
     "tmr_classifier_pack": (_i, [_p] * 4 + [_i, _i, _p, _p]),
     "tmr_timeconv_workspace_bytes": (_sz, [_i, _i, _i]),
     "tmr_timeconv_max_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _i, _p]),
+    "tmr_attention_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "tmr_nlblock_workspace_bytes": (_sz, [_i, _i]),
     "tmr_nlblock_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _sz, _i, _p]),
     "tmr_lstm_workspace_bytes": (_sz, [_i64, _i, _i]),

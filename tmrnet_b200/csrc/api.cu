@@ -261,6 +261,14 @@ int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D
   return timeconv_impl((const float*)packed, x, B, L, out, xr, math_mode, (cudaStream_t)stream);
 }
 
+int tmr_attention_fwd(const float* u, const float* Lt, int B, int L, int D, float* out, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_CHECK_ARG(B >= 0 && L >= 1, "attention: bad B=%d L=%d", B, L);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(u && Lt && out && aligned16(u) && aligned16(Lt) && aligned16(out), "attention: null or unaligned pointer");
+  return launch_attention(u, Lt, B, L, out, 0, (cudaStream_t)stream);
+}
+
 size_t tmr_nlblock_workspace_bytes(int B, int D) { return 3 * fbytes((size_t)(B > 0 ? B : 1) * D); }
 int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B, int L, int D,
                     float* out, void* workspace, size_t workspace_bytes, int math_mode, void* stream) {

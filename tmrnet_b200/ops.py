@@ -258,3 +258,14 @@ def bankconv(timeconv_packed, bank, row_base: int = 0, pb_rows: int = None):
         check(lib.tmr_bankconv_fwd(_ptr(timeconv_packed), _ptr(bank), bank.shape[0], int(row_base), int(pb_rows), D,
                                    _ptr(pb), _ptr(ws), ws.numel(), _stream()))
     return pb
+
+
+def attention(u, Lt):
+    """softmax-over-L weighted sum for a folded query u (B,512) over Lt (B,L,512) -> (B,512)."""
+    u = _dev(u, "u")
+    Lt = _dev(Lt, "Lt")
+    B, L, _ = Lt.shape
+    out = torch.empty((B, D), dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        check(_lib.load().tmr_attention_fwd(_ptr(u), _ptr(Lt), B, L, D, _ptr(out), _stream()))
+    return out
