@@ -195,6 +195,27 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
                               float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* ---- a10: head training step (TRAIN:780,856-887) ----------------------------------------------
+ * Forward in training mode + full backward of the head, fp32.  params/grads: 24 DEVICE pointers in
+ * reference state-dict order and layouts:
+ *   lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
+ *   time_conv.timeconv{1,2,3}.{weight,bias} (NULL x6 for the NL-only wiring),
+ *   nl_block.linear{1..4}.{weight,bias}, nl_block.layer_norm.{weight,bias}, fc_h_c.{weight,bias}, fc_c.{weight,bias}.
+ * x (B,seq,F) backbone features and long_feature (B,L,D) carry no gradient (frozen features / bank).
+ * Loss = CrossEntropyLoss(reduction='sum', weight=class_weight (nullable)) as TRAIN:780,883.
+ * Dropout: p_nl on the NLBlock output (0.2, NLB:18,38), p_fc after fc_h_c (0.5, TRAIN:228,250); masks
+ * come from a counter-based generator keyed by `seed` (pass 0/0 for the deterministic eval-graph grads).
+ * grads are overwritten; logits (B,C), loss (1 float), pred int64[B] (nullable) are outputs. */
+size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C);
+int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                           const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
+                           float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* torch.optim.SGD update on one flat fp32 tensor (momentum, weight decay, dampening 0, no nesterov),
+ * TRAIN:797-805,887:  d = g + wd*p ; buf = first_step ? d : momentum*buf + d ; p -= lr*buf. */
+int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                 float weight_decay, int first_step, void* stream);
+
 /* ---- generic fp32 linear used by the stages above (exposed for tests) --------------------------
  * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N. */
 int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,

@@ -86,3 +86,38 @@ def test_two_rank_gloo_shards_equal_global():
     glob = orc.window_rows(starts, orc.build_start_dict(starts), L)
     assert np.array_equal(got[:, 0], np.asarray(starts))
     assert np.array_equal(got[:, 1:], glob)
+
+
+# ---- training collective plumbing: flat gradient bucket + SUM all-reduce (gloo on CPU) ----
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tmrnet_b200.train import FlatBuffer
+    shapes = [(4, 3), None, (7,), (2, 2, 5)]
+    fbuf = FlatBuffer(shapes, "cpu")
+    for i, v in enumerate(fbuf.views):
+        if v is not None:
+            v.copy_(torch.full(v.shape, float(rank + 1) * (i + 1)))
+    dist.all_reduce(fbuf.flat, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put([None if v is None else v.clone().numpy() for v in fbuf.views])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_allreduce_sum_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[1] is None
+    for i in (0, 2, 3):
+        assert np.all(got[i] == 3.0 * (i + 1))          # (1 + 2) * (i + 1)
+    assert got[3].shape == (2, 2, 5)

@@ -1,0 +1,128 @@
+"""Head training step (a10): gradients of the hand-written backward against torch autograd over the
+oracle graph (fp64, dropout off), union-batch equivalence of summed per-rank gradients, and the SGD
+update against torch.optim.SGD."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as Fn
+
+import tmr_oracle as orc
+import tmrnet_b200 as tb
+from tmrnet_b200 import synth
+from tmrnet_b200.train import PARAM_ORDER, HeadTrainer
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(C=8, B=12, L=30, seq=10, seed=3, use_timeconv=True):
+    dev = torch.device("cuda:0")
+    sd = synth.head_state_dict(num_class=C, seed=seed)
+    if not use_timeconv:
+        sd = {k: v for k, v in sd.items() if not k.startswith("time_conv.")}
+    m = tb.resnet_lstm(num_class=C, sequence_length=seq, use_timeconv=use_timeconv)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(dev)
+    rng = np.random.default_rng(seed)
+    x = synth.features(B * seq, seed=seed).reshape(B, seq, 2048)
+    lf = synth.bank(B * L, seed=seed + 1).reshape(B, L, 512)
+    labels = rng.integers(0, C, size=B)
+    cw = (0.5 + rng.random(C)).astype(np.float32)
+    return dev, sd, m, x, lf, labels, cw
+
+
+def _autograd_reference(sd, x, lf, labels, cw, use_timeconv=True):
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in sd.items()}
+    logits = orc.head(torch.from_numpy(x).double(), torch.from_numpy(lf).double(), _NoDetach(P), use_timeconv, torch.float64)[0]
+    loss = Fn.cross_entropy(logits, torch.from_numpy(labels), weight=torch.from_numpy(cw).double(), reduction="sum")
+    loss.backward()
+    return loss.detach(), logits.detach(), {k: p.grad for k, p in P.items()}
+
+
+class _NoDetach(dict):
+    """orc._t() detaches plain tensors; hand it parameters through a mapping whose values are kept."""
+
+
+def _patch_oracle(monkeypatch):
+    def keep(x, dtype=torch.float32):
+        if isinstance(x, torch.Tensor):
+            return x.to(dtype)
+        return torch.from_numpy(np.ascontiguousarray(x)).to(dtype)
+    monkeypatch.setattr(orc, "_t", keep)
+
+
+@pytest.mark.parametrize("use_timeconv", [True, False])
+def test_gradients_match_autograd(monkeypatch, use_timeconv):
+    _patch_oracle(monkeypatch)
+    dev, sd, m, x, lf, labels, cw = _setup(use_timeconv=use_timeconv)
+    ref_loss, ref_logits, ref_g = _autograd_reference(sd, x, lf, labels, cw, use_timeconv)
+    tr = HeadTrainer(m, class_weight=cw)
+    loss, logits, pred = tr.forward_backward(torch.from_numpy(x).to(dev), torch.from_numpy(lf).to(dev),
+                                             torch.from_numpy(labels).to(dev), dropout=False)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    assert float((logits.cpu().double() - ref_logits).abs().max()) < 1e-5
+    assert torch.equal(pred.cpu(), ref_logits.argmax(1))
+    for i, k in enumerate(PARAM_ORDER):
+        if k not in sd:
+            continue
+        g = tr.grads.views[i].cpu().double()
+        r = ref_g[k].reshape(g.shape)
+        scale = float(r.abs().max())
+        if k == "nl_block.linear2.bias":            # exactly zero analytically (softmax shift invariance)
+            assert float(g.abs().max()) == 0.0 and scale < 1e-9
+            continue
+        err = float((g - r).abs().max())
+        assert err <= 2e-4 * scale + 1e-7, (k, err, scale)
+
+
+def test_summed_rank_gradients_equal_union_batch():
+    """Loss is sum-reduced: grads(A) + grads(B) == grads(A u B) -> all-reduce SUM reproduces 1-GPU training."""
+    dev, sd, m, x, lf, labels, cw = _setup(B=16)
+    tr = HeadTrainer(m, class_weight=cw)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    tr.forward_backward(X, LF, Y, dropout=False)
+    full = tr.grads.flat.clone()
+    tr.forward_backward(X[:7], LF[:7], Y[:7], dropout=False)
+    part = tr.grads.flat.clone()
+    tr.forward_backward(X[7:], LF[7:], Y[7:], dropout=False)
+    part += tr.grads.flat
+    assert float((part - full).abs().max()) <= 2e-5 * float(full.abs().max())
+
+
+def test_sgd_update_matches_torch_and_invalidates_packs():
+    dev, sd, m, x, lf, labels, cw = _setup(B=8, C=7)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    tr = HeadTrainer(m, lr=1e-3, momentum=0.9, weight_decay=5e-4, lstm_lr_scale=0.1, class_weight=cw)
+    named = dict(m.named_parameters())
+    ref = {k: named[k].detach().clone() for k in PARAM_ORDER}
+    opt = torch.optim.SGD([{"params": [ref[k] for k in PARAM_ORDER if k.startswith("lstm.")], "lr": 1e-4},
+                           {"params": [ref[k] for k in PARAM_ORDER if not k.startswith("lstm.")]}],
+                          lr=1e-3, momentum=0.9, weight_decay=5e-4, dampening=0)
+    with torch.no_grad():
+        before = m.eval()(X, LF).clone()
+    for step in range(3):
+        tr.forward_backward(X, LF, Y, dropout=False)
+        for i, k in enumerate(PARAM_ORDER):
+            ref[k].grad = tr.grads.views[i].detach().clone().reshape(ref[k].shape)
+        opt.step()
+        tr.sgd_update()
+        for k in PARAM_ORDER:
+            assert torch.allclose(named[k].detach(), ref[k], rtol=1e-6, atol=1e-8), (step, k)
+    with torch.no_grad():
+        after = m.eval()(X, LF)
+    assert not torch.equal(before, after)          # inference caches were refreshed after the update
+
+
+def test_dropout_masks_are_seeded_and_scaled():
+    dev, sd, m, x, lf, labels, cw = _setup(B=8, C=7)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    a = HeadTrainer(m, class_weight=cw, seed=5)
+    l1, _, _ = a.forward_backward(X, LF, Y)
+    g1 = a.grads.flat.clone()
+    l2, _, _ = a.forward_backward(X, LF, Y)
+    assert torch.equal(g1, a.grads.flat) and torch.equal(l1, l2)       # same (seed, step) -> same masks
+    b = HeadTrainer(m, class_weight=cw, seed=6)
+    l3, _, _ = b.forward_backward(X, LF, Y)
+    assert not torch.equal(g1, b.grads.flat)
+    l0, _, _ = a.forward_backward(X, LF, Y, dropout=False)
+    assert float(l0) != float(l1)

@@ -1,0 +1,556 @@
+// Head training step: forward in training mode + full backward of the TMRNet
+// head, fp32 on CUDA cores (training batches are tens to a few hundred clips: launch-bound, so the
+// register-tiled FFMA GEMM of sgemm_simt.cuh is used for every product, with explicit transposes for
+// the dX = dY.W and dW = dY^T.X forms).  Reference: resnet_lstm.forward in training mode
+// (train_non-local_mutiConv_resnet.py:237-253), CrossEntropyLoss(reduction='sum', weight) (:780,883),
+// loss.backward() (:886); NLBlock / TimeConv (NLBlock_MutiConv6_3.py:10-79); torch.nn.LSTM.
+// Backbone features and the memory bank are inputs without gradient (frozen features).
+//
+// Parameter / gradient order (24 tensors, reference state-dict layouts):
+//   0 lstm.weight_ih_l0 (4D,F)  1 lstm.weight_hh_l0 (4D,D)  2 lstm.bias_ih_l0  3 lstm.bias_hh_l0
+//   4 timeconv1.weight (D,D,3)  5 .bias   6 timeconv2.weight (D,D,5)  7 .bias   8 timeconv3.weight (D,D,7)  9 .bias
+//   10 nl.linear1.weight 11 .bias 12 nl.linear2.weight 13 .bias 14 nl.linear3.weight 15 .bias 16 nl.linear4.weight 17 .bias
+//   18 nl.layer_norm.weight (1,D) 19 .bias   20 fc_h_c.weight (D,2D) 21 .bias   22 fc_c.weight (C,D) 23 .bias
+#include "tmr_internal.h"
+
+namespace tmr {
+namespace train {
+
+static inline size_t fb(size_t n) { return align_up(n * sizeof(float), 256); }
+static inline int64_t pad16(int64_t v) { return (v + 15) / 16 * 16; }
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+#define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+static inline unsigned nblk(int64_t n) { int64_t b = (n + 255) / 256; return (unsigned)(b < 1 ? 1 : (b > 8192 ? 8192 : b)); }
+
+// dst[c][r] = src[r][c] for r < R, 0 for R <= r < Rpad.   src: R x Ccols (ld), dst: Ccols x Rpad
+__global__ void transpose_pad_kernel(const float* __restrict__ src, int64_t R, int Ccols, int64_t ld, float* __restrict__ dst, int64_t Rpad) {
+  __shared__ float t[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i; const int c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < R && c < Ccols) ? src[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i; const int64_t r = r0 + threadIdx.x;
+    if (c < Ccols && r < Rpad) dst[(int64_t)c * Rpad + r] = t[threadIdx.x][i];
+  }
+}
+static int transpose_pad(const float* src, int64_t R, int Ccols, int64_t ld, float* dst, int64_t Rpad, cudaStream_t st) {
+  dim3 grid((Ccols + 31) / 32, (unsigned)((Rpad + 31) / 32));
+  transpose_pad_kernel<<<grid, dim3(32, 8), 0, st>>>(src, R, Ccols, ld, dst, Rpad);
+  TMR_LAUNCH_CHECK("transpose_pad_kernel");
+  return TMR_OK;
+}
+
+// out[c] (+)= sum_r X[r][c] (* Y[r][c])
+__global__ void colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t R, int Ccols, int64_t ld,
+                              float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float part[8][33];
+  float s = 0.f;
+  if (c < Ccols)
+    for (int64_t r = threadIdx.y; r < R; r += blockDim.y) s += Y ? X[r * ld + c] * Y[r * ld + c] : X[r * ld + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < Ccols) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += part[i][threadIdx.x];
+    out[c] = accumulate ? out[c] + tsum : tsum;
+  }
+}
+static int colsum(const float* X, const float* Y, int64_t R, int Ccols, int64_t ld, float* out, int accumulate, cudaStream_t st) {
+  colsum_kernel<<<(Ccols + 31) / 32, dim3(32, 8), 0, st>>>(X, Y, R, Ccols, ld, out, accumulate);
+  TMR_LAUNCH_CHECK("colsum_kernel");
+  return TMR_OK;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = a[i] + b[i]; }
+__global__ void copy_vec_kernel(const float* a, float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = a[i]; }
+__global__ void zero_kernel(float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = 0.f; }
+// (B,S,F) -> (S,B,F)
+__global__ void permute_bsf_kernel(const float* __restrict__ x, int B, int S, int Fw, float* __restrict__ o) {
+  const int64_t n = (int64_t)B * S * Fw;
+  GRID_STRIDE(i, n) {
+    const int f = (int)(i % Fw); const int64_t r = i / Fw; const int b = (int)(r % B); const int t = (int)(r / B);
+    o[i] = x[((int64_t)b * S + t) * Fw + f];
+  }
+}
+
+__device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
+
+// LSTM cell, training forward: pre = xp (+ hh); standard gate order i,f,g,o in 4 blocks of D columns.
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ xp, const float* __restrict__ hh, const float* __restrict__ c_prev,
+                                     float* __restrict__ gates, float* __restrict__ c, float* __restrict__ h, int B) {
+  const int64_t n = (int64_t)B * kD;
+  GRID_STRIDE(idx, n) {
+    const int64_t b = idx / kD; const int u = (int)(idx % kD);
+    const float* xr = xp + b * 4 * kD; const float* hr = hh ? hh + b * 4 * kD : nullptr;
+    const float pi = xr[u] + (hr ? hr[u] : 0.f), pf = xr[kD + u] + (hr ? hr[kD + u] : 0.f);
+    const float pg = xr[2 * kD + u] + (hr ? hr[2 * kD + u] : 0.f), po = xr[3 * kD + u] + (hr ? hr[3 * kD + u] : 0.f);
+    const float gi = sigm(pi), gf = sigm(pf), gg = tanhf(pg), go = sigm(po);
+    const float cn = gf * (c_prev ? c_prev[idx] : 0.f) + gi * gg;
+    float* gr = gates + b * 4 * kD;
+    gr[u] = gi; gr[kD + u] = gf; gr[2 * kD + u] = gg; gr[3 * kD + u] = go;
+    c[idx] = cn; h[idx] = go * tanhf(cn);
+  }
+}
+// backward of one cell: dh, dc (in: from t+1, out: for t-1) -> dpre (B,4D)
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, float* __restrict__ dc, const float* __restrict__ gates,
+                                     const float* __restrict__ c, const float* __restrict__ c_prev, float* __restrict__ dpre, int B) {
+  const int64_t n = (int64_t)B * kD;
+  GRID_STRIDE(idx, n) {
+    const int64_t b = idx / kD; const int u = (int)(idx % kD);
+    const float* gr = gates + b * 4 * kD;
+    const float gi = gr[u], gf = gr[kD + u], gg = gr[2 * kD + u], go = gr[3 * kD + u];
+    const float tc = tanhf(c[idx]);
+    const float dhv = dh[idx];
+    const float dcv = dc[idx] + dhv * go * (1.f - tc * tc);
+    float* dr = dpre + b * 4 * kD;
+    dr[u] = dcv * gg * gi * (1.f - gi);
+    dr[kD + u] = dcv * (c_prev ? c_prev[idx] : 0.f) * gf * (1.f - gf);
+    dr[2 * kD + u] = dcv * gi * (1.f - gg * gg);
+    dr[3 * kD + u] = dhv * tc * go * (1.f - go);
+    dc[idx] = dcv * gf;
+  }
+}
+
+// TimeConv training forward on precomputed conv outputs (bias included): Lt = max(x, pool, c3, c5, c7);
+// branch = 0 if a non-parameter branch (identity / pool) wins, else 1,2,3 for conv3/5/7.  torch's
+// max over cat((y0,y1,y2,y3,y4)) sends the gradient to the FIRST maximal entry (y0 = x first).
+__global__ void timeconv_max_train_kernel(const float* __restrict__ x, const float* __restrict__ c3, const float* __restrict__ c5,
+                                          const float* __restrict__ c7, int L, int64_t n, float* __restrict__ Lt,
+                                          uint8_t* __restrict__ branch) {
+  GRID_STRIDE(i, n) {
+    const int64_t row = i / kD; const int k = (int)(row % L);
+    const float x0 = x[i];
+    const float pool = fmaxf(x0, k > 0 ? x[i - kD] : 0.f);
+    float best = x0; uint8_t br = 0;
+    if (c3[i] > best) { best = c3[i]; br = 1; }
+    if (c5[i] > best) { best = c5[i]; br = 2; }
+    if (c7[i] > best) { best = c7[i]; br = 3; }
+    if (pool > best) { best = pool; br = 0; }
+    Lt[i] = best; branch[i] = br;
+  }
+}
+__global__ void conv_route_kernel(const float* __restrict__ dLt, const uint8_t* __restrict__ branch, int64_t n,
+                                  float* __restrict__ d3, float* __restrict__ d5, float* __restrict__ d7) {
+  GRID_STRIDE(i, n) {
+    const float g = dLt[i]; const uint8_t b = branch[i];
+    d3[i] = b == 1 ? g : 0.f; d5[i] = b == 2 ? g : 0.f; d7[i] = b == 3 ? g : 0.f;
+  }
+}
+// out[(b,k)][c] = x[(b,k+d)][c] or 0 outside the window
+__global__ void shift_rows_kernel(const float* __restrict__ x, int L, int d, int64_t n, float* __restrict__ o) {
+  GRID_STRIDE(i, n) {
+    const int64_t row = i / kD; const int k = (int)(row % L);
+    const int kk = k + d;
+    o[i] = (kk >= 0 && kk < L) ? x[i + (int64_t)d * kD] : 0.f;
+  }
+}
+// dW[(o*D + c)*K + j] = tmp[o*D + c]
+__global__ void scatter_tap_kernel(const float* __restrict__ tmp, int K, int j, float* __restrict__ dW) {
+  const int64_t n = (int64_t)kD * kD;
+  GRID_STRIDE(i, n) dW[i * K + j] = tmp[i];
+}
+// direct conv forward for training: out[(b,k)][o] = bias[o] + sum_j sum_c w[o][c][j] x[(b,k+j-h)][c] is done as
+// K GEMMs on shifted copies (see conv_forward()).
+
+// attention, training forward: warp per clip; saves the softmax p (B,L)
+__global__ void attention_train_fwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
+                                           float* __restrict__ p, float* __restrict__ abar) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* ub = u + (int64_t)b * kD;
+  const float* Lb = Lt + (int64_t)b * L * kD;
+  float mx = -INFINITY;
+  for (int k = 0; k < L; ++k) {
+    float s = 0.f;
+    for (int c = lane; c < kD; c += 32) s = fmaf(ub[c], Lb[(int64_t)k * kD + c], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s *= scale;
+    if (lane == 0) p[(int64_t)b * L + k] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float den = 0.f;
+  for (int k = 0; k < L; ++k) den += expf(p[(int64_t)b * L + k] - mx);
+  __syncwarp();
+  for (int k = lane; k < L; k += 32) p[(int64_t)b * L + k] = expf(p[(int64_t)b * L + k] - mx) / den;
+  __syncwarp();
+  for (int c = lane; c < kD; c += 32) {
+    float a = 0.f;
+    for (int k = 0; k < L; ++k) a = fmaf(p[(int64_t)b * L + k], Lb[(int64_t)k * kD + c], a);
+    abar[(int64_t)b * kD + c] = a;
+  }
+}
+// attention backward: dabar -> du, dLt.  dp_k = dabar.Lt_k ; ds = p (dp - sum p dp) ; du = scale sum ds_k Lt_k ;
+// dLt_k = p_k dabar + scale ds_k u
+__global__ void attention_train_bwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, const float* __restrict__ p,
+                                           const float* __restrict__ dabar, int B, int L, float scale, float* __restrict__ ds_buf,
+                                           float* __restrict__ du, float* __restrict__ dLt) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* ub = u + (int64_t)b * kD; const float* da = dabar + (int64_t)b * kD;
+  const float* Lb = Lt + (int64_t)b * L * kD; const float* pb = p + (int64_t)b * L;
+  float* dsb = ds_buf + (int64_t)b * L;
+  float dot = 0.f;
+  for (int k = 0; k < L; ++k) {
+    float s = 0.f;
+    for (int c = lane; c < kD; c += 32) s = fmaf(da[c], Lb[(int64_t)k * kD + c], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dsb[k] = s;
+    dot = fmaf(pb[k], s, dot);
+  }
+  __syncwarp();
+  for (int k = lane; k < L; k += 32) dsb[k] = pb[k] * (dsb[k] - dot);
+  __syncwarp();
+  for (int c = lane; c < kD; c += 32) {
+    float acc = 0.f;
+    for (int k = 0; k < L; ++k) {
+      acc = fmaf(dsb[k], Lb[(int64_t)k * kD + c], acc);
+      if (dLt) dLt[((int64_t)b * L + k) * kD + c] = pb[k] * da[c] + scale * dsb[k] * ub[c];
+    }
+    du[(int64_t)b * kD + c] = scale * acc;
+  }
+}
+
+// LayerNorm([1,D]) forward (saves xhat, rstd) + ReLU
+__global__ void layernorm_train_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ be, int B,
+                                           float* __restrict__ xhat, float* __restrict__ rstd, float* __restrict__ nout, float* __restrict__ r) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* vb = v + (int64_t)b * kD;
+  float s = 0.f;
+  for (int c = lane; c < kD; c += 32) s += vb[c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / kD;
+  float q = 0.f;
+  for (int c = lane; c < kD; c += 32) { const float a = vb[c] - mean; q += a * a; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rs = rsqrtf(q / kD + 1e-5f);
+  if (lane == 0) rstd[b] = rs;
+  for (int c = lane; c < kD; c += 32) {
+    const float xh = (vb[c] - mean) * rs;
+    const float nn = xh * g[c] + be[c];
+    xhat[(int64_t)b * kD + c] = xh; nout[(int64_t)b * kD + c] = nn; r[(int64_t)b * kD + c] = fmaxf(nn, 0.f);
+  }
+}
+// dn (already masked by relu) -> dv
+__global__ void layernorm_train_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                           const float* __restrict__ g, int B, float* __restrict__ dv) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* d = dn + (int64_t)b * kD; const float* xh = xhat + (int64_t)b * kD;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < kD; c += 32) { const float dx = d[c] * g[c]; s1 += dx; s2 += dx * xh[c]; }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  s1 /= kD; s2 /= kD;
+  const float rs = rstd[b];
+  for (int c = lane; c < kD; c += 32) dv[(int64_t)b * kD + c] = rs * (d[c] * g[c] - s1 - xh[c] * s2);
+}
+
+// counter-based dropout mask: keep with probability 1-p; out = in * keep / (1-p)
+__device__ __forceinline__ uint32_t hash32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+__global__ void dropout_kernel(const float* __restrict__ in, float p, uint64_t seed, int64_t n, float* __restrict__ out, float* __restrict__ mask) {
+  const float inv = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  GRID_STRIDE(i, n) {
+    const float keep = (p <= 0.f) ? 1.f : ((hash32(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i) * (1.0f / 4294967296.0f)) >= p ? 1.f : 0.f);
+    const float m = keep * inv;
+    mask[i] = m; out[i] = in[i] * m;
+  }
+}
+__global__ void mul_mask_kernel(const float* a, const float* m, float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = a[i] * m[i]; }
+__global__ void relu_fwd_kernel(const float* a, float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = fmaxf(a[i], 0.f); }
+__global__ void relu_bwd_kernel(const float* d, const float* pre, float* o, int64_t n) { GRID_STRIDE(i, n) o[i] = pre[i] > 0.f ? d[i] : 0.f; }
+// cat = [St || y1], y1 = St + o'
+__global__ void make_cat_kernel(const float* St, const float* od, int B, float* cat) {
+  const int64_t n = (int64_t)B * kD;
+  GRID_STRIDE(i, n) { const int64_t b = i / kD; const int c = (int)(i % kD); cat[b * 2 * kD + c] = St[i]; cat[b * 2 * kD + kD + c] = St[i] + od[i]; }
+}
+// dSt = dcat[:, :D] + dcat[:, D:] ; do' = dcat[:, D:]
+__global__ void split_dcat_kernel(const float* dcat, int B, float* dSt, float* dod) {
+  const int64_t n = (int64_t)B * kD;
+  GRID_STRIDE(i, n) { const int64_t b = i / kD; const int c = (int)(i % kD); const float a = dcat[b * 2 * kD + c], d = dcat[b * 2 * kD + kD + c]; dSt[i] = a + d; dod[i] = d; }
+}
+__global__ void axpy_kernel(const float* x, float* y, int64_t n) { GRID_STRIDE(i, n) y[i] += x[i]; }
+
+// CrossEntropyLoss(reduction='sum', weight=w): loss = sum_b w[y_b] (-log softmax(logits_b)[y_b]);
+// dlogits (ld 16, zero padded) = w[y_b] (softmax - onehot).  One thread per clip; loss accumulated atomically.
+__global__ void ce_loss_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ cw, int B, int C,
+                               float* __restrict__ dlog16, float* __restrict__ loss, int64_t* __restrict__ pred) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* l = logits + (int64_t)b * C;
+  float mx = l[0]; int am = 0;
+  for (int c = 1; c < C; ++c) if (l[c] > mx) { mx = l[c]; am = c; }
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) den += expf(l[c] - mx);
+  const int y = (int)labels[b];
+  const float w = cw ? cw[y] : 1.f;
+  for (int c = 0; c < 16; ++c) dlog16[(int64_t)b * 16 + c] = c < C ? w * (expf(l[c] - mx) / den - (c == y ? 1.f : 0.f)) : 0.f;
+  atomicAdd(loss, w * (logf(den) + mx - l[y]));
+  if (pred) pred[b] = am;
+}
+
+// SGD with momentum and weight decay exactly as torch.optim.SGD (dampening 0, no nesterov):
+//   d = g + wd * p ; buf = first ? d : mu * buf + d ; p -= lr * buf          (TRAIN:797-805, 887)
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr, float mu,
+                           float wd, int first) {
+  GRID_STRIDE(i, n) {
+    const float d = g[i] + wd * p[i];
+    const float bv = first ? d : mu * buf[i] + d;
+    buf[i] = bv;
+    p[i] -= lr * bv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM helpers on top of simt_linear (out = a . w^T, K-major operands)
+// ---------------------------------------------------------------------------------------------
+static int gemm_nt(const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias, float* out, int64_t ldo,
+                   int64_t M, int N, int K, cudaStream_t st) {
+  LinearArgs g; g.a = a; g.lda = lda; g.w = w; g.ldw = ldw; g.bias = bias; g.out = out; g.ldo = ldo; g.M = M; g.N = N; g.K = K;
+  return simt_linear(g, st);
+}
+
+struct Ws {
+  char* p; size_t left;
+  float* f(size_t n) { size_t b = fb(n); if (b > left) return nullptr; float* r = (float*)p; p += b; left -= b; return r; }
+};
+
+}  // namespace train
+}  // namespace tmr
+
+using namespace tmr;
+using namespace tmr::train;
+
+extern "C" {
+
+size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C) {
+  (void)C;
+  const size_t b = (size_t)(B > 0 ? B : 1), S = seq, R = b * L, Rp = pad16(R), Bp = pad16(b), T = b * S, Tp = pad16(T);
+  size_t n = 0;
+  n += fb(T * F) + fb(4 * D) + fb(T * 4 * D) + fb(b * 4 * D) + fb(T * 4 * D) + 2 * fb(T * D);        // LSTM forward
+  n += 5 * fb(R * D) + fb(R * D / 4 + 64) + fb((size_t)D * D);                                        // TimeConv forward
+  n += 4 * fb((size_t)D * D) + fb((size_t)2 * D * D) + fb((size_t)D * 4 * D) + fb((size_t)D * 16);    // weight transposes
+  n += 26 * fb(b * D) + 2 * fb(b * 2 * D) + 2 * fb(b * L) + fb(b) + fb(b * 16);                       // activations + their grads
+  n += 2 * fb((size_t)2 * D * Bp) + fb((size_t)16 * Bp);                                              // small transposes
+  n += 4 * fb(R * D) + 2 * fb((size_t)D * Rp) + fb((size_t)D * D);                                    // TimeConv backward
+  n += fb(T * 4 * D) + fb((size_t)4 * D * Tp) + fb((size_t)F * Tp);                                   // BPTT
+  return n + (1 << 16);
+}
+
+/* Forward (training mode) + backward of the head for one batch.  params/grads: 24 device pointers in
+ * the order documented at the top of train.cu (timeconv entries may be NULL for the NL-only wiring).
+ * x (B,seq,F) features, long_feature (B,L,D), labels int64[B], class_weight float[C] or NULL.
+ * Dropout p_nl (NLBlock, 0.2 in the reference) and p_fc (0.5) with a counter-based mask from `seed`.
+ * Outputs: grads (overwritten), logits (B,C), loss (1 float, sum-reduced), pred int64[B] (nullable). */
+int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                           const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
+                           float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  TMR_CHECK_ARG(D == kD && F == kF, "train: D/F unsupported");
+  TMR_CHECK_ARG(B >= 1 && seq >= 1 && L >= 1 && C >= 1 && C <= 16, "train: bad sizes (C <= 16)");
+  TMR_CHECK_ARG(params && grads && x && long_feature && labels && logits && loss && workspace, "train: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool has_tc = params[4] != nullptr;
+  const int S = seq;
+  const int64_t R = (int64_t)B * L, Rp = pad16(R), Bp = pad16(B), T = (int64_t)S * B, Tp = pad16(T);
+  const float scale = (float)0.044194173824159216;
+  Ws w{(char*)workspace, workspace_bytes};
+#define TAKE(name, n) float* name = w.f(n); TMR_CHECK_ARG(name, "train: workspace too small at " #name)
+  const float *Wih = params[0], *Whh = params[1];
+  TAKE(x_tm, (size_t)T * kF); TAKE(bsum, 4 * kD); TAKE(xp, (size_t)T * 4 * kD); TAKE(hh, (size_t)B * 4 * kD);
+  TAKE(gates, (size_t)T * 4 * kD); TAKE(cst, (size_t)T * kD); TAKE(hst, (size_t)T * kD);
+  // ---------------- forward: LSTM ----------------
+  permute_bsf_kernel<<<nblk(T * kF), 256, 0, st>>>(x, B, S, kF, x_tm);
+  add_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(params[2], params[3], bsum, 4 * kD);
+  TMR_TRY(gemm_nt(x_tm, kF, Wih, kF, bsum, xp, 4 * kD, T, 4 * kD, kF, st));
+  for (int t = 0; t < S; ++t) {
+    if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st));
+    lstm_cell_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(xp + (size_t)t * B * 4 * kD, t > 0 ? hh : nullptr,
+                                                               t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
+                                                               gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
+                                                               hst + (size_t)t * B * kD, B);
+  }
+  const float* St = hst + (size_t)(S - 1) * B * kD;
+  // ---------------- forward: TimeConv ----------------
+  const float* Lt = long_feature;
+  float *c3 = nullptr, *c5 = nullptr, *c7 = nullptr, *Ltb = nullptr, *shiftb = nullptr;
+  uint8_t* branch = nullptr;
+  float* convs[3] = {nullptr, nullptr, nullptr};
+  if (has_tc) {
+    c3 = w.f((size_t)R * kD); c5 = w.f((size_t)R * kD); c7 = w.f((size_t)R * kD); Ltb = w.f((size_t)R * kD);
+    shiftb = w.f((size_t)R * kD); branch = (uint8_t*)w.f((size_t)R * kD / 4 + 64);
+    TMR_CHECK_ARG(c3 && c5 && c7 && Ltb && shiftb && branch, "train: workspace too small (timeconv)");
+    convs[0] = c3; convs[1] = c5; convs[2] = c7;
+    TAKE(wtap, (size_t)kD * kD);
+    for (int ci = 0; ci < 3; ++ci) {         // conv_K = bias + sum_j shift_j(x) . W_K[:,:,j]^T  (tap matrices gathered from (D,D,K))
+      const int K = 3 + 2 * ci, h = K / 2;
+      const float* Wk = params[4 + 2 * ci];
+      for (int j = 0; j < K; ++j) {
+        // wtap[o][c] = Wk[o][c][j]  (strided gather = transpose_pad of a (D*D) x K matrix column j)
+        transpose_pad_kernel<<<dim3(1, (unsigned)((kD * kD + 31) / 32)), dim3(32, 8), 0, st>>>(Wk + j, (int64_t)kD * kD, 1, K, wtap, (int64_t)kD * kD);
+        shift_rows_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, L, j - h, R * kD, shiftb);
+        LinearArgs g; g.a = shiftb; g.lda = kD; g.w = wtap; g.ldw = kD; g.bias = j == 0 ? params[5 + 2 * ci] : nullptr;
+        g.residual = j == 0 ? nullptr : convs[ci]; g.ldr = kD; g.out = convs[ci]; g.ldo = kD; g.M = R; g.N = kD; g.K = kD;
+        TMR_TRY(simt_linear(g, st));
+      }
+    }
+    timeconv_max_train_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, c3, c5, c7, L, R * kD, Ltb, branch);
+    Lt = Ltb;
+  }
+  // ---------------- forward: NLBlock ----------------
+  TAKE(W1T, (size_t)kD * kD); TAKE(W2T, (size_t)kD * kD); TAKE(W3T, (size_t)kD * kD); TAKE(W4T, (size_t)kD * kD);
+  TAKE(WhT, (size_t)2 * kD * kD); TAKE(WhhT, (size_t)kD * 4 * kD); TAKE(WcT, (size_t)kD * 16);
+  TMR_TRY(transpose_pad(params[10], kD, kD, kD, W1T, kD, st));
+  TMR_TRY(transpose_pad(params[12], kD, kD, kD, W2T, kD, st));
+  TMR_TRY(transpose_pad(params[14], kD, kD, kD, W3T, kD, st));
+  TMR_TRY(transpose_pad(params[16], kD, kD, kD, W4T, kD, st));
+  TMR_TRY(transpose_pad(params[20], kD, 2 * kD, 2 * kD, WhT, kD, st));       // (D,2D) -> (2D, D)
+  TMR_TRY(transpose_pad(Whh, 4 * kD, kD, kD, WhhT, 4 * kD, st));             // (4D,D) -> (D, 4D)
+  TMR_TRY(transpose_pad(params[22], C, kD, kD, WcT, 16, st));                // (C,D)  -> (D, 16) zero padded
+  TAKE(q, (size_t)B * kD); TAKE(u, (size_t)B * kD); TAKE(pbuf, (size_t)B * L); TAKE(abar, (size_t)B * kD);
+  TAKE(v, (size_t)B * kD); TAKE(xhat, (size_t)B * kD); TAKE(rstd, B); TAKE(nrm, (size_t)B * kD); TAKE(r, (size_t)B * kD);
+  TAKE(o, (size_t)B * kD); TAKE(od, (size_t)B * kD); TAKE(m1, (size_t)B * kD); TAKE(cat, (size_t)B * 2 * kD);
+  TAKE(z0, (size_t)B * kD); TAKE(z1, (size_t)B * kD); TAKE(m2, (size_t)B * kD); TAKE(z, (size_t)B * kD);
+  TMR_TRY(gemm_nt(St, kD, params[10], kD, params[11], q, kD, B, kD, kD, st));            // q = St W1^T + b1
+  TMR_TRY(gemm_nt(q, kD, W2T, kD, nullptr, u, kD, B, kD, kD, st));                       // u = W2^T q
+  attention_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, B, L, scale, pbuf, abar);
+  TMR_TRY(gemm_nt(abar, kD, params[14], kD, params[15], v, kD, B, kD, kD, st));          // v = W3 abar + b3
+  layernorm_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, params[18], params[19], B, xhat, rstd, nrm, r);
+  TMR_TRY(gemm_nt(r, kD, params[16], kD, params[17], o, kD, B, kD, kD, st));             // o = W4 r + b4
+  dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(o, p_nl, seed * 2 + 1, (int64_t)B * kD, od, m1);
+  make_cat_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(St, od, B, cat);
+  // ---------------- forward: classifier + loss ----------------
+  TMR_TRY(gemm_nt(cat, 2 * kD, params[20], 2 * kD, params[21], z0, kD, B, kD, 2 * kD, st));
+  dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z0, p_fc, seed * 2 + 2, (int64_t)B * kD, z1, m2);
+  relu_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z1, z, (int64_t)B * kD);
+  TMR_TRY(gemm_nt(z, kD, params[22], kD, params[23], logits, C, B, C, kD, st));
+  TAKE(dlog16, (size_t)B * 16);
+  TMR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  ce_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(logits, labels, class_weight, B, C, dlog16, loss, pred);
+  TMR_LAUNCH_CHECK("train forward");
+
+  // ---------------- backward: classifier ----------------
+  TAKE(tA, (size_t)2 * kD * Bp); TAKE(tB, (size_t)2 * kD * Bp); TAKE(tC, (size_t)16 * Bp);
+  TAKE(dz, (size_t)B * kD); TAKE(dz0, (size_t)B * kD); TAKE(dcat, (size_t)B * 2 * kD); TAKE(dSt, (size_t)B * kD);
+  TAKE(dod, (size_t)B * kD); TAKE(dr, (size_t)B * kD); TAKE(dv, (size_t)B * kD); TAKE(dabar, (size_t)B * kD);
+  TAKE(du, (size_t)B * kD); TAKE(dq, (size_t)B * kD); TAKE(dsb, (size_t)B * L); TAKE(tmpBD, (size_t)B * kD);
+  // dWc = dlogits^T z ; dbc ; dz = dlogits Wc
+  TMR_TRY(transpose_pad(dlog16, B, 16, 16, tC, Bp, st));                                  // (16, Bp)
+  TMR_TRY(transpose_pad(z, B, kD, kD, tA, Bp, st));                                       // (D, Bp)
+  TMR_TRY(gemm_nt(tC, Bp, tA, Bp, nullptr, grads[22], kD, C, kD, (int)Bp, st));
+  TMR_TRY(colsum(dlog16, nullptr, B, C, 16, grads[23], 0, st));
+  TMR_TRY(gemm_nt(dlog16, 16, WcT, 16, nullptr, dz, kD, B, kD, 16, st));
+  relu_bwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dz, z1, dz0, (int64_t)B * kD);
+  mul_mask_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dz0, m2, dz0, (int64_t)B * kD);
+  // dWh = dz0^T cat ; dbh ; dcat = dz0 Wh
+  TMR_TRY(transpose_pad(dz0, B, kD, kD, tA, Bp, st));                                     // (D, Bp)
+  TMR_TRY(transpose_pad(cat, B, 2 * kD, 2 * kD, tB, Bp, st));                             // (2D, Bp)
+  TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[20], 2 * kD, kD, 2 * kD, (int)Bp, st));
+  TMR_TRY(colsum(dz0, nullptr, B, kD, kD, grads[21], 0, st));
+  TMR_TRY(gemm_nt(dz0, kD, WhT, kD, nullptr, dcat, 2 * kD, B, 2 * kD, kD, st));
+  split_dcat_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dcat, B, dSt, dod);
+  // ---------------- backward: NLBlock ----------------
+  mul_mask_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dod, m1, dod, (int64_t)B * kD);   // do
+  TMR_TRY(transpose_pad(dod, B, kD, kD, tA, Bp, st));
+  TMR_TRY(transpose_pad(r, B, kD, kD, tB, Bp, st));
+  TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[16], kD, kD, kD, (int)Bp, st));           // dW4 = do^T r
+  TMR_TRY(colsum(dod, nullptr, B, kD, kD, grads[17], 0, st));
+  TMR_TRY(gemm_nt(dod, kD, W4T, kD, nullptr, dr, kD, B, kD, kD, st));                      // dr = do W4
+  relu_bwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dr, nrm, dr, (int64_t)B * kD);     // dn
+  TMR_TRY(colsum(dr, xhat, B, kD, kD, grads[18], 0, st));                                   // dgamma
+  TMR_TRY(colsum(dr, nullptr, B, kD, kD, grads[19], 0, st));                                // dbeta
+  layernorm_train_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(dr, xhat, rstd, params[18], B, dv);
+  TMR_TRY(transpose_pad(dv, B, kD, kD, tA, Bp, st));
+  TMR_TRY(transpose_pad(abar, B, kD, kD, tB, Bp, st));
+  TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[14], kD, kD, kD, (int)Bp, st));           // dW3 = dv^T abar
+  TMR_TRY(colsum(dv, nullptr, B, kD, kD, grads[15], 0, st));
+  TMR_TRY(gemm_nt(dv, kD, W3T, kD, nullptr, dabar, kD, B, kD, kD, st));                    // dabar = dv W3
+  float* dLt = nullptr;
+  if (has_tc) { dLt = w.f((size_t)R * kD); TMR_CHECK_ARG(dLt, "train: workspace too small (dLt)"); }
+  attention_train_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, pbuf, dabar, B, L, scale, dsb, du, dLt);
+  // u = W2^T q : dq = du W2^T (out[b,i] = sum_j du[b,j] W2[i][j]) ; dW2 = q^T du ; db2 = 0
+  TMR_TRY(gemm_nt(du, kD, params[12], kD, nullptr, dq, kD, B, kD, kD, st));
+  TMR_TRY(transpose_pad(q, B, kD, kD, tA, Bp, st));
+  TMR_TRY(transpose_pad(du, B, kD, kD, tB, Bp, st));
+  TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[12], kD, kD, kD, (int)Bp, st));
+  zero_kernel<<<2, 256, 0, st>>>(grads[13], kD);
+  // q = St W1^T + b1 : dW1 = dq^T St ; db1 ; dSt += dq W1
+  TMR_TRY(transpose_pad(dq, B, kD, kD, tA, Bp, st));
+  TMR_TRY(transpose_pad(St, B, kD, kD, tB, Bp, st));
+  TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[10], kD, kD, kD, (int)Bp, st));
+  TMR_TRY(colsum(dq, nullptr, B, kD, kD, grads[11], 0, st));
+  TMR_TRY(gemm_nt(dq, kD, W1T, kD, nullptr, tmpBD, kD, B, kD, kD, st));
+  axpy_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(tmpBD, dSt, (int64_t)B * kD);
+  // ---------------- backward: TimeConv (weights only; the bank has no gradient) ----------------
+  if (has_tc) {
+    TAKE(d3, (size_t)R * kD); TAKE(d5, (size_t)R * kD); TAKE(d7, (size_t)R * kD);
+    TAKE(dcT, (size_t)kD * Rp); TAKE(shT, (size_t)kD * Rp); TAKE(tap, (size_t)kD * kD);
+    conv_route_kernel<<<nblk(R * kD), 256, 0, st>>>(dLt, branch, R * kD, d3, d5, d7);
+    float* dcs[3] = {d3, d5, d7};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int K = 3 + 2 * ci, h = K / 2;
+      TMR_TRY(colsum(dcs[ci], nullptr, R, kD, kD, grads[5 + 2 * ci], 0, st));
+      TMR_TRY(transpose_pad(dcs[ci], R, kD, kD, dcT, Rp, st));                              // (D_out, Rp)
+      for (int j = 0; j < K; ++j) {
+        shift_rows_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, L, j - h, R * kD, shiftb);
+        TMR_TRY(transpose_pad(shiftb, R, kD, kD, shT, Rp, st));                             // (D_in, Rp)
+        TMR_TRY(gemm_nt(dcT, Rp, shT, Rp, nullptr, tap, kD, kD, kD, (int)Rp, st));          // tap[o][c]
+        scatter_tap_kernel<<<nblk((int64_t)kD * kD), 256, 0, st>>>(tap, K, j, grads[4 + 2 * ci]);
+      }
+    }
+  }
+  // ---------------- backward: LSTM (BPTT) ----------------
+  TAKE(dpre, (size_t)T * 4 * kD); TAKE(dc, (size_t)B * kD); TAKE(dh, (size_t)B * kD);
+  zero_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dc, (int64_t)B * kD);
+  copy_vec_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dSt, dh, (int64_t)B * kD);
+  for (int t = S - 1; t >= 0; --t) {
+    lstm_cell_bwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dh, dc, gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
+                                                               t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
+                                                               dpre + (size_t)t * B * 4 * kD, B);
+    if (t > 0) TMR_TRY(gemm_nt(dpre + (size_t)t * B * 4 * kD, 4 * kD, WhhT, 4 * kD, nullptr, dh, kD, B, kD, 4 * kD, st));   // dh_{t-1} = dpre_t Whh
+  }
+  TAKE(dpT, (size_t)4 * kD * Tp); TAKE(opT, (size_t)kF * Tp);
+  TMR_TRY(transpose_pad(dpre, T, 4 * kD, 4 * kD, dpT, Tp, st));                              // (4D, Tp)
+  TMR_TRY(transpose_pad(x_tm, T, kF, kF, opT, Tp, st));                                      // (F, Tp)
+  TMR_TRY(gemm_nt(dpT, Tp, opT, Tp, nullptr, grads[0], kF, 4 * kD, kF, (int)Tp, st));        // dWih = dpre^T X
+  TMR_TRY(colsum(dpre, nullptr, T, 4 * kD, 4 * kD, grads[2], 0, st));
+  copy_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(grads[2], grads[3], 4 * kD);
+  if (S > 1) {   // dWhh = sum_{t>=1} dpre_t^T h_{t-1}: rows B.. of dpre against rows 0..T-B of the h history
+    const int64_t T1 = T - B, T1p = pad16(T1);
+    TMR_TRY(transpose_pad(dpre + (size_t)B * 4 * kD, T1, 4 * kD, 4 * kD, dpT, T1p, st));
+    TMR_TRY(transpose_pad(hst, T1, kD, kD, opT, T1p, st));
+    TMR_TRY(gemm_nt(dpT, T1p, opT, T1p, nullptr, grads[1], kD, 4 * kD, kD, (int)T1p, st));
+  } else {
+    zero_kernel<<<nblk((int64_t)4 * kD * kD), 256, 0, st>>>(grads[1], (int64_t)4 * kD * kD);
+  }
+  TMR_LAUNCH_CHECK("train backward");
+#undef TAKE
+  return TMR_OK;
+}
+
+/* torch.optim.SGD step on one flat tensor (momentum mu, weight decay wd, dampening 0): see sgd_kernel. */
+int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float mu, float wd,
+                 int first_step, void* stream) {
+  TMR_CHECK_ARG(param && grad && momentum_buf && n >= 0, "sgd: bad arguments");
+  if (n == 0) return TMR_OK;
+  sgd_kernel<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, mu, wd, first_step);
+  TMR_LAUNCH_CHECK("sgd_kernel");
+  return TMR_OK;
+}
+
+}  // extern "C"

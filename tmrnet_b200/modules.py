@@ -28,6 +28,9 @@ class _PackedCache:
         self._k = None
         self._v = None
 
+    def invalidate(self):
+        self._k = None
+
     def get(self, params, fn):
         k = _key(params)
         if k != self._k:
@@ -164,6 +167,14 @@ class resnet_lstm(nn.Module):
                 self.time_conv.packed() if self.time_conv is not None else None,
                 self.nl_block.packed(),
                 self._cls_cache.get(self._cls_params(), ops.pack_classifier))
+
+    def invalidate_packs(self):
+        """Call after parameters were updated in place by non-torch code (tmrnet_b200.train)."""
+        self._lstm_cache.invalidate()
+        self._cls_cache.invalidate()
+        self.nl_block._cache.invalidate()
+        if self.time_conv is not None:
+            self.time_conv._cache.invalidate()
 
     def load_reference_state_dict(self, sd):
         """Load a reference checkpoint (torch.save(model.module.state_dict()),
