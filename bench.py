@@ -44,7 +44,7 @@ FLOP_LSTM_STEP = 2 * 4 * 512 * 512               # 2.097 MFLOP per clip per recu
 FLOP_BANKCONV_ROW = 2 * 512 * 512 * 15           # 7.864 MFLOP per bank row (TimeConv deduplicated per row)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
 # ncu --set full capture (profiles/); None until that capture exists for the current kernel
-NCU_TRAFFIC_LSTM_STEP = None
+NCU_TRAFFIC_LSTM_STEP = 217.0e6   # bytes per launch at 14336 clips (profiles/r1_final_tf32_dedup.md)
 
 
 def peaks():
