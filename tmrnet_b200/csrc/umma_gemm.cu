@@ -47,17 +47,24 @@ int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dim
 }
 
 constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
+enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
+// Per-epilogue configuration.  The LSTM-cell epilogue is latency-bound (gathered projected rows, cell
+// state, MUFU chains), so it gets 16 epilogue warps (4 per SM sub-partition) and pays for their smem
+// transpose tiles with one pipeline stage; the plain epilogue keeps 8 warps and 4 stages.
+template <int EPI> struct Cfg {
+  static constexpr int STAGES = (EPI == EPI_LSTM) ? 3 : 4;
+  static constexpr int EPI_WARPS = (EPI == EPI_LSTM) ? 16 : 8;
+  static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;      // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int COLS_PER_WARP = 1024 / EPI_WARPS;         // 4 warps per TMEM lane quarter share 256 columns
+};
 constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_STAGE_BYTES = 8 * 4096;            // one 32x32 fp32 transpose tile per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 320;                        // 2 control warps + 8 epilogue warps
-constexpr int EPI_WARPS = 8;
+template <int EPI> constexpr int smem_bytes() {
+  return Cfg<EPI>::STAGES * STAGE_BYTES + Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+}
 constexpr int TMEM_COLS = 512;
-
-enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
@@ -82,12 +89,14 @@ __device__ __forceinline__ float fast_tanh(float v) { return fmaf(2.f, rcp_appro
 // weight traffic from L2 per CTA halves (48 -> 32 KB per k-block).  A stage may only be refilled when
 // BOTH consumers have released it: every tcgen05.commit on a stage arrives on both CTAs' empty barrier.
 template <int EPI, int CL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(Cfg<EPI>::NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                  const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  constexpr int STAGES = Cfg<EPI>::STAGES;
+  constexpr int EPI_WARPS = Cfg<EPI>::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + Cfg<EPI>::EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
@@ -182,7 +191,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // element-wise work + global I/O happens in a COALESCED layout (phase B): per instruction 8 lanes
     // cover the 128 contiguous bytes of one row, 4 rows per warp instruction.
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;                   // which 128-column half of the accumulator
+    constexpr int WCOLS = Cfg<EPI>::COLS_PER_WARP;      // accumulator columns owned by this warp (128 or 64)
+    const int colq = (warp - 2) >> 2;                   // which WCOLS-wide slice of the 256 columns
     float* sbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * 1024;   // 32 rows x 32 floats
     const int prow = lane >> 3;                         // phase B: row within a group of 4
     const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
@@ -191,8 +201,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m_base = ((item / n_tiles) * CL + crank) * BM + q * 32;     // first row of this warp
-      const int n0 = (int)(item % n_tiles) * BN + half * (BN / 2);
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+      const int n0 = (int)(item % n_tiles) * BN + colq * WCOLS;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + colq * WCOLS;
 
       // phase A helper: this thread's row of the chunk -> swizzled smem (conflict-free 128-bit stores)
       auto stage_rows = [&](const uint32_t (&r)[32]) {
@@ -207,8 +217,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
       if (EPI == EPI_LSTM) {
         // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
-        // step i.  Projected rows + cell state of chunk cc+1 are loaded while chunk cc is computed, and
-        // chunk 0's loads are issued before waiting for the accumulator.
+        // step i.  Sixteen warps (four per SM sub-partition) hide the latency of the gathered
+        // projected-row / cell-state loads and of the MUFU chains behind one another.
         int xr[8];                                      // projected-row index per phase-B step (-1: row >= M)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -217,23 +227,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         const float* xp0 = p.xp + n0 + 4 * pch;
         const int64_t c0 = (m_base + prow) * kD + (n0 >> 2) + pch;      // + 4*i*kD per step, + cc/4 per chunk
-        float4 xa[8], xb[8];
-        float ca[8], cb[8];
-        auto prefetch = [&](int cc, float4 (&x4)[8], float (&c1)[8]) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < WCOLS; cc += 32) {
+          float4 x4[8];
+          float c1[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 8; ++i) {                   // issue the chunk's global loads first ...
+            x4[i] = make_float4(0.f, 0.f, 0.f, 0.f); c1[i] = 0.f;
             if (xr[i] >= 0) {
               x4[i] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc));
               c1[i] = p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)];
             }
           }
-        };
-        auto compute = [&](int cc, const float4 (&x4)[8], const float (&c1)[8]) {
-          uint32_t r[32];
-          tmem_ld32(t_row + cc, r);
-          tmem_ld_wait();
-          __syncwarp();                                   // previous chunk's phase B reads are done
-          stage_rows(r);
+          {
+            uint32_t r[32];                               // ... then move the accumulator chunk through smem
+            tmem_ld32(t_row + cc, r);
+            tmem_ld_wait();
+            __syncwarp();                                 // previous chunk's phase B reads are done
+            stage_rows(r);
+          }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -247,21 +261,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = hn;
             }
           }
-        };
-        prefetch(0, xa, ca);
-        mbar_wait(&acc_full[acc], acc_phase);
-        tc_fence_after();
-        {
-          prefetch(32, xb, cb);  compute(0, xa, ca);
-          prefetch(64, xa, ca);  compute(32, xb, cb);
-          prefetch(96, xb, cb);  compute(64, xa, ca);
-          compute(96, xb, cb);
         }
       } else {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 2; cc += 32) {
+        for (int cc = 0; cc < WCOLS; cc += 32) {
           uint32_t r[32];
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
@@ -339,12 +344,12 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
   if (cluster == 2 && m_tiles >= 2) {
-    TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
     const int64_t items = ((m_tiles + 1) / 2) * n_tiles;
     const int max_clusters = num_sms() / 2;
     const int clusters = (int)(items < max_clusters ? items : max_clusters);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(Cfg<EPI>::NTHREADS); cfg.dynamicSmemBytes = smem_bytes<EPI>(); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -352,10 +357,10 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, p));
     return TMR_OK;
   }
-  TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
   const int64_t tiles = m_tiles * n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  umma_gemm_kernel<EPI, 1><<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, ta2, tb, p);
+  umma_gemm_kernel<EPI, 1><<<grid, Cfg<EPI>::NTHREADS, smem_bytes<EPI>(), st>>>(ta, ta2, tb, p);
   TMR_LAUNCH_CHECK("umma_gemm_kernel");
   return TMR_OK;
 }
