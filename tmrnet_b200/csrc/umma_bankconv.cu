@@ -16,24 +16,28 @@
 // (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512]; attention_pb_kernel consumes it.
 // 236 MFLOP/clip become 7.9 MFLOP/row; only summation order changes.
 //
-// Tried and dropped (round 1): loading the 134 rows of a chunk once and taking the seven shifts as
-// row-offset views of that smem tile (descriptor start + n*128 B with the matrix-base-offset field)
-// produced wrong products on B200 and was no faster — the kernel is bound by bytes in flight per SM
-// (TMA latency x smem ring), not by the L2 traffic of the shifted loads.
+// The SM's ingest from L2 (about 55 B/cycle) bounds tcgen05 kernels with fp32 operands, so the seven time
+// shifts are NOT taken as seven shifted activation loads: the MMAs multiply the tile's rows unshifted
+// and the epilogue applies the shift by exchanging accumulator rows through shared memory (3-row halo,
+// 122 of 128 rows emitted per tile).  (Taking the shifts as row-offset descriptor views of one smem
+// tile — matrix base offset — was tried first and produced wrong products on B200.)
 #include "tmr_internal.h"
 #include "umma_common.cuh"
 
 namespace tmr {
 namespace umma {
 
-constexpr int BC_BM = 128;                 // bank rows per tile
+constexpr int BC_BM = 128;                 // bank rows whose tap products one tile computes
+constexpr int BC_OUT = BC_BM - 6;          // rows it emits: the 3-row halo on either side feeds the shifts
 constexpr int BC_NCH = 32;                 // output channels per tile
 constexpr int BC_BK = 32;
-constexpr int BC_STAGES = 6;
-constexpr int BC_A_BYTES = BC_BM * BC_BK * 4;          // 16 KB
+constexpr int BC_A_STAGES = 3;
+constexpr int BC_A_BYTES = BC_BM * BC_BK * 4;          // 16 KB: the tile's rows, loaded ONCE per channel chunk
 constexpr int BC_W_BYTES = BC_NCH * BC_BK * 4;         // 4 KB per tap tile
-constexpr int BC_STAGE_BYTES = BC_A_BYTES + 3 * BC_W_BYTES;   // 28 KB
-constexpr int BC_SMEM_BYTES = BC_STAGES * BC_STAGE_BYTES + 1024 + 256;
+constexpr int BC_W_STAGE_BYTES = 3 * BC_W_BYTES;       // 12 KB: the taps of one shift (conv7 | conv5 | conv3)
+constexpr int BC_W_STAGES = 9;
+constexpr int BC_EX_BYTES = 15 * BC_BM * 8 * 4;        // epilogue exchange: 15 taps x 128 rows x 8 channels
+constexpr int BC_SMEM_BYTES = BC_A_STAGES * BC_A_BYTES + BC_W_STAGES * BC_W_STAGE_BYTES + BC_EX_BYTES + 1024 + 512;
 constexpr int BC_THREADS = 192;
 constexpr int BC_TMEM_COLS = 512;
 
@@ -45,8 +49,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 
-// TMEM column of shift group t (t = -3..3) and of conv w inside it (w = 0: conv7, 1: conv5, 2: conv3)
+// TMEM column of shift group t (t = -3..3); inside a group: conv7 | conv5 | conv3 (32 columns each)
 __host__ __device__ constexpr int group_col(int t) {
   return t == -3 ? 0 : t == -2 ? 32 : t == -1 ? 96 : t == 0 ? 192 : t == 1 ? 288 : t == 2 ? 384 : 448;
 }
@@ -56,27 +61,36 @@ struct BankConvParams {
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
 };
 
+// The MMAs compute UNSHIFTED products Q_{K,t}[r] = W_K[:,:,t+h] . bank[r] for the tile's 128 rows, so one
+// activation tile per channel chunk feeds all 15 taps; the time shift P_{K,t}[rho] = Q_{K,t}[rho - t] is
+// applied in the epilogue by exchanging rows through shared memory (hence the 3-row halo).
 __global__ void __launch_bounds__(BC_THREADS, 1)
 umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w3,
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
                      const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BC_STAGES * BC_STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + BC_STAGES;
-  uint64_t* acc_full = bars + 2 * BC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * BC_STAGES + 1);
+  uint8_t* smem_w = smem + BC_A_STAGES * BC_A_BYTES;
+  float* ex = reinterpret_cast<float*>(smem_w + BC_W_STAGES * BC_W_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ex) + BC_EX_BYTES);
+  uint64_t* full_bar = bars;                        // [BC_W_STAGES]
+  uint64_t* empty_bar = bars + BC_W_STAGES;         // [BC_W_STAGES]
+  uint64_t* a_full = bars + 2 * BC_W_STAGES;        // [BC_A_STAGES]
+  uint64_t* a_empty = a_full + BC_A_STAGES;         // [BC_A_STAGES]
+  uint64_t* acc_full = a_empty + BC_A_STAGES;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int N_TILES = kD / BC_NCH;                                 // 16
   const int n0 = (blockIdx.x % N_TILES) * BC_NCH;
-  const int64_t rho0 = p.row_base + (int64_t)(blockIdx.x / N_TILES) * BC_BM;   // first bank row of the tile
+  const int64_t out0 = p.row_base + (int64_t)(blockIdx.x / N_TILES) * BC_OUT;   // first row this tile emits
+  const int64_t q0 = out0 - 3;                                                   // first row it multiplies
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
-    for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < BC_W_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < BC_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -89,51 +103,59 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int a_stage = 0; uint32_t a_phase = 0;
       for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
         const int c0 = chunk * BC_BK;
+        mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+        mbar_expect_tx(&a_full[a_stage], BC_A_BYTES);
+        tma_load_2d(smem + a_stage * BC_A_BYTES, &tma_x, &a_full[a_stage], c0, (int)(q0 - p.r_lo));   // OOB rows -> 0
+        if (++a_stage == BC_A_STAGES) { a_stage = 0; a_phase ^= 1; }
         for (int t = -3; t <= 3; ++t) {
           const int at = t < 0 ? -t : t;
           const int n_w = (at <= 1) ? 3 : (at == 2 ? 2 : 1);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * BC_STAGE_BYTES;
-          uint8_t* sw = sa + BC_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], BC_A_BYTES + n_w * BC_W_BYTES);
-          tma_load_2d(sa, &tma_x, &full_bar[stage], c0, (int)(rho0 - t - p.r_lo));   // rows rho - t (OOB -> 0)
+          uint8_t* sw = smem_w + stage * BC_W_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], n_w * BC_W_BYTES);
           tma_load_2d(sw + 0 * BC_W_BYTES, &tma_w7, &full_bar[stage], (t + 3) * kD + c0, n0);
           if (n_w >= 2) tma_load_2d(sw + 1 * BC_W_BYTES, &tma_w5, &full_bar[stage], (t + 2) * kD + c0, n0);
           if (n_w >= 3) tma_load_2d(sw + 2 * BC_W_BYTES, &tma_w3, &full_bar[stage], (t + 1) * kD + c0, n0);
-          if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == BC_W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int a_stage = 0; uint32_t a_phase = 0;
       for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
+        mbar_wait(&a_full[a_stage], a_phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(smem_u32(smem + a_stage * BC_A_BYTES));
         for (int t = -3; t <= 3; ++t) {
           const int at = t < 0 ? -t : t;
           const int n_w = (at <= 1) ? 3 : (at == 2 ? 2 : 1);
           const uint32_t idesc = make_idesc_tf32(BC_BM, n_w * BC_NCH);           // one MMA covers every conv of the shift
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * BC_STAGE_BYTES);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + BC_A_BYTES);             // tap tiles are stacked along N
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + stage * BC_W_STAGE_BYTES));   // tap tiles stacked along N
           const uint32_t d_tmem = tmem_base + (uint32_t)group_col(t);
 #pragma unroll
           for (int k = 0; k < BC_BK / 8; ++k)
             mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (chunk | k) != 0);
           mma_commit(&empty_bar[stage]);
-          if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == BC_W_STAGES) { stage = 0; phase ^= 1; }
         }
+        mma_commit(&a_empty[a_stage]);                                           // all 15 taps of the chunk issued
+        if (++a_stage == BC_A_STAGES) { a_stage = 0; a_phase ^= 1; }
       }
       mma_commit(acc_full);
     }
   } else {
     const int q = warp & 3;
-    const int64_t rho = rho0 + q * 32 + lane;                       // this thread's bank row
+    const int r = q * 32 + lane;                                    // row inside the tile = TMEM lane
+    const int64_t rho = q0 + r;                                     // bank row of this thread
     const int64_t prow = rho - p.row_base;
-    const bool valid = prow < p.pb_rows && rho >= 0 && rho < p.n_rows;
+    const bool valid = r >= 3 && r < 3 + BC_OUT && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -141,18 +163,55 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     const bool has_next = valid && (rho + 1 < p.n_rows);
     const float* x1p = p.bank + (has_next ? rho + 1 : 0) * kD + n0;
     float* dst = p.pb + (valid ? prow : 0) * (7 * kD) + n0;
+    // exchange layout: ex[tap][row][8]; taps 0..6 = conv7 t=-3..3, 7..11 = conv5 t=-2..2, 12..14 = conv3 t=-1..1
+    auto exq = [&](int tap, int row) -> float* { return ex + ((size_t)tap * BC_BM + row) * 8; };
 #pragma unroll 1
     for (int cc = 0; cc < BC_NCH; cc += 8) {
-      // tap products of this row for 8 channels: P7[t+3], P5[t+2], P3[t+1]
-      float P7[7][8], P5[5][8], P3[3][8];
+      {
+        float v[8];
 #pragma unroll
-      for (int t = -3; t <= 3; ++t) {
-        tmem_ld8(t_row + group_col(t) + cc, P7[t + 3]);
-        if (t >= -2 && t <= 2) tmem_ld8(t_row + group_col(t) + BC_NCH + cc, P5[t + 2]);
-        if (t >= -1 && t <= 1) tmem_ld8(t_row + group_col(t) + 2 * BC_NCH + cc, P3[t + 1]);
+        for (int t = -3; t <= 3; ++t) {
+          tmem_ld8(t_row + group_col(t) + cc, v);
+          tmem_ld_wait();
+          *reinterpret_cast<float4*>(exq(t + 3, r)) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(exq(t + 3, r) + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          if (t >= -2 && t <= 2) {
+            tmem_ld8(t_row + group_col(t) + BC_NCH + cc, v);
+            tmem_ld_wait();
+            *reinterpret_cast<float4*>(exq(7 + t + 2, r)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(exq(7 + t + 2, r) + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (t >= -1 && t <= 1) {
+            tmem_ld8(t_row + group_col(t) + 2 * BC_NCH + cc, v);
+            tmem_ld_wait();
+            *reinterpret_cast<float4*>(exq(12 + t + 1, r)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(exq(12 + t + 1, r) + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
       }
-      tmem_ld_wait();
+      epi_barrier();
       if (valid) {
+        // P_{K,t}[rho] = Q_{K,t}[rho - t]: row r - t of the exchange buffer
+        float P7[7][8], P5[5][8], P3[3][8];
+#pragma unroll
+        for (int t = -3; t <= 3; ++t) {
+          const float4 a = *reinterpret_cast<const float4*>(exq(t + 3, r - t));
+          const float4 b = *reinterpret_cast<const float4*>(exq(t + 3, r - t) + 4);
+          P7[t + 3][0] = a.x; P7[t + 3][1] = a.y; P7[t + 3][2] = a.z; P7[t + 3][3] = a.w;
+          P7[t + 3][4] = b.x; P7[t + 3][5] = b.y; P7[t + 3][6] = b.z; P7[t + 3][7] = b.w;
+          if (t >= -2 && t <= 2) {
+            const float4 c = *reinterpret_cast<const float4*>(exq(7 + t + 2, r - t));
+            const float4 d = *reinterpret_cast<const float4*>(exq(7 + t + 2, r - t) + 4);
+            P5[t + 2][0] = c.x; P5[t + 2][1] = c.y; P5[t + 2][2] = c.z; P5[t + 2][3] = c.w;
+            P5[t + 2][4] = d.x; P5[t + 2][5] = d.y; P5[t + 2][6] = d.z; P5[t + 2][7] = d.w;
+          }
+          if (t >= -1 && t <= 1) {
+            const float4 c = *reinterpret_cast<const float4*>(exq(12 + t + 1, r - t));
+            const float4 d = *reinterpret_cast<const float4*>(exq(12 + t + 1, r - t) + 4);
+            P3[t + 1][0] = c.x; P3[t + 1][1] = c.y; P3[t + 1][2] = c.z; P3[t + 1][3] = c.w;
+            P3[t + 1][4] = d.x; P3[t + 1][5] = d.y; P3[t + 1][6] = d.z; P3[t + 1][7] = d.w;
+          }
+        }
         float b3[8], b5[8], b7[8], x0[8], x1[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -194,6 +253,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           d4[1] = make_float4(out[v][4], out[v][5], out[v][6], out[v][7]);
         }
       }
+      epi_barrier();                                   // exchange buffer is reused by the next 8 channels
     }
   }
 
@@ -234,7 +294,7 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
     }
   }
   TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
-  const int64_t tiles = ((pb_rows + BC_BM - 1) / BC_BM) * (kD / BC_NCH);
+  const int64_t tiles = ((pb_rows + BC_OUT - 1) / BC_OUT) * (kD / BC_NCH);
   umma_bankconv_kernel<<<(unsigned)tiles, BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, p);
   TMR_LAUNCH_CHECK("umma_bankconv_kernel");
   return TMR_OK;
