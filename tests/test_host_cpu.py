@@ -114,3 +114,33 @@ def test_export_matches_reference_format(tmp_path):
     assert open(paths[1]).read().splitlines() == lines[1]
     with pytest.raises(ValueError, match="number error"):
         phase_lines(preds[:-1], lengths, seq)
+
+
+def test_relaxed_boundary_evaluator_hand_cases():
+    """Port of matlab-eval/Evaluate.m: hand-computed cases incl. the relaxed boundary window."""
+    from tmrnet_b200.evaluate import evaluate, evaluate_videos
+    gt = np.array([0] * 30 + [1] * 40 + [2] * 30)
+    # perfect prediction
+    j, p, r, a = evaluate(gt, gt.copy())
+    assert np.allclose(j[:3], 100) and np.isnan(j[3:]).all() and a == 100.0
+    # late transition 0->1 by 5 frames (pred still 0 inside the first 10 s of phase 1): forgiven
+    pred = gt.copy(); pred[30:35] = 0
+    j, p, r, a = evaluate(gt, pred)
+    assert a == 100.0 and np.allclose(j[:3], 100)
+    assert abs(r[0] - 35 / 30 * 100) < 1e-9      # tp counts over the union, like the MATLAB code (Main.m caps at 100)
+    # an EARLY transition is not forgiven: the reference's length-t mask lands on the head of the segment
+    pred = gt.copy(); pred[25:30] = 1
+    assert abs(evaluate(gt, pred)[3] - 95.0) < 1e-9
+    # the same error 15 frames deep is outside the 10 s window: 5 frames counted wrong
+    pred = gt.copy(); pred[30:45] = 0
+    j, p, r, a = evaluate(gt, pred)
+    assert abs(a - 95.0) < 1e-9
+    assert abs(r[1] - (40 - 5) / 40 * 100) < 1e-9
+    # a wrong phase that is not an adjacent transition is never forgiven
+    pred = gt.copy(); pred[50:60] = 0
+    j, p, r, a = evaluate(gt, pred)
+    assert abs(a - 90.0) < 1e-9
+    out = evaluate_videos([gt, gt], [gt.copy(), pred])
+    assert abs(out["mean_accuracy"] - 95.0) < 1e-9 and out["jaccard_per_phase"].shape == (7,)
+    with pytest.raises(ValueError):
+        evaluate(gt, gt[:-1])
