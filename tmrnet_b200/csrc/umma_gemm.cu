@@ -53,6 +53,7 @@ enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 // transpose tiles with one pipeline stage; the plain epilogue keeps 8 warps and 4 stages.
 template <int EPI> struct Cfg {
   static constexpr int STAGES = (EPI == EPI_LSTM) ? 3 : 4;
+  static constexpr int STAGES_2SM = (EPI == EPI_LSTM) ? 5 : 6;      // 32 KB stages in 2-SM mode
   static constexpr int EPI_WARPS = (EPI == EPI_LSTM) ? 16 : 8;
   static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;      // one 32x32 fp32 transpose tile per epilogue warp
@@ -61,10 +62,15 @@ template <int EPI> struct Cfg {
 constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-template <int EPI> constexpr int smem_bytes() {
-  return Cfg<EPI>::STAGES * STAGE_BYTES + Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int EPI, bool TWOSM = false> constexpr int smem_bytes() {
+  return (TWOSM ? Cfg<EPI>::STAGES_2SM * (A_BYTES + B_BYTES / 2) : Cfg<EPI>::STAGES * STAGE_BYTES) +
+         Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 constexpr int TMEM_COLS = 512;
+
+// Debug timeline (TMR_TIMELINE=1): per CTA and tile, clock64 stamps of the MMA thread (wait for a free
+// accumulator, main loop start/end) and of epilogue warp 2 (accumulator ready, epilogue done).
+__device__ long long g_timeline[148 * 16 * 6];
 
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
@@ -72,6 +78,7 @@ struct GemmParams {
   const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
+  int timeline;
 };
 
 // Gate non-linearities of the tensor-core path: MUFU ex2/rcp approximations (2 ulp / 1 ulp), four
@@ -83,16 +90,24 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
 __device__ __forceinline__ float fast_tanh(float v) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * v)), -1.f); }
-
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs on adjacent M tiles of the same N tile; each
 // CTA loads its own A tile and HALF of the shared W tile and multicasts that half into both CTAs, so
 // weight traffic from L2 per CTA halves (48 -> 32 KB per k-block).  A stage may only be refilled when
 // BOTH consumers have released it: every tcgen05.commit on a stage arrives on both CTAs' empty barrier.
+// CL = 3: CTA PAIRS with 2-SM MMA (tcgen05 cta_group::2): the pair computes a 256 x 256 tile, each CTA
+// stages only its own 128 rows of A and its own 128 rows (N half) of W — 32 KB instead of 48 KB per
+// k-block through the SM's ~55 B/cycle ingest, which is what bounds these fp32-operand GEMMs.  The
+// leader CTA's thread issues the MMAs for both; both CTAs' TMA loads complete on the leader's full
+// barrier; tcgen05.commit multicasts stage releases and accumulator-ready signals to both CTAs; both
+// CTAs' epilogues report to the leader's accumulator-empty barrier.
 template <int EPI, int CL>
 __global__ void __launch_bounds__(Cfg<EPI>::NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                  const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  constexpr int STAGES = Cfg<EPI>::STAGES;
+  constexpr bool TWOSM = (CL == 3);
+  constexpr int CSIZE = (CL == 1) ? 1 : 2;                       // CTAs per cluster
+  constexpr int STAGES = TWOSM ? Cfg<EPI>::STAGES_2SM : Cfg<EPI>::STAGES;
+  constexpr int STAGE_BYTES = TWOSM ? (A_BYTES + B_BYTES / 2) : (A_BYTES + B_BYTES);
   constexpr int EPI_WARPS = Cfg<EPI>::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -109,22 +124,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int k_blocks = p.K / BK;
   // work items: CL consecutive M tiles x one N tile; CTA `crank` of the cluster takes M tile CL*mp + crank
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0;
-  const int64_t num_items = ((m_tiles + CL - 1) / CL) * n_tiles;
-  const int64_t item0 = blockIdx.x / CL;
-  const int64_t item_stride = gridDim.x / CL;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+  const uint32_t crank = (CSIZE > 1) ? cluster_ctarank() : 0;
+  const int64_t num_items = ((m_tiles + CSIZE - 1) / CSIZE) * n_tiles;
+  const int64_t item0 = blockIdx.x / CSIZE;
+  const int64_t item_stride = gridDim.x / CSIZE;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSIZE) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_a2); tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+    // empty: CL=2 both consumers release a stage (2 arrivals); 2-SM: one multicast commit per CTA
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL == 2 ? 2 : 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TWOSM ? 2 * EPI_WARPS : EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (TWOSM) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // peer barriers are initialised before anything signals them
+  if (CSIZE > 1) cluster_sync_all();       // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -133,14 +149,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = item0; item < num_items; item += item_stride) {
-        const int m0 = (int)((item / n_tiles) * CL + crank) * BM;
+        const int m0 = (int)((item / n_tiles) * CSIZE + crank) * BM;
         const int n0 = (int)(item % n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);       // CL > 1: released by BOTH CTAs' consumers
+          mbar_wait(&empty_bar[stage], phase ^ 1);       // CL = 2: released by BOTH CTAs' consumers
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           const int k0 = kb * BK;
+          if (TWOSM) {
+            // both CTAs' bytes (2 x 32 KB) land on the LEADER's barrier, which only the leader arms
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (k0 < p.k_split) tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], k0, m0);
+            else tma_load_2d_2sm(sa, &tma_a2, &full_bar[stage], k0 - p.k_split, m0);
+            tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], k0, n0 + (int)crank * (BN / 2));   // my half of W's N rows
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if (k0 < p.k_split) tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
           else tma_load_2d(sa, &tma_a2, &full_bar[stage], k0 - p.k_split, m0);
           if (CL == 1) {
@@ -155,15 +180,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    if (lane == 0 && (!TWOSM || crank == 0)) {                 // 2-SM: only the leader CTA issues
+      constexpr uint32_t idesc = make_idesc_tf32(TWOSM ? 2 * BM : BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        long long tl0 = 0;
+        if (p.timeline && it < 16) tl0 = clock64();
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
+        if (p.timeline && it < 16) { long long* tl = g_timeline + ((int64_t)blockIdx.x * 16 + it) * 6; tl[0] = tl0; tl[1] = clock64(); }
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -173,13 +201,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)              // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-            mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 8; ++k) {            // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+            if (TWOSM) mma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           if (CL == 1) mma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
+          else if (TWOSM) mma_commit_2sm_mcast(&empty_bar[stage], kMask);
           else mma_commit_mcast(&empty_bar[stage], kMask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&acc_full[acc]);                     // accumulator complete -> epilogue
+        if (TWOSM) mma_commit_2sm_mcast(&acc_full[acc], kMask);   // accumulator complete -> both CTAs' epilogues
+        else mma_commit(&acc_full[acc]);
+        if (p.timeline && it < 16) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 2] = clock64();
       }
     }
   } else {
@@ -200,7 +233,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int64_t m_base = ((item / n_tiles) * CL + crank) * BM + q * 32;     // first row of this warp
+      const int64_t m_base = ((item / n_tiles) * CSIZE + crank) * BM + q * 32;  // first row of this warp
       const int n0 = (int)(item % n_tiles) * BN + colq * WCOLS;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + colq * WCOLS;
 
@@ -218,7 +251,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (EPI == EPI_LSTM) {
         // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
         // step i.  Sixteen warps (four per SM sub-partition) hide the latency of the gathered
-        // projected-row / cell-state loads and of the MUFU chains behind one another.
+        // projected-row / cell-state loads and of the MUFU chains behind one another.  Measured with the
+        // device timeline (TMR_TIMELINE=1, scripts/timeline_lstm.py): ~17.7 k cycles per tile against an
+        // ~11 k-cycle main loop, i.e. this epilogue still bounds the recurrent step; tried without gain in
+        // round 1: cross-chunk / cross-tile prefetch of the loads, 7-MUFU cell math, a consecutive-rows
+        // fast path (SASS sampling shows a flat, instruction-bound profile: ~800 instructions per chunk).
         int xr[8];                                      // projected-row index per phase-B step (-1: row >= M)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -227,8 +264,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         const float* xp0 = p.xp + n0 + 4 * pch;
         const int64_t c0 = (m_base + prow) * kD + (n0 >> 2) + pch;      // + 4*i*kD per step, + cc/4 per chunk
+        if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 3] = clock64();
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
+        if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 4] = clock64();
 #pragma unroll 1
         for (int cc = 0; cc < WCOLS; cc += 32) {
           float4 x4[8];
@@ -297,14 +336,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (EPI == EPI_LSTM && p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 5] = clock64();
+      if (lane == 0) { if (TWOSM) mbar_arrive_remote(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's smem / barriers
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (CSIZE > 1) cluster_sync_all();       // the peer may still multicast into this CTA's smem / barriers
+  if (warp == 1) { tc_fence_after(); if (TWOSM) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 static int num_sms() {
@@ -340,21 +380,30 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
     TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
   }
-  static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();
+  static const int tlflag = [] { const char* e = getenv("TMR_TIMELINE"); return e ? atoi(e) : 0; }();
+  const_cast<GemmParams&>(p).timeline = tlflag;
+  static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
-  if (cluster == 2 && m_tiles >= 2) {
-    TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
+  if ((cluster == 2 || cluster == 3) && m_tiles >= 2) {
     const int64_t items = ((m_tiles + 1) / 2) * n_tiles;
     const int max_clusters = num_sms() / 2;
     const int clusters = (int)(items < max_clusters ? items : max_clusters);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(Cfg<EPI>::NTHREADS); cfg.dynamicSmemBytes = smem_bytes<EPI>(); cfg.stream = st;
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(Cfg<EPI>::NTHREADS); cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, p));
+    if (cluster == 3) {
+      cfg.dynamicSmemBytes = smem_bytes<EPI, true>();
+      TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI, true>()));
+      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 3>, ta, ta2, tb, p));
+    } else {
+      cfg.dynamicSmemBytes = smem_bytes<EPI>();
+      TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
+      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, p));
+    }
     return TMR_OK;
   }
   TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
@@ -366,6 +415,12 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
 }
 
 }  // namespace umma
+
+}  // namespace tmr
+extern "C" int tmr_debug_timeline(long long* out_host, int n) {
+  return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
+}
+namespace tmr {
 
 bool umma_available() {
   static int ok = -1;
