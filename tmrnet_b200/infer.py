@@ -25,11 +25,14 @@ class BankInference:
     """
 
     def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 14336,
-                 pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True):
+                 pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True, tail_clips: int = 2048):
         self.model = model
         self.index = index
         self.seq, self.L = int(seq), int(L)
         self.batch_clips = int(batch_clips)
+        # run_host streams features H2D ahead of compute, so the pass ends one batch of compute after the
+        # last copy: a short final batch keeps that exposed tail small
+        self.tail_clips = int(tail_clips)
         self.pad_mode = {"repeat": ops.TMR_PAD_REPEAT, "zero": ops.TMR_PAD_ZERO}[pad_mode]
         self.math_mode = math_mode
         if starts is None:       # every clip of the index; a VideoShard passes its owned clips only
@@ -84,8 +87,10 @@ class BankInference:
         """[(clip_lo, clip_hi, frame_lo, frame_hi)] per batch; frames cover every clip of the batch."""
         out = []
         n = len(self.starts_host)
-        for lo in range(0, n, self.batch_clips):
-            hi = min(n, lo + self.batch_clips)
+        bounds = list(range(0, n, self.batch_clips)) + [n]
+        if self.tail_clips > 0 and len(bounds) > 2 and bounds[-1] - bounds[-2] > 2 * self.tail_clips:
+            bounds.insert(-1, n - self.tail_clips)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
             out.append((lo, hi, int(self.starts_host[lo]), int(self.starts_host[hi - 1]) + self.seq))
         return out
 
