@@ -348,7 +348,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("TMR_MATH", "tf32"), choices=["fp32", "tf32"])
-    ap.add_argument("--batch", type=int, default=14336, help="clips per head launch sequence")
+    ap.add_argument("--batch", type=int, default=18944,
+                    help="clips per head launch sequence (128 x 148 SMs: whole rounds of the persistent GEMMs)")
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

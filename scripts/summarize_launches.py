@@ -1,17 +1,17 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (count, total ms,
-share of the captured window).  Usage: summarize_launches.py launches.csv > profiles/xxx.md"""
+share of the captured window).  Usage: summarize_launches.py launches.csv [skip count] > profiles/xxx.md
+(skip/count select a window of launches, e.g. one timed pass of bench.py)."""
 import collections
 import csv
 import sys
 
 
-def main(path):
+def main(path, skip=0, count=None):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
-    for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    for row in rows[skip:None if count is None else skip + count]:
         v = float(row["Metric Value"].replace(",", ""))
         u = row["Metric Unit"]
         v = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v
@@ -26,4 +26,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], *[int(a) for a in sys.argv[2:4]])

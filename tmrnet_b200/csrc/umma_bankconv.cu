@@ -79,7 +79,9 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
                      const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic on the __shared__ array (no integer round trip) keeps the shared address space, so the
+  // epilogue staging compiles to STS/LDS instead of generic ST.E/LD.E
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* ex = reinterpret_cast<float*>(smem + BC_STAGES * BC_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ex) + BC_EX_BYTES);
   uint64_t* full_bar = bars;                        // [BC_STAGES]

@@ -17,6 +17,15 @@ from .lfb import LFBIndex
 from .ops import D, F, _dev, _mode, _ptr, _stream, _ws, check
 
 
+def default_batch_clips() -> int:
+    """One 128-clip M tile per SM: the persistent GEMMs work on CTA pairs x N tiles, so 128 * SM-count
+    clips (18944 on a 148-SM B200) makes every GEMM of the batch a whole number of rounds over the
+    74 CTA pairs (measured: 10.0 ms/step against 10.7 ms at 14336 clips, 7 rounds where 6.05 are needed)."""
+    if torch.cuda.is_available():
+        return 128 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return 128 * 148
+
+
 class BankInference:
     """Runs the head over every clip of a (shard of a) feature bank in clip batches.
 
@@ -24,15 +33,22 @@ class BankInference:
     index: LFBIndex.from_lengths(video_lengths, seq) for the same frames/rows.
     """
 
-    def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = 14336,
-                 pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True, tail_clips: int = 2048):
+    def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = None,
+                 pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True, tail_clips: int = 0,
+                 host_batch_clips: int = None):
         self.model = model
         self.index = index
         self.seq, self.L = int(seq), int(L)
-        self.batch_clips = int(batch_clips)
-        # run_host streams features H2D ahead of compute, so the pass ends one batch of compute after the
-        # last copy: a short final batch keeps that exposed tail small
+        self.batch_clips = int(batch_clips) if batch_clips else default_batch_clips()
+        # run_host streams features H2D ahead of compute and is PCIe-bound (copies 12.5 ms, kernels
+        # 10 ms per pass of the bench workload): what is left to tune is the compute still running after
+        # the last copy, i.e. the size of the last batches.  Half-size batches (64 clips x SM count)
+        # keep each batch's kernels shorter than its copy and end the pass ~one small batch after the
+        # last copy (scripts/e2e_timeline.py).  tail_clips > 0 additionally splits a short final batch.
+        self.host_batch_clips = int(host_batch_clips) if host_batch_clips else max(128, self.batch_clips // 2)
         self.tail_clips = int(tail_clips)
+        self._host_eng = None
+        self._ctor = dict(pad_mode=pad_mode, math_mode=math_mode, starts=starts, dedup=dedup, tail_clips=tail_clips)
         self.pad_mode = {"repeat": ops.TMR_PAD_REPEAT, "zero": ops.TMR_PAD_ZERO}[pad_mode]
         self.math_mode = math_mode
         if starts is None:       # every clip of the index; a VideoShard passes its owned clips only
@@ -164,23 +180,30 @@ class BankInference:
                 self._launch_batch(ctx, i, feats.data_ptr() + fl * F * 4, out, stream)
         return out
 
-    def run_host(self, feats_host, bank, out=None, host_out=None):
+    def run_host(self, feats_host, bank, out=None, host_out=None, timeline=None):
         """Same pass with the per-frame features in (pinned) HOST memory: each batch's frames are
-        copied H2D on a side stream into one of two staging buffers while the previous batch
-        computes; predictions and scores are copied back D2H at the end.  Returns
+        copied H2D on a side stream into one of three staging buffers while earlier batches
+        compute (three, not two: with two the copy of batch i+2 waits for batch i's kernels, which
+        leaves the last full batch's compute exposed after the final copy); predictions and scores are copied back D2H at the end.  Returns
         (device outputs, (pred_host, score_host))."""
         bank = _dev(bank, "bank")
         dev = bank.device
         if not (isinstance(feats_host, torch.Tensor) and not feats_host.is_cuda and feats_host.dtype == torch.float32
                 and feats_host.dim() == 2 and feats_host.shape[1] == F and feats_host.is_contiguous()):
             raise TypeError(f"feats_host must be a contiguous CPU float32 tensor (n_frames,{F})")
+        if self.host_batch_clips != self.batch_clips:      # host streaming uses its own (smaller) batches
+            if self._host_eng is None:
+                self._host_eng = BankInference(self.model, self.index, self.seq, self.L, self.host_batch_clips,
+                                               host_batch_clips=self.host_batch_clips, **self._ctor)
+            self._host_eng.math_mode = self.math_mode
+            return self._host_eng.run_host(feats_host, bank, out=out, host_out=host_out, timeline=timeline)
         if out is None:
             out = self._alloc_out(dev, False)
         ctx = self._prepare(dev, bank)
         plan = ctx["plan"]
         max_frames = max((fh - fl for _, _, fl, fh in plan), default=1)
         if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < max_frames or self._stage[0].device != dev:
-            self._stage = [torch.empty((max_frames, F), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._stage = [torch.empty((max_frames, F), dtype=torch.float32, device=dev) for _ in range(3)]
             self._copy_stream = torch.cuda.Stream(device=dev)
         if host_out is None:
             n = len(self.starts_host)
@@ -188,20 +211,26 @@ class BankInference:
         with torch.cuda.device(dev):
             compute = torch.cuda.current_stream()
             stream = _stream()
-            copied = [torch.cuda.Event() for _ in plan]
-            freed = [None, None]
+            timed = timeline is not None           # debug: per-batch (copy start, copy done, compute done) events
+            copied = [torch.cuda.Event(enable_timing=timed) for _ in plan]
+            freed = [None, None, None]
             self._copy_stream.wait_stream(compute)          # staging buffers may still be in use by earlier work
             for i, (lo, hi, fl, fh) in enumerate(plan):
-                buf = self._stage[i & 1]
+                buf = self._stage[i % 3]
                 with torch.cuda.stream(self._copy_stream):
-                    if freed[i & 1] is not None:
-                        self._copy_stream.wait_event(freed[i & 1])
+                    if freed[i % 3] is not None:
+                        self._copy_stream.wait_event(freed[i % 3])
+                    if timed:
+                        c0 = torch.cuda.Event(enable_timing=True)
+                        c0.record(self._copy_stream)
                     buf[:fh - fl].copy_(feats_host[fl:fh], non_blocking=True)
                     copied[i].record(self._copy_stream)
                 compute.wait_event(copied[i])
                 self._launch_batch(ctx, i, buf.data_ptr(), out, stream)
-                freed[i & 1] = torch.cuda.Event()
-                freed[i & 1].record(compute)
+                freed[i % 3] = torch.cuda.Event(enable_timing=timed)
+                freed[i % 3].record(compute)
+                if timed:
+                    timeline.append((hi - lo, c0, copied[i], freed[i % 3]))
             host_out[0].copy_(out["pred"], non_blocking=True)
             host_out[1].copy_(out["score"], non_blocking=True)
         return out, host_out
@@ -284,7 +313,7 @@ class VideoShard:
 # ---------------------------------------------------------------------------------------------
 # upstream of the path: bank builder
 # ---------------------------------------------------------------------------------------------
-def build_bank(lfb_model, feats, list_each_length, seq: int = 10, batch_clips: int = 14336, math_mode=None):
+def build_bank(lfb_model, feats, list_each_length, seq: int = 10, batch_clips: int = None, math_mode=None):
     """The reference's LFB construction loop (train_non-local_mutiConv_resnet.py:684-756) with the
     backbone features precomputed: one LSTM pass per valid clip start, h at the last step written
     straight into the device bank (row r = r-th valid start in global order) instead of growing a
@@ -301,6 +330,7 @@ def build_bank(lfb_model, feats, list_each_length, seq: int = 10, batch_clips: i
     lib = _lib.load()
     mode = _mode(math_mode if math_mode is not None else getattr(lfb_model, "math_mode", None))
     ws = None
+    batch_clips = int(batch_clips) if batch_clips else default_batch_clips()
     with torch.cuda.device(dev):
         for lo in range(0, len(starts_host), batch_clips):
             hi = min(len(starts_host), lo + batch_clips)
