@@ -5,7 +5,7 @@ os.environ["TMR_TIMELINE"] = "1"
 import tmrnet_b200 as tb
 from tmrnet_b200 import ops, synth, _lib
 dev = torch.device("cuda:0")
-B, seq = 14336, 10
+B, seq = 18944, 10
 feats = torch.from_numpy(synth.features(B + seq - 1, seed=1)).to(dev)
 sd = synth.head_state_dict(seed=1234)
 m = tb.resnet_lstm(); m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.to(dev).eval()
@@ -24,9 +24,38 @@ a = np.array(buf, dtype=np.int64).reshape(148, 16, 6)
 for cta in (0, 1, 73, 147):
     t0 = a[cta, 0, 0]
     print("CTA", cta)
-    for it in range(7):
+    for it in range(8):
         r = a[cta, it] - t0
         print(f"  tile {it}: mma wait {r[1]-r[0]:6d}  mainloop {r[2]-r[1]:6d}  | epi waits acc {r[4]-r[3]:6d}  epilogue {r[5]-r[4]:6d}   [abs: mma_start {r[1]:7d} mma_end {r[2]:7d} epi_start {r[4]:7d} epi_end {r[5]:7d}]")
-v = a[:, :6]
+v = a[:, :8]
 print("mean mainloop cycles", float((v[:, :, 2] - v[:, :, 1]).mean()), "mean epilogue cycles", float((v[:, :, 5] - v[:, :, 4]).mean()),
       "mean mma wait", float((v[:, :, 1] - v[:, :, 0]).mean()), "mean epi wait", float((v[:, :, 4] - v[:, :, 3]).mean()))
+
+# CTA 0, every epilogue warp: [wait start, accumulator ready, chunk 0 done, done] relative to the MMA thread's t0
+fw = ctypes.CDLL(_lib.LIB_PATH).tmr_debug_timeline_warps
+fw.argtypes = [ctypes.c_void_p, ctypes.c_int]
+bw = (ctypes.c_longlong * (16 * 16 * 4))()
+assert fw(bw, 16 * 16 * 4) == 0
+w = np.array(bw, dtype=np.int64).reshape(16, 16, 4) - a[0, 0, 0]
+for it in range(8):
+    print(f"tile {it}: mma_start {a[0, it, 1] - a[0, 0, 0]} mma_end {a[0, it, 2] - a[0, 0, 0]}")
+    for wi in range(16):
+        r = w[it, wi]
+        print(f"   warp {wi + 2:2d} (q{(wi + 2) & 3}, cols {((wi) >> 2) * 64:3d}): wait_start {r[0]:7d} ready {r[1]:7d} chunk0 {r[2] - r[1]:6d} chunk1 {r[3] - r[2]:6d} done {r[3]:7d}")
+
+# -DTMR_EPI_PROFILE builds only: phases of chunk 0 per warp of CTA 0
+try:
+    fp = ctypes.CDLL(_lib.LIB_PATH).tmr_debug_timeline_phases
+except AttributeError:
+    fp = None
+if fp is not None:
+    fp.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    bp = (ctypes.c_longlong * (16 * 16 * 8))()
+    assert fp(bp, 16 * 16 * 8) == 0
+    ph = np.array(bp, dtype=np.int64).reshape(16, 16, 8)
+    d = np.diff(ph[1:8, :, :7], axis=2).astype(np.float64)      # tiles 1..7
+    names = ["issue loads", "tmem ld", "stage+sync", "wait global", "math", "stores"]
+    print("chunk-0 phases, mean cycles over tiles 1..7 and the 16 warps of CTA 0:")
+    for k, nm in enumerate(names):
+        print(f"   {nm:12s} {d[:, :, k].mean():8.0f}  (min {d[:, :, k].min():6.0f}, max {d[:, :, k].max():6.0f})")
+    print("   total       ", (ph[1:8, :, 6] - ph[1:8, :, 0]).mean())

@@ -56,6 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                "--expt-extended-lambda", "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd[1:1] = os.environ.get("TMR_B200_NVCC_FLAGS", "").split()      # e.g. -DTMR_EPI_PROFILE (experiments)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

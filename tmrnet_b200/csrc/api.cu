@@ -5,6 +5,7 @@
 
 #include <vector>
 
+#include <stdlib.h>
 #include "tmr_internal.h"
 
 namespace tmr {
@@ -38,7 +39,7 @@ static int do_linear(const LinearArgs& g, int mode, cudaStream_t st) {
   if (mode != TMR_MATH_TF32) return simt_linear(g, st);
   LinearArgs h = g;
   if (g.a_scratch) {       // A operand is raw fp32: round it to TF32 (RN) once, then feed the MMA
-    TMR_TRY(launch_round_concat(g.a, g.lda, g.a2, g.lda2, g.k_split, g.K, g.M, g.a_scratch, st));
+    TMR_TRY(launch_round_concat(g.a, g.lda, g.a2, g.lda2, g.k_split, g.K, g.M, g.a_scratch, st, g.a2_plus_a));
     h.a = g.a_scratch; h.lda = g.K; h.a2 = nullptr; h.lda2 = 0; h.k_split = 0;
   }
   return umma_linear(h, st);
@@ -61,8 +62,10 @@ static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof
 // mirror of the pack.  fp32 mode touches neither.
 struct NLWs { float* w0; float* w1; float* s; };
 struct PbSrc { const float* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output
+// defer_residual (tensor-core head paths): `out` gets W4 r + b4 only; the consumer (classifier_impl with
+// y1_plus_St) adds St while it rounds [St || y1] for its GEMM
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
-                        NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr) {
+                        NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr, bool defer_residual = false) {
   const bool tc = mode == TMR_MATH_TF32;
   const float* w = pk + (tc ? NLBlockPacked::fp32_total : 0);
   LinearArgs g;
@@ -86,7 +89,8 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
   TMR_TRY(launch_layernorm_relu(ws.w1, pk + NLBlockPacked::lnw_off, pk + NLBlockPacked::lnb_off, B, ws.w0, tc, st));
   // out = St + W4 r + b4   (dropout is the identity in eval)               (NLB:37-40)
   g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w4_off; g.ldw = kD;
-  g.bias = pk + NLBlockPacked::b4_off; g.residual = St; g.ldr = kD; g.out = out; g.ldo = kD;
+  g.bias = pk + NLBlockPacked::b4_off; g.out = out; g.ldo = kD;
+  if (!(defer_residual && tc)) { g.residual = St; g.ldr = kD; }
   g.M = B; g.N = kD; g.K = kD;
   return do_linear(g, mode, st);
 }
@@ -103,17 +107,30 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   g.a_scratch = tc ? ws.xr : nullptr;
   TMR_TRY(do_linear(g, mode, st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
-  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
-  float* hcur = (seq == 1) ? out : ws.h0;
-  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, ws.c, B, tc && seq > 1, st));
-  for (int t = 1; t < seq; ++t) {
-    const bool last = (t == seq - 1);
-    float* hnext = last ? out : (hcur == ws.h0 ? ws.h1 : ws.h0);
-    if (tc)
-      TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, !last, st));
-    else
-      TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, st));
-    hcur = hnext;
+  // The recurrence runs sub-batch by sub-batch (all seq steps of one before the next): a step reads per clip
+  // 8 KB of projected row + 2 KB c + 2 KB h and writes 2 + 2 KB, i.e. it is HBM-bound (16 KB/clip against
+  // 2.1 MFLOP) unless the sub-batch's rows stay in L2 from one step to the next - consecutive clips share
+  // their projected rows across steps (clip b at step t reads frame b + t).
+  static const int sub_env = [] { const char* e = getenv("TMR_LSTM_SUB"); return e ? atoi(e) : 0; }();
+  const int SUB = (tc && sub_env > 0) ? sub_env : B;
+  for (int lo = 0; lo < B; lo += SUB) {
+    const int nb = (B - lo < SUB) ? B - lo : SUB;
+    const int64_t* st_lo = starts ? starts + lo : nullptr;
+    const float* xp_lo = starts ? xp : xp + (int64_t)lo * seq * 4 * kD;      // no starts: row = m*seq + t
+    float* out_lo = out + (int64_t)lo * kD;
+    float* h0 = ws.h0 + (int64_t)lo * kD; float* h1 = ws.h1 + (int64_t)lo * kD; float* c = ws.c + (int64_t)lo * kD;
+    // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
+    float* hcur = (seq == 1) ? out_lo : h0;
+    TMR_TRY(launch_lstm_cell0(xp_lo, st_lo, seq, hcur, c, nb, tc && seq > 1, st));
+    for (int t = 1; t < seq; ++t) {
+      const bool last = (t == seq - 1);
+      float* hnext = last ? out_lo : (hcur == h0 ? h1 : h0);
+      if (tc)
+        TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, !last, st));
+      else
+        TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, st));
+      hcur = hnext;
+    }
   }
   return TMR_OK;
 }
@@ -121,13 +138,13 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
 struct ClsWs { float* z; float* s; };
 static int classifier_impl(const float* pk, const float* St, const float* y1, int B, int C,
                            float* logits, int64_t* pred, float* score, ClsWs ws, int mode,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool y1_plus_St = false) {
   const bool tc = mode == TMR_MATH_TF32;
   const float* w = pk + (tc ? ClassifierPacked::fp32_total : 0);
   LinearArgs g;   // z = relu(fc_h_c([St || y1]))   (TRAIN:249-251, eval: dropout = identity)
   g.a = St; g.lda = kD; g.a2 = y1; g.lda2 = kD; g.k_split = kD; g.w = w + ClassifierPacked::wh_off;
   g.ldw = 2 * kD; g.bias = pk + ClassifierPacked::bh_off; g.out = ws.z; g.ldo = kD; g.M = B; g.N = kD;
-  g.K = 2 * kD; g.relu = 1; g.a_scratch = tc ? ws.s : nullptr;
+  g.K = 2 * kD; g.relu = 1; g.a_scratch = tc ? ws.s : nullptr; g.a2_plus_a = tc && y1_plus_St;
   TMR_TRY(do_linear(g, mode, st));
   // fc_c (512 -> C) + softmax score + argmax stay fp32 on CUDA cores
   return launch_fc_argmax(ws.z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
@@ -366,8 +383,8 @@ static int head_tail(const void* timeconv_packed, const void* nlblock_packed, co
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, window, B, L, ws.Lt, ws.xr, mode, st));
     Lt_in = ws.Lt;
   }
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st));
-  return classifier_impl((const float*)classifier_packed, St, ws.y1, B, C, logits, pred, score, ws.cls, mode, st);
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st, nullptr, true));
+  return classifier_impl((const float*)classifier_packed, St, ws.y1, B, C, logits, pred, score, ws.cls, mode, st, true);
 }
 
 size_t tmr_head_workspace_bytes(int B, int seq, int L, int D) {
@@ -518,8 +535,8 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, win_i, n_irregular, L, lt_i, xr_i, mode, st));
   }
   PbSrc pbs{pb, lt_i, src_idx};
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs));
-  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, mode, st);
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs, true));
+  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, mode, st, true);
 }
 
 int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,

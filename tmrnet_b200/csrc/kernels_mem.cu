@@ -389,24 +389,31 @@ int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st) 
   TMR_LAUNCH_CHECK("round_tf32_kernel");
   return TMR_OK;
 }
+// dst[m] = round_tf32([a[m] || a2[m]]); a2_plus_a: the second half is round(a2[m] + a[m]) (the non-local
+// block's residual St + W4 r, added here instead of in the GEMM epilogue, which pays ~30 us per batch for it)
 __global__ void round_concat_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ a2, int64_t lda2,
-                                    int k_split, int K, int64_t M, float* __restrict__ dst) {
+                                    int k_split, int K, int64_t M, float* __restrict__ dst, int a2_plus_a) {
   const int64_t n4 = M * (K / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / (K / 4);
     const int k = (int)(i - m * (K / 4)) * 4;
     const float* src = (k < k_split) ? a + m * lda + k : a2 + m * lda2 + (k - k_split);
     float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    if (a2_plus_a && k >= k_split) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(a + m * lda + (k - k_split)));
+      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+    }
     v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
     *reinterpret_cast<float4*>(dst + m * K + k) = v;
   }
 }
 int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
-                        int64_t M, float* dst, cudaStream_t st) {
+                        int64_t M, float* dst, cudaStream_t st, bool a2_plus_a) {
   if (M == 0) return TMR_OK;
   int64_t b = (M * (K / 4) + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
-  round_concat_kernel<<<(unsigned)b, 256, 0, st>>>(a, lda, a2, lda2, a2 ? k_split : K, K, M, dst);
+  round_concat_kernel<<<(unsigned)b, 256, 0, st>>>(a, lda, a2, lda2, a2 ? k_split : K, K, M, dst,
+                                                   (a2 && a2_plus_a && K == 2 * k_split) ? 1 : 0);
   TMR_LAUNCH_CHECK("round_concat_kernel");
   return TMR_OK;
 }

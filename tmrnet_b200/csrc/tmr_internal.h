@@ -16,6 +16,7 @@ struct LinearArgs {
   int64_t M = 0; int N = 0; int K = 0; int relu = 0;
   int round_out = 0;            // round outputs to TF32 (they only feed another tensor-core GEMM)
   float* a_scratch = nullptr;   // TF32 path: [M,K] buffer; A (|a2) is RN-rounded into it first
+  bool a2_plus_a = false;       // with a_scratch and a2: the a2 half becomes round(a2 + a) (deferred residual)
 };
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) ----
@@ -56,7 +57,7 @@ int launch_layernorm_relu(const float* v, const float* w, const float* b, int B,
 int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st);
 // dst[M,K] = round_tf32([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))
 int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
-                        int64_t M, float* dst, cudaStream_t st);
+                        int64_t M, float* dst, cudaStream_t st, bool a2_plus_a = false);
 // logits = z . Wc^T + bc ; score = max softmax prob ; pred = first argmax
 int launch_fc_argmax(const float* z, const float* wc, const float* bc, int B, int C, float* logits,
                      int64_t* pred, float* score, cudaStream_t st);

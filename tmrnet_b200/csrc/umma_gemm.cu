@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "tmr_internal.h"
+#include <type_traits>
 #include "umma_common.cuh"
 
 namespace tmr {
@@ -48,6 +49,9 @@ int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dim
 
 constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
+#ifndef TMR_ABL
+#define TMR_ABL 0     // timing ablations of the LSTM epilogue (WRONG results): 1 no projected-row loads, 2 no c/h I/O, 4 no cell math, 8 no TMEM load
+#endif
 // Per-epilogue configuration.  The LSTM-cell epilogue is latency-bound (gathered projected rows, cell
 // state, MUFU chains), so it gets 16 epilogue warps (4 per SM sub-partition) and pays for their smem
 // transpose tiles with one pipeline stage; the plain epilogue keeps 8 warps and 4 stages.
@@ -71,6 +75,16 @@ constexpr int TMEM_COLS = 512;
 // Debug timeline (TMR_TIMELINE=1): per CTA and tile, clock64 stamps of the MMA thread (wait for a free
 // accumulator, main loop start/end) and of epilogue warp 2 (accumulator ready, epilogue done).
 __device__ long long g_timeline[148 * 16 * 6];
+__device__ long long g_timeline_warps[16 * 16 * 4];   // CTA 0: [tile][epilogue warp][wait start, acc ready, chunk 0 done, done]
+#ifdef TMR_EPI_PROFILE
+// -DTMR_EPI_PROFILE: phase stamps inside chunk 0 of every tile of CTA 0 (scripts/timeline_lstm.py)
+__device__ long long g_timeline_phases[16 * 16 * 8];
+__device__ __forceinline__ long long stamp_dep(float v) {
+  long long t;
+  asm volatile("{ .reg .f32 tmp; mov.f32 tmp, %1; mov.u64 %0, %%clock64; }" : "=l"(t) : "f"(v) : "memory");
+  return t;
+}
+#endif
 
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
@@ -79,6 +93,7 @@ struct GemmParams {
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
   int timeline;
+  int stages;      // > 0: use only this many pipeline stages (experiments)
 };
 
 // Gate non-linearities of the tensor-core path: MUFU ex2/rcp approximations (2 ulp / 1 ulp), four
@@ -90,6 +105,27 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_sigmoid(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
 __device__ __forceinline__ float fast_tanh(float v) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * v)), -1.f); }
+// LSTM cell with 7 MUFU operations instead of 10 (the epilogue is bound by the MIO queue that feeds the
+// MUFU and shared-memory pipes): sigmoid(i)*tanh(g) and f share ONE reciprocal of the product of their
+// denominators, o*tanh(c') another.  With a = e^-i, b = e^-f, d = e^-2g:
+//   sigmoid(i) tanh(g) = (1-d) / ((1+a)(1+d)),  sigmoid(f) = 1 / (1+b).
+// Exponent arguments are clamped to 2^40 so the three-term product stays finite (a gate at -27 is 0 in
+// fp32 anyway); for d = 2^40 the quotient (1-d)/(1+d) is exactly -1.
+__device__ __forceinline__ void lstm_cell_fast(float gi, float gf, float gg, float go, float c, float& cn, float& hn) {
+  const float a = ex2_approx(fminf(-1.4426950408889634f * gi, 40.f));
+  const float b = ex2_approx(fminf(-1.4426950408889634f * gf, 40.f));
+  const float d = ex2_approx(fminf(-2.8853900817779268f * gg, 40.f));
+  const float e = ex2_approx(fminf(-1.4426950408889634f * go, 40.f));
+  const float pa = 1.f + a, pb = 1.f + b, pd = 1.f + d;
+  const float pad = pa * pd;
+  const float r = rcp_approx(pad * pb);
+  cn = (pad * c + (1.f - d) * pb) * r;                     // f*c + i*g
+  const float f2 = ex2_approx(fminf(-2.8853900817779268f * cn, 40.f));
+  hn = (1.f - f2) * rcp_approx((1.f + e) * (1.f + f2));    // o * tanh(c')
+}
+__device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
+  return (mr < p.M) ? (int)((p.starts ? p.starts[mr] : mr * p.seq) + p.t) : -1;
+}
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs on adjacent M tiles of the same N tile; each
 // CTA loads its own A tile and HALF of the shared W tile and multicasts that half into both CTAs, so
 // weight traffic from L2 per CTA halves (48 -> 32 KB per k-block).  A stage may only be refilled when
@@ -120,6 +156,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  const int NST = (p.stages > 0 && p.stages < STAGES) ? p.stages : STAGES;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -164,7 +201,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (k0 < p.k_split) tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], k0, m0);
             else tma_load_2d_2sm(sa, &tma_a2, &full_bar[stage], k0 - p.k_split, m0);
             tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], k0, n0 + (int)crank * (BN / 2));   // my half of W's N rows
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -176,7 +213,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           } else {   // my half of the W tile, written into both CTAs
             tma_load_2d_mcast(sb + crank * (B_BYTES / 2), &tma_b, &full_bar[stage], k0, n0 + (int)crank * (BN / 2), kMask);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -210,7 +247,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (CL == 1) mma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
           else if (TWOSM) mma_commit_2sm_mcast(&empty_bar[stage], kMask);
           else mma_commit_mcast(&empty_bar[stage], kMask);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         if (TWOSM) mma_commit_2sm_mcast(&acc_full[acc], kMask);   // accumulator complete -> both CTAs' epilogues
         else mma_commit(&acc_full[acc]);
@@ -232,6 +269,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int prow = lane >> 3;                         // phase B: row within a group of 4
     const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
     int it = 0;
+    int xrow_next = -1;
     for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -252,57 +290,126 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
       if (EPI == EPI_LSTM) {
         // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
-        // step i.  Sixteen warps (four per SM sub-partition) hide the latency of the gathered
-        // projected-row / cell-state loads and of the MUFU chains behind one another.  Measured with the
-        // device timeline (TMR_TIMELINE=1, scripts/timeline_lstm.py): ~17.7 k cycles per tile against an
-        // ~11 k-cycle main loop, i.e. this epilogue still bounds the recurrent step; tried without gain in
-        // round 1: cross-chunk / cross-tile prefetch of the loads, 7-MUFU cell math, a consecutive-rows
-        // fast path (SASS sampling shows a flat, instruction-bound profile: ~800 instructions per chunk).
+        // step i.  This epilogue, not the MMAs, bounds the recurrent step: ~14.5 k cycles per 128x256 tile
+        // (+ ~3.7 k between tiles) against a ~10 k-cycle main loop (device timeline, TMR_TIMELINE=1,
+        // scripts/timeline_lstm.py).  Phase stamps (-DTMR_EPI_PROFILE) per 32x32 chunk and warp, 16 warps
+        // in lock step: issue 16 loads 1.4 k, tcgen05.ld + wait 2.1 k (TMEM reads ~64 B/clk/SM), staging
+        // 1.0 k, wait for global data ~0, cell math 1.8 k, stores 1.0 k cycles - every phase queues on its
+        // own per-SM port while the others idle.  Without effect on the kernel time in round 1: 10 -> 7
+        // MUFU per cell, prefetching the row indices a tile ahead, fewer TMA stages in flight, cross-chunk
+        // load prefetch; removing the smem staging altogether (wrong results, timing only) gave -4 %.
+        const bool full = m_base + 32 <= p.M;           // warp-uniform: only the last M tile has rows >= M
+        // projected-row index of row m_base + lane: ONE coalesced load per warp, fetched a tile ahead
+        // (the dependent starts[] loads used to sit on the critical path between two tiles)
+        if (it == 0) xrow_next = lstm_xrow(p, m_base + lane);
+        const int xrow = xrow_next;
+        {
+          const int64_t nitem = item + item_stride;
+          if (nitem < num_items) xrow_next = lstm_xrow(p, ((nitem / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
+        }
         int xr[8];                                      // projected-row index per phase-B step (-1: row >= M)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t mr = m_base + 4 * i + prow;
-          xr[i] = (mr < p.M) ? (int)((p.starts ? p.starts[mr] : mr * p.seq) + p.t) : -1;
-        }
+        for (int i = 0; i < 8; ++i) xr[i] = __shfl_sync(0xffffffffu, xrow, 4 * i + prow);
         const float* xp0 = p.xp + n0 + 4 * pch;
         const int64_t c0 = (m_base + prow) * kD + (n0 >> 2) + pch;      // + 4*i*kD per step, + cc/4 per chunk
+        // h only feeds the next step's MMA: round to nearest TF32 ((bits + half ulp) & mask, |h| < 1 is finite)
+        const uint32_t h_add = p.round_h ? 0x1000u : 0u, h_mask = p.round_h ? 0xffffe000u : 0xffffffffu;
+        const bool tlw = p.timeline && it < 16 && blockIdx.x == 0 && lane == 0 && EPI_WARPS == 16;
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 3] = clock64();
+        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 0] = clock64();
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 4] = clock64();
-#pragma unroll 1
-        for (int cc = 0; cc < WCOLS; cc += 32) {
+        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 1] = clock64();
+        // FULL: straight-line code for the eight cells of a chunk, so their MUFU chains interleave
+        auto chunk = [&](int cc, auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
           float4 x4[8];
           float c1[8];
+#ifdef TMR_EPI_PROFILE
+          if (tlw && cc == 0) g_timeline_phases[(it * 16 + warp - 2) * 8 + 0] = clock64();
+#endif
 #pragma unroll
           for (int i = 0; i < 8; ++i) {                   // issue the chunk's global loads first ...
             x4[i] = make_float4(0.f, 0.f, 0.f, 0.f); c1[i] = 0.f;
-            if (xr[i] >= 0) {
+            if (FULL || xr[i] >= 0) {
+#if !(TMR_ABL & 1)
               x4[i] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc));
+#endif
+#if !(TMR_ABL & 2)
               c1[i] = p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)];
+#endif
             }
           }
+#ifdef TMR_EPI_PROFILE
+          long long* ph = g_timeline_phases + (it * 16 + warp - 2) * 8;
+          const bool prof = tlw && cc == 0;
+          if (prof) ph[1] = clock64();                    // loads issued
+#endif
           {
             uint32_t r[32];                               // ... then move the accumulator chunk through smem
+#if (TMR_ABL & 8)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(cc + j + lane);
+#else
             tmem_ld32(t_row + cc, r);
             tmem_ld_wait();
+#endif
+#ifdef TMR_EPI_PROFILE
+            if (prof) ph[2] = stamp_dep(__uint_as_float(r[31]));   // accumulator chunk in registers
+#endif
             __syncwarp();                                 // previous chunk's phase B reads are done
             stage_rows(r);
           }
           __syncwarp();
+#ifdef TMR_EPI_PROFILE
+          if (prof) ph[3] = clock64();                    // staged
+          if (prof) ph[4] = stamp_dep(x4[0].x + x4[7].w + c1[7]);   // global loads have landed
+          float cns[8], hns[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (xr[i] >= 0) {
-              const float4 g = staged(i);
-              const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
-              const float cn = fast_sigmoid(gf) * c1[i] + fast_sigmoid(gi) * fast_tanh(gg);
-              float hn = fast_sigmoid(go) * fast_tanh(cn);
-              if (p.round_h) hn = round_tf32(hn);         // only feeds the next step's MMA
-              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
-              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = hn;
+            const float4 g = staged(i);
+            const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
+            lstm_cell_fast(gi, gf, gg, go, c1[i], cns[i], hns[i]);
+          }
+          if (prof) ph[5] = stamp_dep(((hns[0] + hns[1]) + (hns[2] + hns[3])) + ((hns[4] + hns[5]) + (hns[6] + hns[7])));   // math done
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (FULL || xr[i] >= 0) {
+              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cns[i];
+              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = __uint_as_float((__float_as_uint(hns[i]) + h_add) & h_mask);
             }
           }
+          if (prof) ph[6] = clock64();                    // stores issued
+          return;
+#endif
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (FULL || xr[i] >= 0) {
+              const float4 g = staged(i);
+              const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
+              float cn, hn;
+#if (TMR_ABL & 4)
+              cn = gi + gf + c1[i]; hn = gg + go;
+#else
+              lstm_cell_fast(gi, gf, gg, go, c1[i], cn, hn);
+#endif
+#if (TMR_ABL & 2)
+              if (cn == 123.456f && hn == 654.321f) p.c[0] = cn;      // keep the math alive
+#else
+              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
+              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = __uint_as_float((__float_as_uint(hn) + h_add) & h_mask);
+#endif
+            }
+          }
+        };
+#pragma unroll 1
+        for (int cc = 0; cc < WCOLS; cc += 32) {
+          if (full) chunk(cc, std::true_type{});
+          else chunk(cc, std::false_type{});
+          if (tlw && cc == 0) g_timeline_warps[(it * 16 + warp - 2) * 4 + 2] = clock64();
         }
+        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 3] = clock64();
       } else {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
@@ -384,6 +491,8 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
   }
   static const int tlflag = [] { const char* e = getenv("TMR_TIMELINE"); return e ? atoi(e) : 0; }();
   const_cast<GemmParams&>(p).timeline = tlflag;
+  static const int lstm_stages = [] { const char* e = getenv("TMR_LSTM_STAGES"); return e ? atoi(e) : 0; }();
+  const_cast<GemmParams&>(p).stages = (EPI == EPI_LSTM) ? lstm_stages : 0;
   static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
@@ -419,6 +528,14 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
 }  // namespace umma
 
 }  // namespace tmr
+#ifdef TMR_EPI_PROFILE
+extern "C" int tmr_debug_timeline_phases(long long* out_host, int n) {
+  return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_phases, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
+}
+#endif
+extern "C" int tmr_debug_timeline_warps(long long* out_host, int n) {
+  return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_warps, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
+}
 extern "C" int tmr_debug_timeline(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
 }
