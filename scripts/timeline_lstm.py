@@ -59,3 +59,21 @@ if fp is not None:
     for k, nm in enumerate(names):
         print(f"   {nm:12s} {d[:, :, k].mean():8.0f}  (min {d[:, :, k].min():6.0f}, max {d[:, :, k].max():6.0f})")
     print("   total       ", (ph[1:8, :, 6] - ph[1:8, :, 0]).mean())
+
+# kernel span seen by the device clock of each CTA (first MMA-thread stamp -> last epilogue stamp of warp 2)
+n_t = int((a[0, :, 5] > 0).sum())
+span = a[::2, n_t - 1, 5] - a[::2, 0, 0]
+print(f"tiles per CTA {n_t}; span per leader CTA: mean {span.mean():.0f} max {span.max():.0f} cycles; per tile {span.mean() / n_t:.0f}")
+lead = a[::2, :n_t]
+print("leader CTAs: mainloop", float((lead[:, :, 2] - lead[:, :, 1]).mean()), "mma wait", float((lead[:, :, 1] - lead[:, :, 0]).mean()),
+      "| gap epi_end(t) -> epi_wait_start(t+1)", float((lead[:, 1:, 3] - lead[:, :-1, 5]).mean()),
+      "| tile period (mma_start deltas)", float(np.diff(lead[:, :, 1], axis=1).mean()))
+
+fc = ctypes.CDLL(_lib.LIB_PATH).tmr_debug_timeline_cta
+fc.argtypes = [ctypes.c_void_p, ctypes.c_int]
+bc = (ctypes.c_longlong * (148 * 4))()
+assert fc(bc, 148 * 4) == 0
+k = np.array(bc, dtype=np.int64).reshape(148, 4)
+print("per CTA (cycles): entry->setup done", float((k[:, 1] - k[:, 0]).mean()), "| setup->roles done", float((k[:, 2] - k[:, 1]).mean()),
+      "| roles done->exit", float((k[:, 3] - k[:, 2]).mean()), "| entry->exit mean", float((k[:, 3] - k[:, 0]).mean()), "max", float((k[:, 3] - k[:, 0]).max()))
+print("leader: entry -> first MMA-thread stamp", float((a[::2, 0, 0] - k[::2, 0]).mean()), "| last epilogue stamp (warp 2) -> roles done", float((k[::2, 2] - a[::2, n_t - 1, 5]).mean()))

@@ -126,7 +126,8 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
       const bool last = (t == seq - 1);
       float* hnext = last ? out_lo : (hcur == h0 ? h1 : h0);
       if (tc)
-        TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, !last, st));
+        TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, !last, st,
+                               ws.xp, n_rows_x, frame0));
       else
         TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, st));
       hcur = hnext;

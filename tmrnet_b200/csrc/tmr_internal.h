@@ -31,8 +31,11 @@ int simt_lstm_step(const float* whh, const float* xp, const int64_t* starts, int
 int umma_linear(const LinearArgs& g, cudaStream_t st);
 // x_r = x rounded to TF32 (MMA operand); x = exact values for the identity / pool branches
 int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, int L, float* out, cudaStream_t st);
+// xp_base/xp_rows/xp_row0: the projected matrix itself ([xp_rows][4D], its row 0 = projected-row index
+// xp_row0) so that warps whose 32 clips read 32 consecutive projected rows can fetch them by TMA
 int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
-                   const float* h_prev, float* h_out, float* c, int B, int round_h, cudaStream_t st);
+                   const float* h_prev, float* h_out, float* c, int B, int round_h, cudaStream_t st,
+                   const float* xp_base = nullptr, int64_t xp_rows = 0, int64_t xp_row0 = 0);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const float* bank_r, int64_t n_rows, int64_t r_lo,

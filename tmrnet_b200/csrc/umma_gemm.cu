@@ -49,18 +49,17 @@ int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dim
 
 constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
-#ifndef TMR_ABL
-#define TMR_ABL 0     // timing ablations of the LSTM epilogue (WRONG results): 1 no projected-row loads, 2 no c/h I/O, 4 no cell math, 8 no TMEM load
-#endif
-// Per-epilogue configuration.  The LSTM-cell epilogue is latency-bound (gathered projected rows, cell
-// state, MUFU chains), so it gets 16 epilogue warps (4 per SM sub-partition) and pays for their smem
-// transpose tiles with one pipeline stage; the plain epilogue keeps 8 warps and 4 stages.
+// Per-epilogue configuration.  The LSTM-cell epilogue, not the MMAs, bounds the recurrent step, so it gets
+// 16 epilogue warps (4 per SM sub-partition) and pays for their 32x32 fp32 smem tiles (TMEM transpose
+// staging, and the landing zone of each warp's own TMA loads of projected rows) with one pipeline stage;
+// the plain epilogue keeps 8 warps and 4 / 6 stages.
 template <int EPI> struct Cfg {
   static constexpr int STAGES = (EPI == EPI_LSTM) ? 3 : 4;
   static constexpr int STAGES_2SM = (EPI == EPI_LSTM) ? 5 : 6;      // 32 KB stages in 2-SM mode
   static constexpr int EPI_WARPS = (EPI == EPI_LSTM) ? 16 : 8;
   static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;      // one 32x32 fp32 transpose tile per epilogue warp
+  static constexpr int EPI_TILES = 1;                              // 32x32 fp32 smem tiles per epilogue warp
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_TILES * 4096;
   static constexpr int COLS_PER_WARP = 1024 / EPI_WARPS;         // 4 warps per TMEM lane quarter share 256 columns
 };
 constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
@@ -68,13 +67,14 @@ constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 template <int EPI, bool TWOSM = false> constexpr int smem_bytes() {
   return (TWOSM ? Cfg<EPI>::STAGES_2SM * (A_BYTES + B_BYTES / 2) : Cfg<EPI>::STAGES * STAGE_BYTES) +
-         Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+         Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 constexpr int TMEM_COLS = 512;
 
 // Debug timeline (TMR_TIMELINE=1): per CTA and tile, clock64 stamps of the MMA thread (wait for a free
 // accumulator, main loop start/end) and of epilogue warp 2 (accumulator ready, epilogue done).
 __device__ long long g_timeline[148 * 16 * 6];
+__device__ long long g_timeline_cta[148 * 4];          // per CTA: kernel entry, setup done, roles done, exit (clock64) 
 __device__ long long g_timeline_warps[16 * 16 * 4];   // CTA 0: [tile][epilogue warp][wait start, acc ready, chunk 0 done, done]
 #ifdef TMR_EPI_PROFILE
 // -DTMR_EPI_PROFILE: phase stamps inside chunk 0 of every tile of CTA 0 (scripts/timeline_lstm.py)
@@ -92,6 +92,8 @@ struct GemmParams {
   const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
+  int x_tma; int64_t x_row0;          // tma_x covers the projected rows; its row 0 is projected row x_row0
+  const float* xp_base; int64_t xp_rows;   // host side only: what tma_x is built over
   int timeline;
   int stages;      // > 0: use only this many pipeline stages (experiments)
 };
@@ -139,7 +141,8 @@ __device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
 template <int EPI, int CL>
 __global__ void __launch_bounds__(Cfg<EPI>::NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
-                 const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_x,
+                 const GemmParams p) {
   constexpr bool TWOSM = (CL == 3);
   constexpr int CSIZE = (CL == 1) ? 1 : 2;                       // CTAs per cluster
   constexpr int STAGES = TWOSM ? Cfg<EPI>::STAGES_2SM : Cfg<EPI>::STAGES;
@@ -155,8 +158,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* xfull = bars + 2 * STAGES + 6;   // [EPI_WARPS]  EPI_LSTM: a warp's own projected-row tile has landed
 
   const int NST = (p.stages > 0 && p.stages < STAGES) ? p.stages : STAGES;
+  if (p.timeline && threadIdx.x == 0 && blockIdx.x < 148) g_timeline_cta[blockIdx.x * 4 + 0] = clock64();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BN - 1) / BN;
@@ -174,6 +179,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // empty: CL=2 both consumers release a stage (2 arrivals); 2-SM: one multicast commit per CTA
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL == 2 ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TWOSM ? 2 * EPI_WARPS : EPI_WARPS); }
+    if (EPI == EPI_LSTM) { tma_prefetch_desc(&tma_x); for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&xfull[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { if (TWOSM) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
@@ -182,6 +188,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (CSIZE > 1) cluster_sync_all();       // peer barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.timeline && threadIdx.x == 0 && blockIdx.x < 148) g_timeline_cta[blockIdx.x * 4 + 1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -269,7 +276,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int prow = lane >> 3;                         // phase B: row within a group of 4
     const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
     int it = 0;
+    // EPI_LSTM state: projected-row index of row (m_base + lane) for the next tile; whether the current
+    // chunk's projected rows are in flight by TMA; parity of this warp's mbarrier
     int xrow_next = -1;
+    uint32_t xpar = 0;
+    bool x_pend = false;
+    uint64_t* my_xfull = xfull + (warp - 2);
+    // rows x0 .. x0+31 of the projected matrix, columns col .. col+31 -> this warp's tile (same
+    // SWIZZLE_128B layout as the TMEM staging: row = lane, 16-byte chunk j at j ^ (lane & 7))
+    auto issue_x = [&](int x0, int col) {
+      if (lane == 0) {
+        mbar_expect_tx(my_xfull, 4096);
+        tma_load_2d(sbuf, &tma_x, my_xfull, col, (int)(x0 - p.x_row0));
+      }
+    };
+    if (EPI == EPI_LSTM && item0 < num_items) {
+      xrow_next = lstm_xrow(p, ((item0 / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
+      const int x0 = __shfl_sync(0xffffffffu, xrow_next, 0);
+      if (p.x_tma && __all_sync(0xffffffffu, xrow_next == x0 + lane)) {
+        issue_x(x0, (int)(item0 % n_tiles) * BN + colq * Cfg<EPI>::COLS_PER_WARP);
+        x_pend = true;
+      }
+    }
     for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -290,126 +318,128 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
       if (EPI == EPI_LSTM) {
         // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
-        // step i.  This epilogue, not the MMAs, bounds the recurrent step: ~14.5 k cycles per 128x256 tile
-        // (+ ~3.7 k between tiles) against a ~10 k-cycle main loop (device timeline, TMR_TIMELINE=1,
-        // scripts/timeline_lstm.py).  Phase stamps (-DTMR_EPI_PROFILE) per 32x32 chunk and warp, 16 warps
-        // in lock step: issue 16 loads 1.4 k, tcgen05.ld + wait 2.1 k (TMEM reads ~64 B/clk/SM), staging
-        // 1.0 k, wait for global data ~0, cell math 1.8 k, stores 1.0 k cycles - every phase queues on its
-        // own per-SM port while the others idle.  Without effect on the kernel time in round 1: 10 -> 7
-        // MUFU per cell, prefetching the row indices a tile ahead, fewer TMA stages in flight, cross-chunk
-        // load prefetch; removing the smem staging altogether (wrong results, timing only) gave -4 %.
+        // step i.  This epilogue, not the MMAs, bounds the recurrent step (device timeline TMR_TIMELINE=1,
+        // scripts/timeline_lstm.py: ~14.5 k cycles per 128x256 tile against a ~10 k-cycle main loop when
+        // every lane fetched its projected rows with LDG).  Timing ablations: cell math and the TMEM load
+        // are free, the LSU traffic is not - projected-row loads cost 27 of 94 us per 18944-clip step, the
+        // c/h loads and stores another 30.  So when the warp's 32 clips read 32 CONSECUTIVE projected rows
+        // (every warp except those straddling a video boundary or the end of the batch) the rows arrive by
+        // TMA, one chunk ahead, in the warp's own swizzled tile, and phase A ADDS the accumulator onto them.
         const bool full = m_base + 32 <= p.M;           // warp-uniform: only the last M tile has rows >= M
         // projected-row index of row m_base + lane: ONE coalesced load per warp, fetched a tile ahead
-        // (the dependent starts[] loads used to sit on the critical path between two tiles)
-        if (it == 0) xrow_next = lstm_xrow(p, m_base + lane);
         const int xrow = xrow_next;
-        {
-          const int64_t nitem = item + item_stride;
-          if (nitem < num_items) xrow_next = lstm_xrow(p, ((nitem / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
-        }
-        int xr[8];                                      // projected-row index per phase-B step (-1: row >= M)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xr[i] = __shfl_sync(0xffffffffu, xrow, 4 * i + prow);
-        const float* xp0 = p.xp + n0 + 4 * pch;
-        const int64_t c0 = (m_base + prow) * kD + (n0 >> 2) + pch;      // + 4*i*kD per step, + cc/4 per chunk
+        const int64_t nitem = item + item_stride;
+        if (nitem < num_items) xrow_next = lstm_xrow(p, ((nitem / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
+        const int x0 = __shfl_sync(0xffffffffu, xrow, 0);
+        const bool contig = p.x_tma && __all_sync(0xffffffffu, xrow == x0 + lane);
+        // phase B: a lane owns FOUR consecutive hidden units (16 gate columns) of rows lane/2 and lane/2 + 16,
+        // so c / h move as 128-bit accesses, one full 32-byte sector per row and instruction (a quarter of
+        // the LSU instructions of a unit-per-lane mapping; timing ablation: the c/h traffic, not the cell
+        // math, is what this epilogue pays for)
+        const int half = lane & 1;
+        int xr[2];                                      // projected-row index of the lane's two rows (-1: row >= M)
+        xr[0] = __shfl_sync(0xffffffffu, xrow, lane >> 1);
+        xr[1] = __shfl_sync(0xffffffffu, xrow, (lane >> 1) + 16);
+        const float* xp0 = p.xp + n0 + 16 * half;
+        const int64_t c0 = (m_base + (lane >> 1)) * kD + (n0 >> 2) + 4 * half;   // + 16*kD for the second row, + cc/4 per chunk
         // h only feeds the next step's MMA: round to nearest TF32 ((bits + half ulp) & mask, |h| < 1 is finite)
         const uint32_t h_add = p.round_h ? 0x1000u : 0u, h_mask = p.round_h ? 0xffffe000u : 0xffffffffu;
-        const bool tlw = p.timeline && it < 16 && blockIdx.x == 0 && lane == 0 && EPI_WARPS == 16;
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 3] = clock64();
-        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 0] = clock64();
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 4] = clock64();
-        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 1] = clock64();
-        // FULL: straight-line code for the eight cells of a chunk, so their MUFU chains interleave
-        auto chunk = [&](int cc, auto full_tag) {
+        // FULL: straight-line code for the eight cells of a chunk, so their MUFU chains interleave.
+        // XSMEM: the chunk's projected rows are (being) written into this warp's tile by TMA.
+        // nx_ok: the FOLLOWING chunk's rows can come by TMA too (rows nx_x0.., columns nx_col..): issued as
+        // soon as this chunk's gates have left the tile, so the load flies during the cell math and stores.
+        auto chunk = [&](int cc, auto full_tag, auto xsmem_tag, bool nx_ok, int nx_x0, int nx_col) {
           constexpr bool FULL = decltype(full_tag)::value;
-          float4 x4[8];
-          float c1[8];
-#ifdef TMR_EPI_PROFILE
-          if (tlw && cc == 0) g_timeline_phases[(it * 16 + warp - 2) * 8 + 0] = clock64();
-#endif
+          constexpr bool XSMEM = decltype(xsmem_tag)::value;
+          float4 x4[XSMEM ? 1 : 8];
+          float4 c4[2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {                   // issue the chunk's global loads first ...
-            x4[i] = make_float4(0.f, 0.f, 0.f, 0.f); c1[i] = 0.f;
+          for (int i = 0; i < 2; ++i) {                   // issue the chunk's global loads first ...
+            c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!XSMEM) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) x4[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             if (FULL || xr[i] >= 0) {
-#if !(TMR_ABL & 1)
-              x4[i] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc));
-#endif
-#if !(TMR_ABL & 2)
-              c1[i] = p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)];
-#endif
+              if (!XSMEM) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  x4[4 * i + k] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc + 4 * k));
+              }
+              c4[i] = *reinterpret_cast<const float4*>(p.c + c0 + (int64_t)i * (16 * kD) + (cc >> 2));
             }
           }
-#ifdef TMR_EPI_PROFILE
-          long long* ph = g_timeline_phases + (it * 16 + warp - 2) * 8;
-          const bool prof = tlw && cc == 0;
-          if (prof) ph[1] = clock64();                    // loads issued
-#endif
           {
             uint32_t r[32];                               // ... then move the accumulator chunk through smem
-#if (TMR_ABL & 8)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(cc + j + lane);
-#else
             tmem_ld32(t_row + cc, r);
             tmem_ld_wait();
-#endif
-#ifdef TMR_EPI_PROFILE
-            if (prof) ph[2] = stamp_dep(__uint_as_float(r[31]));   // accumulator chunk in registers
-#endif
-            __syncwarp();                                 // previous chunk's phase B reads are done
-            stage_rows(r);
-          }
-          __syncwarp();
-#ifdef TMR_EPI_PROFILE
-          if (prof) ph[3] = clock64();                    // staged
-          if (prof) ph[4] = stamp_dep(x4[0].x + x4[7].w + c1[7]);   // global loads have landed
-          float cns[8], hns[8];
+            if (XSMEM) {                                  // gates = projected rows (TMA) + accumulator
+              mbar_wait(my_xfull, xpar);
+              xpar ^= 1u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 g = staged(i);
-            const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
-            lstm_cell_fast(gi, gf, gg, go, c1[i], cns[i], hns[i]);
-          }
-          if (prof) ph[5] = stamp_dep(((hns[0] + hns[1]) + (hns[2] + hns[3])) + ((hns[4] + hns[5]) + (hns[6] + hns[7])));   // math done
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (FULL || xr[i] >= 0) {
-              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cns[i];
-              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = __uint_as_float((__float_as_uint(hns[i]) + h_add) & h_mask);
+              for (int j = 0; j < 8; ++j) {
+                float4* a4 = reinterpret_cast<float4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2));
+                float4 v = *a4;
+                v.x += __uint_as_float(r[4 * j]); v.y += __uint_as_float(r[4 * j + 1]);
+                v.z += __uint_as_float(r[4 * j + 2]); v.w += __uint_as_float(r[4 * j + 3]);
+                *a4 = v;
+              }
+            } else {
+              stage_rows(r);
             }
           }
-          if (prof) ph[6] = clock64();                    // stores issued
-          return;
-#endif
+          __syncwarp();
+          float4 g[8];                                    // the lane's 2 rows x 4 units x (i,f,g,o)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 2; ++i) {
+            const int row = (lane >> 1) + 16 * i;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                 // unit 4*half + k of the chunk = 16-byte chunk 4*half + k of the row
+              float4 v = *reinterpret_cast<const float4*>(sbuf + row * 32 + (((4 * half + k) ^ (row & 7)) << 2));
+              if (!XSMEM) { v.x += x4[4 * i + k].x; v.y += x4[4 * i + k].y; v.z += x4[4 * i + k].z; v.w += x4[4 * i + k].w; }
+              g[4 * i + k] = v;
+            }
+          }
+          fence_proxy_async_smem();                       // the tile's generic accesses before its next TMA write
+          __syncwarp();
+          if (nx_ok) issue_x(nx_x0, nx_col);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
             if (FULL || xr[i] >= 0) {
-              const float4 g = staged(i);
-              const float gi = g.x + x4[i].x, gf = g.y + x4[i].y, gg = g.z + x4[i].z, go = g.w + x4[i].w;
-              float cn, hn;
-#if (TMR_ABL & 4)
-              cn = gi + gf + c1[i]; hn = gg + go;
-#else
-              lstm_cell_fast(gi, gf, gg, go, c1[i], cn, hn);
-#endif
-#if (TMR_ABL & 2)
-              if (cn == 123.456f && hn == 654.321f) p.c[0] = cn;      // keep the math alive
-#else
-              p.c[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = cn;
-              p.h_out[c0 + (int64_t)i * (4 * kD) + (cc >> 2)] = __uint_as_float((__float_as_uint(hn) + h_add) & h_mask);
-#endif
+              const float cin[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
+              float cn[4], hn[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 v = g[4 * i + k];
+                lstm_cell_fast(v.x, v.y, v.z, v.w, cin[k], cn[k], hn[k]);
+                hn[k] = __uint_as_float((__float_as_uint(hn[k]) + h_add) & h_mask);
+              }
+              const int64_t o = c0 + (int64_t)i * (16 * kD) + (cc >> 2);
+              *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+              *reinterpret_cast<float4*>(p.h_out + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             }
           }
         };
 #pragma unroll 1
         for (int cc = 0; cc < WCOLS; cc += 32) {
-          if (full) chunk(cc, std::true_type{});
-          else chunk(cc, std::false_type{});
-          if (tlw && cc == 0) g_timeline_warps[(it * 16 + warp - 2) * 4 + 2] = clock64();
+          bool nx_ok = false;
+          int nx_x0 = 0, nx_col = 0;
+          if (cc + 32 < WCOLS) {
+            nx_ok = contig; nx_x0 = x0; nx_col = n0 + cc + 32;
+          } else if (nitem < num_items) {
+            nx_x0 = __shfl_sync(0xffffffffu, xrow_next, 0);
+            nx_ok = p.x_tma && __all_sync(0xffffffffu, xrow_next == nx_x0 + lane);
+            nx_col = (int)(nitem % n_tiles) * BN + colq * WCOLS;
+          }
+          if (x_pend) chunk(cc, std::true_type{}, std::true_type{}, nx_ok, nx_x0, nx_col);
+          else if (full) chunk(cc, std::true_type{}, std::false_type{}, nx_ok, nx_x0, nx_col);
+          else chunk(cc, std::false_type{}, std::false_type{}, nx_ok, nx_x0, nx_col);
+          x_pend = nx_ok;
         }
-        if (tlw) g_timeline_warps[(it * 16 + warp - 2) * 4 + 3] = clock64();
       } else {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
@@ -452,8 +482,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.timeline && threadIdx.x == 0 && blockIdx.x < 148) g_timeline_cta[blockIdx.x * 4 + 2] = clock64();
   if (CSIZE > 1) cluster_sync_all();       // the peer may still multicast into this CTA's smem / barriers
   if (warp == 1) { tc_fence_after(); if (TWOSM) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (p.timeline && threadIdx.x == 0 && blockIdx.x < 148) g_timeline_cta[blockIdx.x * 4 + 3] = clock64();
 }
 
 static int num_sms() {
@@ -470,7 +502,7 @@ static int num_sms() {
 template <int EPI>
 static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, const float* w,
                        int64_t ldw, const GemmParams& p, cudaStream_t st) {
-  CUtensorMap ta, ta2, tb;
+  CUtensorMap ta, ta2, tb, tx;
   {
     const int ka = a2 ? k_split : p.K;
     uint64_t dims[2] = {(uint64_t)ka, (uint64_t)p.M};
@@ -488,6 +520,15 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     uint64_t sw[1] = {(uint64_t)ldw * 4};
     uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
     TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
+    tx = ta;
+    const_cast<GemmParams&>(p).x_tma = 0;
+    if (EPI == EPI_LSTM && p.xp_base && p.xp_rows > 0) {   // projected rows [xp_rows][N], 32 x 32 boxes per epilogue warp
+      uint64_t dx[2] = {(uint64_t)p.N, (uint64_t)p.xp_rows};
+      uint64_t sx[1] = {(uint64_t)p.N * 4};
+      uint32_t bx[2] = {32, 32};
+      TMR_TRY(make_tmap(&tx, p.xp_base, 2, dx, sx, bx));
+      const_cast<GemmParams&>(p).x_tma = 1;
+    }
   }
   static const int tlflag = [] { const char* e = getenv("TMR_TIMELINE"); return e ? atoi(e) : 0; }();
   const_cast<GemmParams&>(p).timeline = tlflag;
@@ -509,18 +550,18 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
     if (cluster == 3) {
       cfg.dynamicSmemBytes = smem_bytes<EPI, true>();
       TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI, true>()));
-      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 3>, ta, ta2, tb, p));
+      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 3>, ta, ta2, tb, tx, p));
     } else {
       cfg.dynamicSmemBytes = smem_bytes<EPI>();
       TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
-      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, p));
+      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 2>, ta, ta2, tb, tx, p));
     }
     return TMR_OK;
   }
   TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI>()));
   const int64_t tiles = m_tiles * n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  umma_gemm_kernel<EPI, 1><<<grid, Cfg<EPI>::NTHREADS, smem_bytes<EPI>(), st>>>(ta, ta2, tb, p);
+  umma_gemm_kernel<EPI, 1><<<grid, Cfg<EPI>::NTHREADS, smem_bytes<EPI>(), st>>>(ta, ta2, tb, tx, p);
   TMR_LAUNCH_CHECK("umma_gemm_kernel");
   return TMR_OK;
 }
@@ -533,6 +574,9 @@ extern "C" int tmr_debug_timeline_phases(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_phases, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
 }
 #endif
+extern "C" int tmr_debug_timeline_cta(long long* out_host, int n) {
+  return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_cta, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
+}
 extern "C" int tmr_debug_timeline_warps(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_warps, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
 }
@@ -566,10 +610,12 @@ int umma_linear(const LinearArgs& g, cudaStream_t st) {
 }
 
 int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t, const float* h_prev,
-                   float* h_out, float* c, int B, int round_h, cudaStream_t st) {
+                   float* h_out, float* c, int B, int round_h, cudaStream_t st, const float* xp_base,
+                   int64_t xp_rows, int64_t xp_row0) {
   if (B == 0) return TMR_OK;
   umma::GemmParams p{};
   p.round_h = round_h;
+  p.xp_base = xp_base; p.xp_rows = xp_rows; p.x_row0 = xp_row0;
   p.M = B; p.N = 4 * kD; p.K = kD; p.k_split = kD;
   p.xp = xp; p.starts = starts; p.seq = seq; p.t = t; p.h_out = h_out; p.c = c;
   return umma::launch_gemm<umma::EPI_LSTM>(h_prev, kD, nullptr, 0, 0, whh, kD, p, st);

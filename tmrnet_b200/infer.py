@@ -17,13 +17,20 @@ from .lfb import LFBIndex
 from .ops import D, F, _dev, _mode, _ptr, _stream, _ws, check
 
 
-def default_batch_clips() -> int:
-    """One 128-clip M tile per SM: the persistent GEMMs work on CTA pairs x N tiles, so 128 * SM-count
-    clips (18944 on a 148-SM B200) makes every GEMM of the batch a whole number of rounds over the
-    74 CTA pairs (measured: 10.0 ms/step against 10.7 ms at 14336 clips, 7 rounds where 6.05 are needed)."""
+MAX_BATCH_CLIPS = 65536      # ~40 KB of workspace per clip (projected rows, rounded features, TimeConv tap products)
+
+
+def _sm_count() -> int:
     if torch.cuda.is_available():
-        return 128 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    return 128 * 148
+        return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return 148
+
+
+def default_host_batch_clips() -> int:
+    """Host-streamed pass: 64 clips x SM count (9472 on a 148-SM B200) - the persistent GEMMs work on
+    CTA pairs x N tiles, so this is a whole number of rounds over the 74 CTA pairs, and each batch's
+    kernels stay shorter than its H2D copy (scripts/e2e_timeline.py)."""
+    return 64 * _sm_count()
 
 
 class BankInference:
@@ -39,13 +46,17 @@ class BankInference:
         self.model = model
         self.index = index
         self.seq, self.L = int(seq), int(L)
-        self.batch_clips = int(batch_clips) if batch_clips else default_batch_clips()
+        # resident pass: as few, equally sized batches as MAX_BATCH_CLIPS allows - every kernel of a batch
+        # pays a pipeline ramp (first main loop, last epilogue), measured on the bench workload (83 k
+        # clips): 9.04 ms/step at 18944 clips per batch, 8.67 at 27776, 8.48 at 41600
+        self.batch_clips = int(batch_clips) if batch_clips else None
         # run_host streams features H2D ahead of compute and is PCIe-bound (copies 12.5 ms, kernels
         # 10 ms per pass of the bench workload): what is left to tune is the compute still running after
         # the last copy, i.e. the size of the last batches.  Half-size batches (64 clips x SM count)
         # keep each batch's kernels shorter than its copy and end the pass ~one small batch after the
         # last copy (scripts/e2e_timeline.py).  tail_clips > 0 additionally splits a short final batch.
-        self.host_batch_clips = int(host_batch_clips) if host_batch_clips else max(128, self.batch_clips // 2)
+        self.host_batch_clips = int(host_batch_clips) if host_batch_clips else (
+            max(128, self.batch_clips // 2) if self.batch_clips else default_host_batch_clips())
         self.tail_clips = int(tail_clips)
         self._host_eng = None
         self._ctor = dict(pad_mode=pad_mode, math_mode=math_mode, starts=starts, dedup=dedup, tail_clips=tail_clips)
@@ -103,7 +114,11 @@ class BankInference:
         """[(clip_lo, clip_hi, frame_lo, frame_hi)] per batch; frames cover every clip of the batch."""
         out = []
         n = len(self.starts_host)
-        bounds = list(range(0, n, self.batch_clips)) + [n]
+        per = self.batch_clips
+        if not per:                                # even split, rounded up to whole 128-clip M tiles
+            nb = max(1, -(-n // MAX_BATCH_CLIPS))
+            per = max(128, -(-(-(-n // nb)) // 128) * 128)
+        bounds = list(range(0, n, per)) + [n]
         if self.tail_clips > 0 and len(bounds) > 2 and bounds[-1] - bounds[-2] > 2 * self.tail_clips:
             bounds.insert(-1, n - self.tail_clips)
         for lo, hi in zip(bounds[:-1], bounds[1:]):
@@ -330,7 +345,7 @@ def build_bank(lfb_model, feats, list_each_length, seq: int = 10, batch_clips: i
     lib = _lib.load()
     mode = _mode(math_mode if math_mode is not None else getattr(lfb_model, "math_mode", None))
     ws = None
-    batch_clips = int(batch_clips) if batch_clips else default_batch_clips()
+    batch_clips = int(batch_clips) if batch_clips else MAX_BATCH_CLIPS
     with torch.cuda.device(dev):
         for lo in range(0, len(starts_host), batch_clips):
             hi = min(len(starts_host), lo + batch_clips)
