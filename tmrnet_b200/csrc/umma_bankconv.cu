@@ -21,6 +21,7 @@
 // and the epilogue applies the shift by exchanging accumulator rows through shared memory (3-row halo,
 // 122 of 128 rows emitted per tile).  (Taking the shifts as row-offset descriptor views of one smem
 // tile — matrix base offset — was tried first and produced wrong products on B200.)
+#include <stdlib.h>
 #include "tmr_internal.h"
 #include "umma_common.cuh"
 
@@ -64,6 +65,7 @@ struct BankConvParams {
   const float* bank; float* pb; const float* bias3; const float* bias5; const float* bias7;
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
   int64_t num_tiles;
+  int ablate;      // timing experiments (WRONG results), env TMR_BC_ABL: 1 = epilogue only hands the accumulator back, 2 = no global stores
 };
 
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 =
@@ -153,50 +155,90 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     }
   } else {
     const int q = warp & 3;
-    const int r = q * 32 + lane;                                    // row inside the tile = TMEM lane
-    // exchange layout: ex[tap][row][8]; taps 0..6 = conv7 t=-3..3, 7..11 = conv5 t=-2..2, 12..14 = conv3 t=-1..1
-    auto exq = [&](int tap, int row) -> float* { return ex + ((size_t)tap * BC_BM + row) * 8; };
+    const int r = q * 32 + lane;                                    // phase 1: row inside the tile = TMEM lane
+    // exchange layout: ex[tap][row][8 channels]; taps 0..6 = conv7 t=-3..3, 7..11 = conv5 t=-2..2, 12..14 =
+    // conv3 t=-1..1.  The two 16-byte halves of a row swap places in rows with bit 2 set, so 128-bit accesses
+    // by eight consecutive rows (phase 1) or by eight (row, half) pairs (phase 2) never share a bank group.
+    auto exh = [&](int tap, int row, int h) -> float4* {
+      return reinterpret_cast<float4*>(ex + ((size_t)tap * BC_BM + row) * 8 + ((h ^ ((row >> 2) & 1)) << 2));
+    };
+    // phase 2: a lane owns FOUR channels (half = lane & 1 of the 8-channel chunk) of rows 32q + lane/2 and
+    // 32q + lane/2 + 16, so every global load / store instruction covers whole 32-byte sectors (16 rows x
+    // 32 B) instead of 32 half-filled ones (row per thread).
+    const int half = lane & 1;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int n0 = (int)(tile % N_TILES) * BC_NCH;
       const int64_t q0 = p.row_base + (tile / N_TILES) * BC_OUT - 3;
-      const int64_t rho = q0 + r;                                   // bank row of this thread
-      const int64_t prow = rho - p.row_base;
-      const bool valid = r >= 3 && r < 3 + BC_OUT && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
-      const bool has_next = valid && (rho + 1 < p.n_rows);
-      // exact bank values of this row and of the next one (identity / pool branches): requested before the
-      // accumulator is ready so their latency hides behind the main loop
-      float4 x0v[BC_NCH / 4], x1v[BC_NCH / 4];
+      bool valid[2];
+      int64_t prow[2];
+      // exact bank values of the lane's rows and of the next ones (identity / pool branches): requested before
+      // the accumulator is ready so their latency hides behind the main loop
+      float4 x0v[2][2], x1v[2][2];                                  // [pass][8-channel chunk]
 #pragma unroll
-      for (int h = 0; h < BC_NCH / 4; ++h) {
-        x0v[h] = valid ? __ldg(reinterpret_cast<const float4*>(p.bank + rho * kD + n0) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x1v[h] = has_next ? __ldg(reinterpret_cast<const float4*>(p.bank + (rho + 1) * kD + n0) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ps = 0; ps < 2; ++ps) {
+        const int r2 = q * 32 + (lane >> 1) + 16 * ps;
+        const int64_t rho = q0 + r2;                                // bank row
+        prow[ps] = rho - p.row_base;
+        valid[ps] = r2 >= 3 && r2 < 3 + BC_OUT && prow[ps] >= 0 && prow[ps] < p.pb_rows && rho < p.n_rows;
+        const bool has_next = valid[ps] && (rho + 1 < p.n_rows);
+#pragma unroll
+        for (int c8 = 0; c8 < 2; ++c8) {
+          const float* src = p.bank + rho * kD + n0 + 8 * c8 + 4 * half;
+          x0v[ps][c8] = valid[ps] ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x1v[ps][c8] = has_next ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      float* dst = p.pb + (valid ? prow : 0) * (7 * kD) + n0;
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (p.ablate & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        continue;
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll
       for (int cc = 0; cc < BC_NCH; cc += 8) {
         {
-          // a channel's taps are consecutive TMEM columns: three 8-column loads per channel (7 / 5 / 3 taps used)
-          float v[8];
+          // phase 1.  A channel's taps are consecutive TMEM columns, so the chunk's 8 channels x K taps are ONE
+          // run of 56 / 40 / 24 columns: a few wide tcgen05.ld instead of 24 narrow load + wait pairs, and
+          // the row goes to the exchange buffer as two 128-bit stores per tap (8 channels).
+          uint32_t v[32], w[32];
+          tmem_ld32(t_row + col7(cc), v);
+          tmem_ld32(t_row + col7(cc) + 32, w);           // 56 used; the rest belongs to the next channels / conv5
+          tmem_ld_wait();
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            tmem_ld8(t_row + col7(cc + ch), v);
-            tmem_ld_wait();
+          for (int t = 0; t < 7; ++t)
 #pragma unroll
-            for (int t = 0; t < 7; ++t) exq(t, r)[ch] = v[t];
-            tmem_ld8(t_row + col5(cc + ch), v);
-            tmem_ld_wait();
+            for (int h = 0; h < 2; ++h) {
+              uint32_t e[4];
 #pragma unroll
-            for (int t = 0; t < 5; ++t) exq(7 + t, r)[ch] = v[t];
-            tmem_ld8(t_row + col3(cc + ch), v);
-            tmem_ld_wait();
+              for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 7 + t; e[c] = idx < 32 ? v[idx] : w[idx - 32]; }
+              *reinterpret_cast<uint4*>(exh(t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+          float f8[8];
+          tmem_ld32(t_row + col5(cc), v);
+          tmem_ld8(t_row + col5(cc) + 32, f8);
+          tmem_ld_wait();
 #pragma unroll
-            for (int t = 0; t < 3; ++t) exq(12 + t, r)[ch] = v[t];
-          }
+          for (int t = 0; t < 5; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t e[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 5 + t; e[c] = idx < 32 ? v[idx] : __float_as_uint(f8[idx - 32]); }
+              *reinterpret_cast<uint4*>(exh(7 + t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
+            }
+          tmem_ld32(t_row + col3(cc), v);                // 24 used (columns up to 247 of the 256-column buffer)
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              *reinterpret_cast<uint4*>(exh(12 + t, r, h)) =
+                  make_uint4(v[(4 * h) * 3 + t], v[(4 * h + 1) * 3 + t], v[(4 * h + 2) * 3 + t], v[(4 * h + 3) * 3 + t]);
         }
         if (cc + 8 >= BC_NCH) {                         // last TMEM read of this tile: hand the buffer back early
           tc_fence_before();
@@ -204,45 +246,34 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
         epi_barrier();
-        if (valid) {
-          // P_{K,t}[rho] = Q_{K,t}[rho - t]: row r - t of the exchange buffer
-          float P7[7][8], P5[5][8], P3[3][8];
+        const float4 bb3 = __ldg(reinterpret_cast<const float4*>(p.bias3 + n0 + cc + 4 * half));
+        const float4 bb5 = __ldg(reinterpret_cast<const float4*>(p.bias5 + n0 + cc + 4 * half));
+        const float4 bb7 = __ldg(reinterpret_cast<const float4*>(p.bias7 + n0 + cc + 4 * half));
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          if (!valid[ps]) continue;
+          const int r2 = q * 32 + (lane >> 1) + 16 * ps;
+          // P_{K,t}[rho] = Q_{K,t}[rho - t]: row r2 - t of the exchange buffer
+          float P7[7][4], P5[5][4], P3[3][4];
 #pragma unroll
           for (int t = -3; t <= 3; ++t) {
-            const float4 a = *reinterpret_cast<const float4*>(exq(t + 3, r - t));
-            const float4 b = *reinterpret_cast<const float4*>(exq(t + 3, r - t) + 4);
+            const float4 a = *exh(t + 3, r2 - t, half);
             P7[t + 3][0] = a.x; P7[t + 3][1] = a.y; P7[t + 3][2] = a.z; P7[t + 3][3] = a.w;
-            P7[t + 3][4] = b.x; P7[t + 3][5] = b.y; P7[t + 3][6] = b.z; P7[t + 3][7] = b.w;
             if (t >= -2 && t <= 2) {
-              const float4 c = *reinterpret_cast<const float4*>(exq(7 + t + 2, r - t));
-              const float4 d = *reinterpret_cast<const float4*>(exq(7 + t + 2, r - t) + 4);
+              const float4 c = *exh(7 + t + 2, r2 - t, half);
               P5[t + 2][0] = c.x; P5[t + 2][1] = c.y; P5[t + 2][2] = c.z; P5[t + 2][3] = c.w;
-              P5[t + 2][4] = d.x; P5[t + 2][5] = d.y; P5[t + 2][6] = d.z; P5[t + 2][7] = d.w;
             }
             if (t >= -1 && t <= 1) {
-              const float4 c = *reinterpret_cast<const float4*>(exq(12 + t + 1, r - t));
-              const float4 d = *reinterpret_cast<const float4*>(exq(12 + t + 1, r - t) + 4);
+              const float4 c = *exh(12 + t + 1, r2 - t, half);
               P3[t + 1][0] = c.x; P3[t + 1][1] = c.y; P3[t + 1][2] = c.z; P3[t + 1][3] = c.w;
-              P3[t + 1][4] = d.x; P3[t + 1][5] = d.y; P3[t + 1][6] = d.z; P3[t + 1][7] = d.w;
             }
           }
-          float b3[8], b5[8], b7[8], x0[8], x1[8];
+          const float b3[4] = {bb3.x, bb3.y, bb3.z, bb3.w}, b5[4] = {bb5.x, bb5.y, bb5.z, bb5.w}, b7[4] = {bb7.x, bb7.y, bb7.z, bb7.w};
+          const float4 xa = x0v[ps][cc / 8], xb = x1v[ps][cc / 8];
+          const float x0[4] = {xa.x, xa.y, xa.z, xa.w}, x1[4] = {xb.x, xb.y, xb.z, xb.w};
+          float out[7][4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias3 + n0 + cc) + h);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias5 + n0 + cc) + h);
-            const float4 c = __ldg(reinterpret_cast<const float4*>(p.bias7 + n0 + cc) + h);
-            const float4 d = x0v[cc / 4 + h];
-            const float4 e = x1v[cc / 4 + h];
-            b3[4 * h] = a.x; b3[4 * h + 1] = a.y; b3[4 * h + 2] = a.z; b3[4 * h + 3] = a.w;
-            b5[4 * h] = b.x; b5[4 * h + 1] = b.y; b5[4 * h + 2] = b.z; b5[4 * h + 3] = b.w;
-            b7[4 * h] = c.x; b7[4 * h + 1] = c.y; b7[4 * h + 2] = c.z; b7[4 * h + 3] = c.w;
-            x0[4 * h] = d.x; x0[4 * h + 1] = d.y; x0[4 * h + 2] = d.z; x0[4 * h + 3] = d.w;
-            x1[4 * h] = e.x; x1[4 * h + 1] = e.y; x1[4 * h + 2] = e.z; x1[4 * h + 3] = e.w;
-          }
-          float out[7][8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             // R_b = bias + sum_{t=0..b} P_t ; Lf_a = sum_{t=-a..-1} P_t ; conv(a,b) = Lf_a + R_b
             const float r7_0 = b7[j] + P7[3][j], r7_1 = r7_0 + P7[4][j], r7_2 = r7_1 + P7[5][j], r7_3 = r7_2 + P7[6][j];
             const float l7_1 = P7[2][j], l7_2 = l7_1 + P7[1][j], l7_3 = l7_2 + P7[0][j];
@@ -260,11 +291,11 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
             out[5][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_1, l5_2 + r5_1), full3), idp);         // k = L-2
             out[6][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_2, full5), full3), idp);               // k = L-3
           }
+          if (!(p.ablate & 2) || out[0][0] == 123.456f) {
+            float* dst = p.pb + prow[ps] * (7 * kD) + n0 + cc + 4 * half;
 #pragma unroll
-          for (int v = 0; v < 7; ++v) {
-            float4* d4 = reinterpret_cast<float4*>(dst + v * kD + cc);
-            d4[0] = make_float4(out[v][0], out[v][1], out[v][2], out[v][3]);
-            d4[1] = make_float4(out[v][4], out[v][5], out[v][6], out[v][7]);
+            for (int v = 0; v < 7; ++v)
+              *reinterpret_cast<float4*>(dst + v * kD) = make_float4(out[v][0], out[v][1], out[v][2], out[v][3]);
           }
         }
         epi_barrier();                                   // exchange buffer is reused by the next 8 channels / tile
@@ -292,6 +323,8 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
   p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
   p.n_rows = n_rows; p.row_base = row_base; p.pb_rows = pb_rows; p.r_lo = r_lo;
   p.num_tiles = ((pb_rows + BC_OUT - 1) / BC_OUT) * (kD / BC_NCH);
+  static const int abl = [] { const char* e = getenv("TMR_BC_ABL"); return e ? atoi(e) : 0; }();
+  p.ablate = abl;
   CUtensorMap tx, tw3, tw5, tw7;
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
