@@ -70,7 +70,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,7 +95,7 @@ class ClockSampler:
         window = "timed region"
         if not rows:                       # timed region shorter than one sample: use the whole loaded run
             rows = [r for _, r in self.rows]
-            window = "warm-up + timed + e2e (timed region shorter than the 100 ms sampling period)"
+            window = "warm-up + timed + e2e (timed region shorter than the sampling period)"
         for r in rows:
             try:
                 sm.append(float(r[0]))
