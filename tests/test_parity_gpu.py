@@ -575,3 +575,34 @@ def test_bank_builder_is_self_consistent_with_the_head():
     lf = orc.get_long_feature(starts, orc.build_start_dict(starts.tolist()), ref_bank.numpy(), L)
     ref_logits = orc.head(x, lf, _sd(7))[0]
     assert rel_err(out["logits"], ref_logits) < 2e-3      # bank itself came from the TF32 path
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA-graph replay of the per-clip head at the reference's batch sizes (tmrnet_b200.graphs)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B", [4, 120])
+def test_graphed_head_is_bit_identical_to_direct_calls(mode, B):
+    _need_mode(mode)
+    from tmrnet_b200.graphs import GraphedHead
+    m = _model(7)
+    m.math_mode = mode
+    gh = GraphedHead(m, B, L=30)
+    rng = np.random.default_rng(B)
+    for rep in range(3):                       # replays with fresh inputs; outputs are static views -> clone
+        x = torch.from_numpy(rng.standard_normal((B, 10, 2048), dtype=np.float32)).clamp_min(0).mul(0.5).to(_dev())
+        lf = torch.from_numpy(np.tanh(rng.standard_normal((B, 30, 512), dtype=np.float32)) * 0.5).to(_dev())
+        logits, pred, score = (t.clone() for t in gh.run(x.reshape(-1, 2048), lf))
+        with torch.no_grad():
+            l2, p2, s2 = m.predict(x, lf)
+        assert torch.equal(logits, l2) and torch.equal(pred, p2) and torch.equal(score, s2)
+    # a weight update rebuilds the packs: the graph must be re-captured, not replayed on stale weights
+    with torch.no_grad():
+        m.fc_c.bias.add_(0.25)
+    logits, _, _ = (t.clone() for t in gh.run(x, lf))
+    with torch.no_grad():
+        l2 = m(x, lf)
+        m.fc_c.bias.sub_(0.25)
+    assert torch.equal(logits, l2)
+    m.math_mode = None

@@ -1,0 +1,69 @@
+"""CUDA-graph replay of the per-clip head for the reference's own batch sizes.
+
+The reference calls `model.forward(inputs, long_feature)` on batches of 1200 frames / seq = 120 clips
+(train_non-local_mutiConv_resnet.py:836-880, eval ...resnest.py:470-495).  At that size the ~27 kernels of
+`tmr_head_fwd` are launch-bound, so `GraphedHead` captures them ONCE into a CUDA graph over static buffers
+and replays it per batch: inputs are copied into the static buffers on the caller's stream, outputs are
+views of static tensors (valid until the next `run`).  Nothing else changes: same C ABI call, same kernels,
+same results bit for bit.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+F, D = 2048, 512
+
+
+class GraphedHead:
+    """model: tmrnet_b200.resnet_lstm (eval).  One graph per (B, L); re-captured when the packed weights are
+    rebuilt (parameter update / load_state_dict) or the math mode changes."""
+
+    def __init__(self, model, batch_clips: int, L: int = 30, device=None):
+        self.model = model
+        self.B, self.L, self.seq = int(batch_clips), int(L), int(model.sequence_length)
+        dev = torch.device(device) if device is not None else next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedHead needs a CUDA device (there is no CPU fallback)")
+        self.device = dev
+        self.x = torch.zeros((self.B, self.seq, F), dtype=torch.float32, device=dev)
+        self.long_feature = torch.zeros((self.B, self.L, D), dtype=torch.float32, device=dev)
+        self._graph = None
+        self._key = None
+        self._out = None
+
+    def _capture_key(self):
+        packs = self.model.packs()
+        mode = ops._mode(self.model.math_mode)
+        return tuple(p.data_ptr() if p is not None else 0 for p in packs) + (mode,)
+
+    def _capture(self):
+        packs = self.model.packs()
+        mode = self.model.math_mode
+
+        def call():
+            return ops.head_fwd(*packs, self.x, self.long_feature, self.model.num_class, mode)
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                     # warm-up outside capture (attribute setup, allocator)
+            for _ in range(2):
+                call()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = call()
+        self._graph, self._out, self._packs = g, out, packs      # keep the packs (and workspace) alive
+
+    def run(self, x, long_feature):
+        """x: (B, seq, 2048) or (B*seq, 2048); long_feature: (B, L, 512).  Returns (logits, pred, score)."""
+        with torch.no_grad(), torch.cuda.device(self.device):
+            key = self._capture_key()
+            if self._graph is None or key != self._key:
+                self._capture()
+                self._key = key
+            self.x.copy_(x.reshape(self.B, self.seq, F), non_blocking=True)
+            self.long_feature.copy_(long_feature, non_blocking=True)
+            self._graph.replay()
+        return self._out
