@@ -176,6 +176,11 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
  *   src_idx          device int32[B]: regular clip -> (frame2row[starts[b]] - 1) - pb_row_base (>= L-1);
  *                    irregular clip -> -1 - j, j its position in irregular_starts;
  *   irregular_starts device int64[n_irregular] global start frames of the irregular clips;
+ *   irregular_rows   device int32[n_irregular_rows], ascending: the DISTINCT bank rows the irregular clips'
+ *                    windows touch (a few dozen around each video start).  Given them, the irregular clips'
+ *                    TimeConv is assembled from per-row tap products as well (15 x D per listed row, summed
+ *                    per (clip, slot) over the slot's own neighbours); with n_irregular_rows = 0 they go
+ *                    through the per-clip gather + TimeConv instead;
  *   pb_row_base, pb_rows  bank row range covering slot L-1 of the first regular clip .. slot 0 of the
  *                    last one (pb_rows = 0 when the batch has no regular clip).  Needs L >= 6. */
 /* The bank-level TimeConv alone: pb[(row - row_base)*7 + v][D] for bank rows row_base .. row_base+pb_rows-1,
@@ -183,14 +188,15 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
 size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D);
 int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
                      int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream);
-size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
-                                             int L, int D);
+size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int n_irregular_rows,
+                                             int64_t pb_rows, int L, int D);
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
                               const void* nlblock_packed, const void* classifier_packed,
                               const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
                               int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
                               int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
-                              const int64_t* irregular_starts, int n_irregular, int64_t pb_row_base,
+                              const int64_t* irregular_starts, int n_irregular, const int32_t* irregular_rows,
+                              int n_irregular_rows, int64_t pb_row_base,
                               int64_t pb_rows, int seq, int L, int F, int D, int C, int pad_mode,
                               float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
                               size_t workspace_bytes, void* stream);

@@ -50,8 +50,8 @@ SIGNATURES = {
                             + [_p, _p, _p, _p, _p, _sz, _i, _p]),
     "tmr_bankconv_workspace_bytes": (_sz, [_i64, _i]),
     "tmr_bankconv_fwd": (_i, [_p, _p, _i64, _i64, _i64, _i, _p, _p, _sz, _p]),
-    "tmr_head_frames_dedup_workspace_bytes": (_sz, [_i64, _i, _i, _i64, _i, _i]),
-    "tmr_head_frames_dedup_fwd": (_i, [_p] * 5 + [_i64, _i64, _p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _i64, _i64]
+    "tmr_head_frames_dedup_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i64, _i, _i]),
+    "tmr_head_frames_dedup_fwd": (_i, [_p] * 5 + [_i64, _i64, _p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _p, _i, _i64, _i64]
                                   + [_i] * 6 + [_p, _p, _p, _p, _p, _sz, _p]),
     "tmr_head_train_workspace_bytes": (_sz, [_i] * 6),
     "tmr_head_train_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _p, _p, _sz, _p]),

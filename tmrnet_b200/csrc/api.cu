@@ -470,13 +470,16 @@ int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_r
   return umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows, pb, st);
 }
 
-size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int64_t pb_rows,
-                                             int L, int D) {
+size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int n_irregular_rows,
+                                             int64_t pb_rows, int L, int D) {
   const size_t b = (size_t)(B > 0 ? B : 1);
   const size_t ni = (size_t)(n_irregular > 0 ? n_irregular : 1);
   const size_t pr = (size_t)(pb_rows > 0 ? pb_rows : 1);
+  const size_t nr = (size_t)(n_irregular_rows > 0 ? n_irregular_rows : 0);
+  const size_t irr = (n_irregular > 0 && nr > 0) ? fbytes(nr * 15 * D) + fbytes(nr * D) + fbytes(ni * L)
+                                                 : 2 * fbytes(ni * L * D);
   return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + fbytes((pr + 8) * D) + fbytes(pr * 7 * D) +
-         3 * fbytes(ni * L * D) + 2 * fbytes(b * D) + tmr_nlblock_workspace_bytes((int)b, D) +
+         fbytes(ni * L * D) + irr + 2 * fbytes(b * D) + tmr_nlblock_workspace_bytes((int)b, D) +
          tmr_classifier_workspace_bytes((int)b, D);
 }
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
@@ -484,7 +487,8 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
                               const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
                               int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
                               int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
-                              const int64_t* irregular_starts, int n_irregular, int64_t pb_row_base,
+                              const int64_t* irregular_starts, int n_irregular, const int32_t* irregular_rows,
+                              int n_irregular_rows, int64_t pb_row_base,
                               int64_t pb_rows, int seq, int L, int F, int D, int C, int pad_mode,
                               float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
                               size_t workspace_bytes, void* stream) {
@@ -500,6 +504,8 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   TMR_CHECK_ARG(lstm_packed && timeconv_packed && nlblock_packed && classifier_packed && feats && bank && frame2row &&
                 starts && src_idx && logits && workspace, "head_frames_dedup: null pointer");
   TMR_CHECK_ARG(n_irregular == 0 || irregular_starts, "head_frames_dedup: irregular_starts is null");
+  TMR_CHECK_ARG(n_irregular_rows >= 0 && (n_irregular_rows == 0 || irregular_rows), "head_frames_dedup: irregular_rows is null");
+  const bool irr_rows = n_irregular > 0 && n_irregular_rows > 0;   // assemble from per-row tap products
   TMR_CHECK_ARG(pad_mode != TMR_PAD_ZERO || frame2vstart, "head_frames_dedup: TMR_PAD_ZERO needs frame2vstart");
   TMR_CHECK_ARG(pb_row_base >= 0 && pb_row_base + pb_rows <= n_rows, "head_frames_dedup: PB row range outside the bank");
   TMR_CHECK_ARG(aligned16(feats) && aligned16(bank) && aligned16(workspace), "head_frames_dedup: pointers must be 16-byte aligned");
@@ -512,16 +518,24 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   float* bank_r = cv.take((size_t)(pb_rows + 8) * kD);
   float* pb = cv.take((size_t)(pb_rows > 0 ? pb_rows : 1) * 7 * kD);
   const size_t ni = (size_t)(n_irregular > 0 ? n_irregular : 1);
-  float* win_i = cv.take(ni * L * kD);
   float* lt_i = cv.take(ni * L * kD);
-  float* xr_i = cv.take(ni * L * kD);
+  float *win_i = nullptr, *xr_i = nullptr, *q_i = nullptr, *xc_i = nullptr;
+  int32_t* wrows_i = nullptr;
+  if (irr_rows) {
+    q_i = cv.take((size_t)n_irregular_rows * 15 * kD); xc_i = cv.take((size_t)n_irregular_rows * kD);
+    wrows_i = reinterpret_cast<int32_t*>(cv.take(ni * L));
+    ok = ok && q_i && xc_i && wrows_i;
+  } else {
+    win_i = cv.take(ni * L * kD); xr_i = cv.take(ni * L * kD);
+    ok = ok && win_i && xr_i;
+  }
   float* St_ws = cv.take((size_t)B * kD);
   float* y1 = cv.take((size_t)B * kD);
   NLWs nl; nl.w0 = cv.take((size_t)B * kD); nl.w1 = cv.take((size_t)B * kD); nl.s = cv.take((size_t)B * kD);
   ClsWs cls;
-  ok = ok && bank_r && pb && win_i && lt_i && xr_i && St_ws && y1 && nl.w0 && nl.w1 && nl.s && carve_cls(cv, B, cls);
+  ok = ok && bank_r && pb && lt_i && St_ws && y1 && nl.w0 && nl.w1 && nl.s && carve_cls(cv, B, cls);
   TMR_CHECK_ARG(ok, "head_frames_dedup: workspace too small (%zu < %zu)", workspace_bytes,
-                tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, pb_rows, L, D));
+                tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, n_irregular_rows, pb_rows, L, D));
   float* St = St_out ? St_out : St_ws;
   TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0));
   if (pb_rows > 0) {
@@ -530,7 +544,17 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
     TMR_TRY(umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, pb_row_base,
                           pb_rows, pb, st));
   }
-  if (n_irregular > 0) {      // clips whose window crosses a video start: per-clip gather + TimeConv
+  if (irr_rows) {
+    // clips whose window crosses a video start: tap products once per DISTINCT row their windows touch,
+    // then each (clip, slot) sums the taps of its own neighbours (no per-clip GEMM)
+    const float* tp = (const float*)timeconv_packed;
+    TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, irregular_starts, n_irregular, L,
+                          pad_mode, nullptr, wrows_i, st));
+    TMR_TRY(launch_compact_rows_round(bank, irregular_rows, n_irregular_rows, xc_i, st));
+    TMR_TRY(umma_bankconv_raw(tp, xc_i, n_irregular_rows, q_i, st));
+    TMR_TRY(launch_irr_assemble(q_i, irregular_rows, n_irregular_rows, wrows_i, bank, tp + TimeConvPacked::b3_off,
+                                tp + TimeConvPacked::b5_off, tp + TimeConvPacked::b7_off, n_irregular, L, lt_i, st));
+  } else if (n_irregular > 0) {      // no row list given: per-clip gather + TimeConv
     TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, irregular_starts, n_irregular, L,
                           pad_mode, win_i, nullptr, st));
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, win_i, n_irregular, L, lt_i, xr_i, mode, st));

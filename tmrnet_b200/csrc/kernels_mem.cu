@@ -53,18 +53,20 @@ gather_kernel(const float* __restrict__ bank, int64_t n_rows, const int32_t* __r
     } else {
       row = (key >= 0) ? (int64_t)f2r[key] : 0;
     }
-    float4 v[4];
-    if (row >= 0) {
-      const float4* src = reinterpret_cast<const float4*>(bank + row * kD);
+    if (out) {                                 // out == nullptr: window ROW INDICES only
+      float4 v[4];
+      if (row >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(bank + row * kD);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = ldg_nc(src + i * 32 + lane);
-    } else {
+        for (int i = 0; i < 4; ++i) v[i] = ldg_nc(src + i * 32 + lane);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4* dst = reinterpret_cast<float4*>(out + w * kD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stg_na(dst + i * 32 + lane, v[i]);
     }
-    float4* dst = reinterpret_cast<float4*>(out + w * kD);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) stg_na(dst + i * 32 + lane, v[i]);
     if (rows_out && lane == 0) rows_out[w] = (int32_t)row;
   }
 }
@@ -81,6 +83,103 @@ int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const i
   gather_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, st>>>(bank, n_rows, f2r, f2v, starts, total,
                                                                L, pad_mode, out, rows_out);
   TMR_LAUNCH_CHECK("gather_kernel");
+  return TMR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Irregular clips of the bank-level path (windows that repeat-fill / leak across a video start): their
+// TimeConv is assembled from UNSHIFTED per-row tap products instead of a per-clip implicit GEMM.
+//   compact_rows_round: xc[i] = round_tf32(bank[rows[i]])        (the distinct rows those windows touch)
+//   umma_bankconv_raw : q[i][tap] = W_tap . xc[i]                (15 taps x 512 per row, once per row)
+//   irr_assemble      : Lt[b,k] = max(x[k], k>0 ? x[k-1] : 0, conv3, conv5, conv7),
+//                       conv_K[k] = b_K + sum_{t, 0<=k+t<L} q[row(slot k+t)][tap(K,t)]      (NLB:55-68)
+// A clip's 236 MFLOP become ~34 KB of L2 reads per slot; only fp32 summation order changes.
+// -------------------------------------------------------------------------------------------
+__global__ void compact_rows_round_kernel(const float* __restrict__ bank, const int32_t* __restrict__ rows, int n,
+                                          float* __restrict__ out) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // float4 index
+  if (i4 >= (int64_t)n * (kD / 4)) return;
+  const int i = (int)(i4 / (kD / 4));
+  const int c4 = (int)(i4 - (int64_t)i * (kD / 4));
+  float4 v = __ldg(reinterpret_cast<const float4*>(bank + (int64_t)rows[i] * kD) + c4);
+  v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+  reinterpret_cast<float4*>(out)[i4] = v;
+}
+int launch_compact_rows_round(const float* bank, const int32_t* rows, int n, float* out, cudaStream_t st) {
+  if (n <= 0) return TMR_OK;
+  const int64_t total = (int64_t)n * (kD / 4);
+  compact_rows_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bank, rows, n, out);
+  TMR_LAUNCH_CHECK("compact_rows_round_kernel");
+  return TMR_OK;
+}
+
+constexpr int kAsmWarps = 8;
+__global__ void __launch_bounds__(kAsmWarps * 32)
+irr_assemble_kernel(const float* __restrict__ q, const int32_t* __restrict__ crows, int n_c,
+                    const int32_t* __restrict__ wrows, const float* __restrict__ bank,
+                    const float* __restrict__ b3, const float* __restrict__ b5, const float* __restrict__ b7,
+                    int64_t total, int L, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * kAsmWarps + (threadIdx.x >> 5);    // (clip, slot)
+  if (w >= total) return;
+  const int64_t b = w / L;
+  const int k = (int)(w - b * L);
+  // lanes 0..6 resolve the window rows of slots k-3 .. k+3 to positions in the compact row list
+  int row_t = -1, ci = -1;
+  if (lane < 7) {
+    const int kk = k + lane - 3;
+    if (kk >= 0 && kk < L) {
+      row_t = wrows[b * L + kk];
+      if (row_t >= 0) {
+        int lo = 0, hi = n_c - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (crows[mid] < row_t) lo = mid + 1; else hi = mid; }
+        ci = (crows[lo] == row_t) ? lo : -1;
+      }
+    }
+  }
+  float4 a7[4], a5[4], a3[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a7[i] = __ldg(reinterpret_cast<const float4*>(b7) + i * 32 + lane);
+    a5[i] = __ldg(reinterpret_cast<const float4*>(b5) + i * 32 + lane);
+    a3[i] = __ldg(reinterpret_cast<const float4*>(b3) + i * 32 + lane);
+  }
+  auto add4 = [](float4& a, const float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
+#pragma unroll
+  for (int t = -3; t <= 3; ++t) {
+    const int c = __shfl_sync(0xffffffffu, ci, t + 3);
+    if (c < 0) continue;                                  // slot outside the window, or a zero-padded slot
+    const float4* base = reinterpret_cast<const float4*>(q + (int64_t)c * (15 * kD));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      add4(a7[i], __ldg(base + (t + 3) * (kD / 4) + i * 32 + lane));
+      if (t >= -2 && t <= 2) add4(a5[i], __ldg(base + (7 + t + 2) * (kD / 4) + i * 32 + lane));
+      if (t >= -1 && t <= 1) add4(a3[i], __ldg(base + (12 + t + 1) * (kD / 4) + i * 32 + lane));
+    }
+  }
+  const int row_k = __shfl_sync(0xffffffffu, row_t, 3);
+  const int row_p = __shfl_sync(0xffffffffu, row_t, 2);   // slot k-1 (-1 when k == 0: the pool sees the zero pad)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 x0 = row_k >= 0 ? __ldg(reinterpret_cast<const float4*>(bank + (int64_t)row_k * kD) + i * 32 + lane) : z;
+    const float4 x1 = row_p >= 0 ? __ldg(reinterpret_cast<const float4*>(bank + (int64_t)row_p * kD) + i * 32 + lane) : z;
+    float4 o;
+    o.x = fmaxf(fmaxf(fmaxf(a7[i].x, a5[i].x), a3[i].x), fmaxf(x0.x, x1.x));
+    o.y = fmaxf(fmaxf(fmaxf(a7[i].y, a5[i].y), a3[i].y), fmaxf(x0.y, x1.y));
+    o.z = fmaxf(fmaxf(fmaxf(a7[i].z, a5[i].z), a3[i].z), fmaxf(x0.z, x1.z));
+    o.w = fmaxf(fmaxf(fmaxf(a7[i].w, a5[i].w), a3[i].w), fmaxf(x0.w, x1.w));
+    reinterpret_cast<float4*>(out + w * kD)[i * 32 + lane] = o;
+  }
+}
+int launch_irr_assemble(const float* q, const int32_t* crows, int n_c, const int32_t* wrows, const float* bank,
+                        const float* b3, const float* b5, const float* b7, int n_clips, int L, float* out,
+                        cudaStream_t st) {
+  const int64_t total = (int64_t)n_clips * L;
+  if (total == 0) return TMR_OK;
+  irr_assemble_kernel<<<(unsigned)((total + kAsmWarps - 1) / kAsmWarps), kAsmWarps * 32, 0, st>>>(
+      q, crows, n_c, wrows, bank, b3, b5, b7, total, L, out);
+  TMR_LAUNCH_CHECK("irr_assemble_kernel");
   return TMR_OK;
 }
 

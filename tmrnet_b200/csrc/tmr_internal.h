@@ -45,6 +45,13 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
 int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
                   int64_t n_frames, const int64_t* starts, int B, int L, int pad_mode, float* out,
                   int32_t* rows_out, cudaStream_t st);
+// irregular clips of the bank-level path: compact + round the rows their windows touch, assemble their
+// TimeConv from unshifted per-row tap products (umma_bankconv_raw)
+int launch_compact_rows_round(const float* bank, const int32_t* rows, int n, float* out, cudaStream_t st);
+int launch_irr_assemble(const float* q, const int32_t* crows, int n_c, const int32_t* wrows, const float* bank,
+                        const float* b3, const float* b5, const float* b7, int n_clips, int L, float* out,
+                        cudaStream_t st);
+int umma_bankconv_raw(const float* packed, const float* rows_r, int64_t n, float* q, cudaStream_t st);
 // step 0 of the LSTM from zero state: c = sig(i)*tanh(g), h = sig(o)*tanh(c) from xp rows.
 int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
                       int round_h, cudaStream_t st);

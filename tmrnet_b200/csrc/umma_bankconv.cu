@@ -65,6 +65,7 @@ struct BankConvParams {
   const float* bank; float* pb; const float* bias3; const float* bias5; const float* bias7;
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
   int64_t num_tiles;
+  float* q_out; int raw;   // raw: emit the UNSHIFTED tap products Q[row][15][512] instead of the 7 variants
   int ablate;      // timing experiments (WRONG results), env TMR_BC_ABL: 1 = epilogue only hands the accumulator back, 2 = no global stores
 };
 
@@ -186,8 +187,8 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
           const float* src = p.bank + rho * kD + n0 + 8 * c8 + 4 * half;
-          x0v[ps][c8] = valid[ps] ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x1v[ps][c8] = has_next ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x0v[ps][c8] = (valid[ps] && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x1v[ps][c8] = (has_next && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
@@ -246,6 +247,18 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
         epi_barrier();
+        if (p.raw) {            // Q_{K,t}[rho] = W_K[:,:,t+h] . x[rho] as computed: any window can be assembled from these
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            if (!valid[ps]) continue;
+            const int r2 = q * 32 + (lane >> 1) + 16 * ps;
+            float* dst = p.q_out + prow[ps] * (15 * kD) + n0 + cc + 4 * half;
+#pragma unroll
+            for (int tap = 0; tap < 15; ++tap) *reinterpret_cast<float4*>(dst + tap * kD) = *exh(tap, r2, half);
+          }
+          epi_barrier();
+          continue;
+        }
         const float4 bb3 = __ldg(reinterpret_cast<const float4*>(p.bias3 + n0 + cc + 4 * half));
         const float4 bb5 = __ldg(reinterpret_cast<const float4*>(p.bias5 + n0 + cc + 4 * half));
         const float4 bb7 = __ldg(reinterpret_cast<const float4*>(p.bias7 + n0 + cc + 4 * half));
@@ -310,6 +323,21 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
 }  // namespace umma
 
+static int launch_bankconv(const float* packed, const float* bank_r, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st);
+
+// Unshifted tap products of `n` (TF32-rounded) rows: q[(row*15 + tap)][512], taps 0..6 = conv7 t=-3..3,
+// 7..11 = conv5 t=-2..2, 12..14 = conv3 t=-1..1.  The TimeConv of ANY window over these rows is
+// conv_K[k] = b_K + sum_t q[row(slot k+t)][tap(K,t)] (irr_assemble_kernel).
+int umma_bankconv_raw(const float* packed, const float* rows_r, int64_t n, float* q, cudaStream_t st) {
+  using namespace umma;
+  if (n <= 0) return TMR_OK;
+  BankConvParams p{};
+  p.bank = nullptr; p.pb = nullptr; p.q_out = q; p.raw = 1;
+  p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
+  p.n_rows = n; p.row_base = 0; p.pb_rows = n; p.r_lo = 0;
+  return launch_bankconv(packed, rows_r, n, p, st);
+}
+
 // pb[(row - row_base)*7 + v][512] for bank rows row_base .. row_base + pb_rows - 1.
 // bank = exact values (identity / pool branches); bank_r = rows r_lo .. r_lo + r_cnt - 1 of the bank
 // rounded to TF32 (MMA operand) — must cover row_base - 3 .. row_base + pb_rows + 2 where they exist.
@@ -322,7 +350,12 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
   p.bank = bank; p.pb = pb;
   p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
   p.n_rows = n_rows; p.row_base = row_base; p.pb_rows = pb_rows; p.r_lo = r_lo;
-  p.num_tiles = ((pb_rows + BC_OUT - 1) / BC_OUT) * (kD / BC_NCH);
+  return launch_bankconv(packed, bank_r, r_cnt, p, st);
+}
+
+static int launch_bankconv(const float* packed, const float* bank_r, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
+  using namespace umma;
+  p.num_tiles = ((p.pb_rows + BC_OUT - 1) / BC_OUT) * (kD / BC_NCH);
   static const int abl = [] { const char* e = getenv("TMR_BC_ABL"); return e ? atoi(e) : 0; }();
   p.ablate = abl;
   CUtensorMap tx, tw3, tw5, tw7;

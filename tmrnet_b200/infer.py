@@ -42,7 +42,7 @@ class BankInference:
 
     def __init__(self, model, index: LFBIndex, seq: int = 10, L: int = 30, batch_clips: int = None,
                  pad_mode: str = "repeat", math_mode=None, starts=None, dedup: bool = True, tail_clips: int = 0,
-                 host_batch_clips: int = None):
+                 host_batch_clips: int = None, irr_from_rows: bool = True):
         self.model = model
         self.index = index
         self.seq, self.L = int(seq), int(L)
@@ -59,7 +59,11 @@ class BankInference:
             max(128, self.batch_clips // 2) if self.batch_clips else default_host_batch_clips())
         self.tail_clips = int(tail_clips)
         self._host_eng = None
-        self._ctor = dict(pad_mode=pad_mode, math_mode=math_mode, starts=starts, dedup=dedup, tail_clips=tail_clips)
+        # irregular clips (first L of every video): TimeConv assembled from per-row tap products of the rows
+        # their windows touch (True) or per-clip gather + TimeConv (False)
+        self.irr_from_rows = bool(irr_from_rows)
+        self._ctor = dict(pad_mode=pad_mode, math_mode=math_mode, starts=starts, dedup=dedup, tail_clips=tail_clips,
+                          irr_from_rows=irr_from_rows)
         self.pad_mode = {"repeat": ops.TMR_PAD_REPEAT, "zero": ops.TMR_PAD_ZERO}[pad_mode]
         self.math_mode = math_mode
         if starts is None:       # every clip of the index; a VideoShard passes its owned clips only
@@ -99,14 +103,27 @@ class BankInference:
                     src[regular] = (r0[regular] - row_base).astype(np.int32)
                 else:
                     row_base, pb_rows = 0, 0
-                out.append(dict(src=src, irr=irr.astype(np.int64), row_base=row_base, pb_rows=pb_rows))
+                # distinct bank rows the irregular windows touch (same rule as gather_kernel): their TimeConv
+                # is assembled from per-row tap products of exactly these rows
+                if len(irr) and self.irr_from_rows:
+                    key = irr[:, None] - np.arange(1, self.L + 1, dtype=np.int64)[None, :]
+                    rows = f2r[np.maximum(key, 0)]
+                    if self.pad_mode == ops.TMR_PAD_ZERO:
+                        rows = rows[key >= f2v[irr][:, None]]
+                    else:
+                        rows = np.where(key >= 0, rows, 0)
+                    irr_rows = np.unique(rows).astype(np.int32)
+                else:
+                    irr_rows = np.zeros(0, dtype=np.int32)
+                out.append(dict(src=src, irr=irr.astype(np.int64), irr_rows=irr_rows, row_base=row_base, pb_rows=pb_rows))
             self._dedup_plan = out
         return self._dedup_plan
 
     def _dedup_tensors(self, dev):
         if dev not in self._dedup_dev:
             self._dedup_dev[dev] = [(torch.from_numpy(d["src"]).to(dev),
-                                     torch.from_numpy(d["irr"]).to(dev) if len(d["irr"]) else None)
+                                     torch.from_numpy(d["irr"]).to(dev) if len(d["irr"]) else None,
+                                     torch.from_numpy(d["irr_rows"]).to(dev) if len(d["irr_rows"]) else None)
                                     for d in self.dedup_plan()]
         return self._dedup_dev[dev]
 
@@ -144,7 +161,7 @@ class BankInference:
         dplan = dten = None
         if dedup:
             dplan, dten = self.dedup_plan(), self._dedup_tensors(dev)
-            need = max((lib.tmr_head_frames_dedup_workspace_bytes(fh - fl, hi - lo, len(d["irr"]), d["pb_rows"], self.L, D)
+            need = max((lib.tmr_head_frames_dedup_workspace_bytes(fh - fl, hi - lo, len(d["irr"]), len(d["irr_rows"]), d["pb_rows"], self.L, D)
                         for (lo, hi, fl, fh), d in zip(plan, dplan)), default=256)
         else:
             need = max((lib.tmr_head_frames_workspace_bytes(fh - fl, hi - lo, self.L, D) for lo, hi, fl, fh in plan),
@@ -172,8 +189,9 @@ class BankInference:
                       C.c_void_p(st.data_ptr() + lo * D * 4) if st is not None else C.c_void_p(0),
                       _ptr(ws), ws.numel())
         if ctx["dedup"]:
-            d, (src_dev, irr_dev) = ctx["dplan"][i], ctx["dten"][i]
+            d, (src_dev, irr_dev, irr_rows_dev) = ctx["dplan"][i], ctx["dten"][i]
             check(lib.tmr_head_frames_dedup_fwd(*common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
+                                                _ptr(irr_rows_dev), len(d["irr_rows"]),
                                                 d["row_base"], d["pb_rows"], self.seq, self.L, F, D, Cn,
                                                 self.pad_mode, *common_out, stream))
         else:
@@ -266,7 +284,8 @@ class BankInference:
             return (lstm + 1 + 1 + 2 * tc + tail + 2) * len(self.plan())
         n = 0
         for d in self.dedup_plan():
-            n += (lstm + 1) + (2 if d["pb_rows"] > 0 else 0) + (3 if len(d["irr"]) else 0) + tail + 2
+            n += ((lstm + 1) + (2 if d["pb_rows"] > 0 else 0) + (0 if not len(d["irr"]) else 4 if len(d["irr_rows"]) else 3)
+                  + tail + 2)
         return n
 
 
