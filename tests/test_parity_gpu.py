@@ -614,3 +614,40 @@ def test_graphed_head_is_bit_identical_to_direct_calls(mode, B):
         m.fc_c.bias.sub_(0.25)
     assert torch.equal(logits, l2)
     m.math_mode = None
+
+
+@pytest.mark.gpu
+def test_bank_inference_graph_replay_equals_eager_passes():
+    """BankInference.run captures its launch sequence into a CUDA graph on the second pass over the same
+    buffers and replays it afterwards: every pass must give exactly the eager results, also after the
+    features change in place and after a weight update (new packs -> eager again, then a new graph)."""
+    from tmrnet_b200.infer import BankInference
+    dev = _dev()
+    lengths = [57, 12, 140, 33, 210]
+    seq, L = 10, 30
+    feats = torch.from_numpy(synth.features(sum(lengths), seed=21)).to(dev)
+    bank = torch.from_numpy(synth.bank(len(synth.clip_starts(lengths, seq)), seed=21)).to(dev)
+    m = _model(7)
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    eng = BankInference(m, idx, seq, L, batch_clips=200)
+    ref = {k: v.clone() for k, v in BankInference(m, idx, seq, L, batch_clips=200).run(feats, bank, graph=False).items()}
+    out = eng.run(feats, bank)
+    for rep in range(4):                                   # pass 1 eager, pass 2 eager + capture, then replays
+        out = eng.run(feats, bank, out=out)
+        assert all(torch.equal(out[k], ref[k]) for k in ref), rep
+    assert eng._graph is not None
+    feats.mul_(0.5)                                        # same buffers, new contents: the replay must see them
+    ref2 = {k: v.clone() for k, v in BankInference(m, idx, seq, L, batch_clips=200).run(feats, bank, graph=False).items()}
+    out = eng.run(feats, bank, out=out)
+    assert all(torch.equal(out[k], ref2[k]) for k in ref2)
+    assert not torch.equal(ref2["logits"], ref["logits"])
+    with torch.no_grad():
+        m.fc_c.bias.add_(0.5)
+    try:
+        ref3 = {k: v.clone() for k, v in BankInference(m, idx, seq, L, batch_clips=200).run(feats, bank, graph=False).items()}
+        for rep in range(3):
+            out = eng.run(feats, bank, out=out)
+            assert all(torch.equal(out[k], ref3[k]) for k in ref3), rep
+    finally:
+        with torch.no_grad():
+            m.fc_c.bias.sub_(0.5)

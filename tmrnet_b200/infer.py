@@ -59,6 +59,8 @@ class BankInference:
             max(128, self.batch_clips // 2) if self.batch_clips else default_host_batch_clips())
         self.tail_clips = int(tail_clips)
         self._host_eng = None
+        self._graph = None          # (key, CUDAGraph, ...) of the resident pass, see run()
+        self._last_key = None
         # irregular clips (first L of every video): TimeConv assembled from per-row tap products of the rows
         # their windows touch (True) or per-clip gather + TimeConv (False)
         self.irr_from_rows = bool(irr_from_rows)
@@ -198,19 +200,43 @@ class BankInference:
             check(lib.tmr_head_frames_fwd(*common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
                                           *common_out, ctx["mode"], stream))
 
-    def run(self, feats, bank, out=None, want_st=False):
+    def run(self, feats, bank, out=None, want_st=False, graph=None):
         """All clips of the index in global clip order, features resident on the device.
-        Returns dict(logits, pred, score[, St]) of device tensors."""
+        Returns dict(logits, pred, score[, St]) of device tensors.
+
+        graph: None (default) - the second pass over the SAME buffers (features, bank, outputs, packed
+        weights) is captured into a CUDA graph and later passes replay it (one launch instead of ~55, no
+        per-launch tensor-map encoding on the host); True / False force or forbid that."""
         feats = _dev(feats, "feats")
         bank = _dev(bank, "bank")
         dev = feats.device
         if out is None:
             out = self._alloc_out(dev, want_st)
         ctx = self._prepare(dev, bank)
-        with torch.cuda.device(dev):
+
+        def enqueue():
             stream = _stream()
             for i, (lo, hi, fl, fh) in enumerate(ctx["plan"]):
                 self._launch_batch(ctx, i, feats.data_ptr() + fl * F * 4, out, stream)
+
+        key = (feats.data_ptr(), bank.data_ptr(), tuple(sorted((k, v.data_ptr()) for k, v in out.items())),
+               tuple(p.data_ptr() for p in ctx["packs"] if p is not None), ctx["ws"].data_ptr(), ctx["mode"],
+               ctx["dedup"], str(dev))
+        with torch.cuda.device(dev):
+            if graph is False:
+                enqueue()
+            elif self._graph is not None and self._graph[0] == key:
+                self._graph[1].replay()
+            elif graph is True or self._last_key == key:
+                enqueue()                                   # this pass, eagerly (also warms lazy attribute setup) ...
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.current_stream(dev).synchronize()
+                with torch.cuda.graph(g):                   # ... and its launch sequence for the following ones
+                    enqueue()
+                self._graph = (key, g, ctx, out, feats, bank)        # keeps every captured buffer alive
+            else:
+                enqueue()
+        self._last_key = key
         return out
 
     def run_host(self, feats_host, bank, out=None, host_out=None, timeline=None):
