@@ -69,15 +69,22 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
   const bool tc = mode == TMR_MATH_TF32;
   const float* w = pk + (tc ? NLBlockPacked::fp32_total : 0);
   LinearArgs g;
-  // q = St W1^T + b1                                   (NLB:26-27)
-  g = LinearArgs(); g.a = St; g.lda = kD; g.w = w + NLBlockPacked::w1_off; g.ldw = kD;
-  g.bias = pk + NLBlockPacked::b1_off; g.out = ws.w0; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
-  g.a_scratch = tc ? ws.s : nullptr; g.round_out = tc;
-  TMR_TRY(do_linear(g, mode, st));
-  // u = W2^T q  (phi folded onto the query; b2 cancels in the softmax)     (NLB:28-30)
-  g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w2t_off; g.ldw = kD;
-  g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
-  TMR_TRY(do_linear(g, mode, st));
+  if (tc) {
+    // u = W2^T (W1 St + b1) = W21 St + bu: the query linear and the phi fold in ONE GEMM (W21, bu built at pack time)
+    g = LinearArgs(); g.a = St; g.lda = kD; g.w = w + NLBlockPacked::w21_off; g.ldw = kD;
+    g.bias = pk + NLBlockPacked::bu_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+    g.a_scratch = ws.s;
+    TMR_TRY(do_linear(g, mode, st));
+  } else {
+    // q = St W1^T + b1                                   (NLB:26-27)
+    g = LinearArgs(); g.a = St; g.lda = kD; g.w = w + NLBlockPacked::w1_off; g.ldw = kD;
+    g.bias = pk + NLBlockPacked::b1_off; g.out = ws.w0; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+    TMR_TRY(do_linear(g, mode, st));
+    // u = W2^T q  (phi folded onto the query; b2 cancels in the softmax)     (NLB:28-30)
+    g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w2t_off; g.ldw = kD;
+    g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
+    TMR_TRY(do_linear(g, mode, st));
+  }
   // a = sum_k softmax(scale u.Lt_k) Lt_k                                   (NLB:30-34)
   if (pbs) TMR_TRY(launch_attention_pb(ws.w1, pbs->pb, pbs->lt_irr, pbs->src, B, L, ws.w0, tc, st));
   else TMR_TRY(launch_attention(ws.w1, Lt, B, L, ws.w0, tc, st));
@@ -121,7 +128,7 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
     float* h0 = ws.h0 + (int64_t)lo * kD; float* h1 = ws.h1 + (int64_t)lo * kD; float* c = ws.c + (int64_t)lo * kD;
     // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
     float* hcur = (seq == 1) ? out_lo : h0;
-    TMR_TRY(launch_lstm_cell0(xp_lo, st_lo, seq, hcur, c, nb, tc && seq > 1, st));
+    TMR_TRY(launch_lstm_cell0(xp_lo, st_lo, seq, hcur, c, nb, tc && seq > 1, st, tc));
     for (int t = 1; t < seq; ++t) {
       const bool last = (t == seq - 1);
       float* hnext = last ? out_lo : (hcur == h0 ? h1 : h0);

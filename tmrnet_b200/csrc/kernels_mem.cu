@@ -187,26 +187,48 @@ int launch_irr_assemble(const float* q, const int32_t* crows, int n_c, const int
 // LSTM step 0 from zero state: gates = xp row (bias already folded), c = sig(i) tanh(g).
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ float ex2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// One thread per (clip, 4 units): 64 contiguous bytes of the projected row in, 128-bit c / h out.
+// FAST (tensor-core mode): MUFU ex2/rcp gates like the recurrent-step epilogue; fp32 mode keeps expf/tanhf.
+template <bool FAST>
 __global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* __restrict__ starts,
-                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total, int round_h) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (clip, unit)
-  if (idx >= total) return;
-  const int64_t m = idx / kD;
-  const int unit = (int)(idx - m * kD);
+                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total4, int round_h) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (clip, unit quad)
+  if (idx >= total4) return;
+  const int64_t m = idx / (kD / 4);
+  const int u4 = (int)(idx - m * (kD / 4)) * 4;
   const int64_t xr = starts ? starts[m] : m * seq;
-  const float4 p = __ldg(reinterpret_cast<const float4*>(xp + xr * (4 * kD) + unit * 4));
-  const float cn = sigmoidf_(p.x) * tanhf(p.z);     // f * 0 drops out
-  c[idx] = cn;
-  const float hn = sigmoidf_(p.w) * tanhf(cn);
-  h[idx] = round_h ? round_tf32(hn) : hn;
+  const float4* src = reinterpret_cast<const float4*>(xp + xr * (4 * kD) + u4 * 4);
+  float cn[4], hn[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 p = __ldg(src + k);                   // (i, f, g, o) of unit u4 + k; f * 0 drops out
+    if (FAST) {
+      const float a = ex2f_approx(fminf(-1.4426950408889634f * p.x, 40.f));
+      const float d = ex2f_approx(fminf(-2.8853900817779268f * p.z, 40.f));
+      const float e = ex2f_approx(fminf(-1.4426950408889634f * p.w, 40.f));
+      cn[k] = (1.f - d) * rcpf_approx((1.f + a) * (1.f + d));          // sigmoid(i) tanh(g)
+      const float f2 = ex2f_approx(fminf(-2.8853900817779268f * cn[k], 40.f));
+      hn[k] = (1.f - f2) * rcpf_approx((1.f + e) * (1.f + f2));        // sigmoid(o) tanh(c)
+    } else {
+      cn[k] = sigmoidf_(p.x) * tanhf(p.z);
+      hn[k] = sigmoidf_(p.w) * tanhf(cn[k]);
+    }
+    if (round_h) hn[k] = round_tf32(hn[k]);
+  }
+  *reinterpret_cast<float4*>(c + m * kD + u4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  *reinterpret_cast<float4*>(h + m * kD + u4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
 }
 
 int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      int round_h, cudaStream_t st) {
-  const int64_t total = (int64_t)B * kD;
-  if (total == 0) return TMR_OK;
-  lstm_cell0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xp, starts, seq, h, c, total, round_h);
+                      int round_h, cudaStream_t st, bool fast_math) {
+  const int64_t total4 = (int64_t)B * (kD / 4);
+  if (total4 == 0) return TMR_OK;
+  const unsigned blocks = (unsigned)((total4 + 255) / 256);
+  if (fast_math) lstm_cell0_kernel<true><<<blocks, 256, 0, st>>>(xp, starts, seq, h, c, total4, round_h);
+  else lstm_cell0_kernel<false><<<blocks, 256, 0, st>>>(xp, starts, seq, h, c, total4, round_h);
   TMR_LAUNCH_CHECK("lstm_cell0_kernel");
   return TMR_OK;
 }
@@ -545,6 +567,20 @@ int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const
   copy_kernel<<<2, 256, 0, st>>>(lnw, packed + NLBlockPacked::lnw_off, kD);
   copy_kernel<<<2, 256, 0, st>>>(lnb, packed + NLBlockPacked::lnb_off, kD);
   TMR_LAUNCH_CHECK("pack_nlblock");
+  {
+    // W21[j][i] = sum_k W2T[j][k] W1[k][i] and bu[j] = sum_k W2T[j][k] b1[k], fp32; W1^T is staged in the
+    // mirror half, which the rounding pass below overwrites
+    float* w1t = packed + NLBlockPacked::fp32_total;
+    transpose_kernel<<<dim3(kD / 32, kD / 32), dim3(32, 8), 0, st>>>(w1, w1t, kD);
+    LinearArgs g;
+    g.a = packed + NLBlockPacked::w2t_off; g.lda = kD; g.w = w1t; g.ldw = kD;
+    g.out = packed + NLBlockPacked::w21_off; g.ldo = kD; g.M = kD; g.N = kD; g.K = kD;
+    TMR_TRY(simt_linear(g, st));
+    LinearArgs b;
+    b.a = packed + NLBlockPacked::b1_off; b.lda = kD; b.w = packed + NLBlockPacked::w2t_off; b.ldw = kD;
+    b.out = packed + NLBlockPacked::bu_off; b.ldo = kD; b.M = 1; b.N = kD; b.K = kD;
+    TMR_TRY(simt_linear(b, st));
+  }
   return launch_round_tf32(packed, packed + NLBlockPacked::fp32_total, NLBlockPacked::fp32_total, st);
 }
 

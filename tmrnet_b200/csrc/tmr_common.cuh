@@ -68,7 +68,8 @@ struct TimeConvPacked {
   static constexpr size_t fp32_total = b7_off + kD;
   static constexpr size_t total = 2 * fp32_total;   // + TF32-rounded (RN) mirror for the tensor-core path
 };
-// NLBlock: W1[n][k], W2T[n][k] = W2[k][n], W3[n][k], W4[n][k], b1, b3, b4, ln_w, ln_b.
+// NLBlock: W1[n][k], W2T[n][k] = W2[k][n], W3[n][k], W4[n][k], b1, b3, b4, ln_w, ln_b, then the query fold
+// W21 = W2^T W1 ([n][k]) and bu = W2^T b1, so the tensor-core path gets u = W2^T (W1 St + b1) from ONE GEMM.
 // (b2 cancels inside the softmax over L: q.(W2 l_k + b2) = (W2^T q).l_k + const.)
 struct NLBlockPacked {
   static constexpr size_t w1_off = 0;
@@ -80,7 +81,9 @@ struct NLBlockPacked {
   static constexpr size_t b4_off = b3_off + kD;
   static constexpr size_t lnw_off = b4_off + kD;
   static constexpr size_t lnb_off = lnw_off + kD;
-  static constexpr size_t fp32_total = lnb_off + kD;
+  static constexpr size_t w21_off = lnb_off + kD;
+  static constexpr size_t bu_off = w21_off + (size_t)kD * kD;
+  static constexpr size_t fp32_total = bu_off + kD;
   static constexpr size_t total = 2 * fp32_total;
 };
 // LSTM: gate-interleaved rows r' = unit*4 + gate (gate order i,f,g,o) so one float4 of the

@@ -54,7 +54,7 @@ int launch_irr_assemble(const float* q, const int32_t* crows, int n_c, const int
 int umma_bankconv_raw(const float* packed, const float* rows_r, int64_t n, float* q, cudaStream_t st);
 // step 0 of the LSTM from zero state: c = sig(i)*tanh(g), h = sig(o)*tanh(c) from xp rows.
 int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      int round_h, cudaStream_t st);
+                      int round_h, cudaStream_t st, bool fast_math = false);
 // a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]
 int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st);
 // same attention over the bank-level TimeConv output (see umma_bankconv.cu)

@@ -297,15 +297,17 @@ class BankInference:
     def launches_per_run(self) -> int:
         """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
         projection + cell0 + (seq-1) steps | gather | timeconv | q, u, attention, v, layernorm, out |
-        fc_h_c, fc_c; TF32 mode adds the TF32 rounding passes (features, window, St, [St|y1]); the
-        dedup path replaces gather+round+timeconv over all clips by round(bank rows) + bankconv and
-        runs gather+round+timeconv only when the batch has irregular clips."""
+        fc_h_c, fc_c; TF32 mode adds the TF32 rounding passes (features, window, St, [St|y1]) and folds
+        q, u into one GEMM; the dedup path replaces gather+round+timeconv over all clips by round(bank rows)
+        + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw bankconv +
+        assemble (or gather+round+timeconv without the row list)."""
         mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
         tc = 1 if self.model.time_conv is not None else 0
         lstm = 1 + 1 + (self.seq - 1)
         tail = 6 + 2
         if mode != ops.TMR_MATH_TF32:
             return (lstm + 1 + tc + tail) * len(self.plan())
+        tail -= 1                                      # u = W21 St + bu: one GEMM for q and u
         if not self._use_dedup():
             return (lstm + 1 + 1 + 2 * tc + tail + 2) * len(self.plan())
         n = 0
