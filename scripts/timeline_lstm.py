@@ -43,23 +43,6 @@ for it in range(8):
         r = w[it, wi]
         print(f"   warp {wi + 2:2d} (q{(wi + 2) & 3}, cols {((wi) >> 2) * 64:3d}): wait_start {r[0]:7d} ready {r[1]:7d} chunk0 {r[2] - r[1]:6d} chunk1 {r[3] - r[2]:6d} done {r[3]:7d}")
 
-# -DTMR_EPI_PROFILE builds only: phases of chunk 0 per warp of CTA 0
-try:
-    fp = ctypes.CDLL(_lib.LIB_PATH).tmr_debug_timeline_phases
-except AttributeError:
-    fp = None
-if fp is not None:
-    fp.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    bp = (ctypes.c_longlong * (16 * 16 * 8))()
-    assert fp(bp, 16 * 16 * 8) == 0
-    ph = np.array(bp, dtype=np.int64).reshape(16, 16, 8)
-    d = np.diff(ph[1:8, :, :7], axis=2).astype(np.float64)      # tiles 1..7
-    names = ["issue loads", "tmem ld", "stage+sync", "wait global", "math", "stores"]
-    print("chunk-0 phases, mean cycles over tiles 1..7 and the 16 warps of CTA 0:")
-    for k, nm in enumerate(names):
-        print(f"   {nm:12s} {d[:, :, k].mean():8.0f}  (min {d[:, :, k].min():6.0f}, max {d[:, :, k].max():6.0f})")
-    print("   total       ", (ph[1:8, :, 6] - ph[1:8, :, 0]).mean())
-
 # kernel span seen by the device clock of each CTA (first MMA-thread stamp -> last epilogue stamp of warp 2)
 n_t = int((a[0, :, 5] > 0).sum())
 span = a[::2, n_t - 1, 5] - a[::2, 0, 0]

@@ -114,31 +114,21 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   g.a_scratch = tc ? ws.xr : nullptr;
   TMR_TRY(do_linear(g, mode, st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
-  // The recurrence runs sub-batch by sub-batch (all seq steps of one before the next): a step reads per clip
-  // 8 KB of projected row + 2 KB c + 2 KB h and writes 2 + 2 KB, i.e. it is HBM-bound (16 KB/clip against
-  // 2.1 MFLOP) unless the sub-batch's rows stay in L2 from one step to the next - consecutive clips share
-  // their projected rows across steps (clip b at step t reads frame b + t).
-  static const int sub_env = [] { const char* e = getenv("TMR_LSTM_SUB"); return e ? atoi(e) : 0; }();
-  const int SUB = (tc && sub_env > 0) ? sub_env : B;
-  for (int lo = 0; lo < B; lo += SUB) {
-    const int nb = (B - lo < SUB) ? B - lo : SUB;
-    const int64_t* st_lo = starts ? starts + lo : nullptr;
-    const float* xp_lo = starts ? xp : xp + (int64_t)lo * seq * 4 * kD;      // no starts: row = m*seq + t
-    float* out_lo = out + (int64_t)lo * kD;
-    float* h0 = ws.h0 + (int64_t)lo * kD; float* h1 = ws.h1 + (int64_t)lo * kD; float* c = ws.c + (int64_t)lo * kD;
-    // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
-    float* hcur = (seq == 1) ? out_lo : h0;
-    TMR_TRY(launch_lstm_cell0(xp_lo, st_lo, seq, hcur, c, nb, tc && seq > 1, st, tc));
-    for (int t = 1; t < seq; ++t) {
-      const bool last = (t == seq - 1);
-      float* hnext = last ? out_lo : (hcur == h0 ? h1 : h0);
-      if (tc)
-        TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, !last, st,
-                               ws.xp, n_rows_x, frame0));
-      else
-        TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp_lo, st_lo, seq, t, hcur, hnext, c, nb, st));
-      hcur = hnext;
-    }
+  // (Running the recurrence in L2-sized sub-batches - all steps of one before the next, so that the projected
+  // rows consecutive clips share stay in L2 - was measured slower at every size: the extra pipeline ramps
+  // cost more than the HBM re-reads; profiles/r1_final_ncu.md.)
+  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
+  float* hcur = (seq == 1) ? out : ws.h0;
+  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, ws.c, B, tc && seq > 1, st, tc));
+  for (int t = 1; t < seq; ++t) {
+    const bool last = (t == seq - 1);
+    float* hnext = last ? out : (hcur == ws.h0 ? ws.h1 : ws.h0);
+    if (tc)
+      TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, !last, st,
+                             ws.xp, n_rows_x, frame0));
+    else
+      TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, st));
+    hcur = hnext;
   }
   return TMR_OK;
 }

@@ -76,15 +76,6 @@ constexpr int TMEM_COLS = 512;
 __device__ long long g_timeline[148 * 16 * 6];
 __device__ long long g_timeline_cta[148 * 4];          // per CTA: kernel entry, setup done, roles done, exit (clock64) 
 __device__ long long g_timeline_warps[16 * 16 * 4];   // CTA 0: [tile][epilogue warp][wait start, acc ready, chunk 0 done, done]
-#ifdef TMR_EPI_PROFILE
-// -DTMR_EPI_PROFILE: phase stamps inside chunk 0 of every tile of CTA 0 (scripts/timeline_lstm.py)
-__device__ long long g_timeline_phases[16 * 16 * 8];
-__device__ __forceinline__ long long stamp_dep(float v) {
-  long long t;
-  asm volatile("{ .reg .f32 tmp; mov.f32 tmp, %1; mov.u64 %0, %%clock64; }" : "=l"(t) : "f"(v) : "memory");
-  return t;
-}
-#endif
 
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
@@ -569,11 +560,6 @@ static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda
 }  // namespace umma
 
 }  // namespace tmr
-#ifdef TMR_EPI_PROFILE
-extern "C" int tmr_debug_timeline_phases(long long* out_host, int n) {
-  return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_phases, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
-}
-#endif
 extern "C" int tmr_debug_timeline_cta(long long* out_host, int n) {
   return cudaMemcpyFromSymbol(out_host, tmr::umma::g_timeline_cta, sizeof(long long) * n) == cudaSuccess ? 0 : 2;
 }
