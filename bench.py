@@ -336,7 +336,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "dtype": "f16" if args.math == "f16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "L": L, "seq": SEQ, "videos_per_gpu": NUM_VIDEOS,
                        "clips_per_gpu": n_clips, "frames_per_gpu": n_frames, "batch_clips": batch_clips, "host_batch_clips": eng.host_batch_clips,
                        "math": args.math, "l2": "inputs (818 MB/GPU) exceed the 126 MB L2; no flush",
@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default=os.environ.get("TMR_MATH", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("TMR_MATH", "f16"), choices=["fp32", "f16"])
     ap.add_argument("--batch", type=int, default=0,
                     help="clips per head launch sequence (0: the engine's default, an even split into batches of <= 65536)")
     ap.add_argument("--cpu-iters", type=int, default=40)

@@ -38,9 +38,10 @@ extern "C" {
 
 /* math mode of the GEMM-shaped stages */
 #define TMR_MATH_FP32 0  /* fp32 FFMA on CUDA cores (exact-order reference path)          */
-#define TMR_MATH_TF32 1  /* tcgen05.mma kind::tf32 on operands rounded to TF32 (round-to-nearest) by
-                            their producers, fp32 accumulate in TMEM; softmax / LayerNorm / gates /
-                            max / final 512->C FC stay fp32                                     */
+#define TMR_MATH_F16 1   /* tcgen05.mma kind::f16: operands converted to fp16 (round-to-nearest, saturating
+                            at +-65504; the same 10 mantissa bits as TF32 at twice the rate and half the
+                            bytes) by their producers, fp32 accumulate in TMEM; softmax / LayerNorm /
+                            gates / max / final 512->C FC stay fp32                             */
 
 /* window padding at the start of the bank / of a video */
 #define TMR_PAD_REPEAT 0 /* reference semantics (TRAIN:298-326): repeat-fill, leaks into previous video */
@@ -97,8 +98,8 @@ int tmr_classifier_pack(const float* w_h, const float* b_h, const float* w_c, co
 /* ---- a5: TimeConv.forward (NLB:43-79) ---------------------------------------------------------
  * x (B,L,D) -> out (B,L,D): out[b,k,c] = max(x[k], k>0 ? max(x[k],x[k-1]) : max(x[k],0),
  * conv3, conv5, conv7) with zero "same" padding inside each window.  Any L >= 1.
- * workspace >= tmr_timeconv_workspace_bytes(B,L,D) (used by TMR_MATH_TF32 for the TF32-rounded copy
- * of x that feeds the tensor cores; may be NULL in TMR_MATH_FP32). */
+ * workspace >= tmr_timeconv_workspace_bytes(B,L,D) (used by TMR_MATH_F16 for the fp16 copy of x
+ * that feeds the tensor cores; may be NULL in TMR_MATH_FP32). */
 size_t tmr_timeconv_workspace_bytes(int B, int L, int D);
 int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D, float* out,
                          void* workspace, size_t workspace_bytes, int math_mode, void* stream);
@@ -163,7 +164,7 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
                         float* St_out, void* workspace, size_t workspace_bytes, int math_mode,
                         void* stream);
 
-/* ---- bank-level head with the TimeConv deduplicated per bank ROW (TMR_MATH_TF32 only) ----------
+/* ---- bank-level head with the TimeConv deduplicated per bank ROW (TMR_MATH_F16 only) ----------
  * Same contract and results (up to fp32 summation order) as tmr_head_frames_fwd, for clip batches
  * sorted by start frame.  A clip is REGULAR when its window is a contiguous run of bank rows, i.e.
  * it lies at least L clips into its video (starts[b] - frame2vstart[starts[b]] >= L); then slot k of
@@ -222,9 +223,10 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
 int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                  float weight_decay, int first_step, void* stream);
 
-/* ---- generic fp32 linear used by the stages above (exposed for tests) --------------------------
- * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N. */
-int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,
+/* ---- generic linear used by the stages above (exposed for tests) -------------------------------
+ * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N.
+ * TMR_MATH_FP32: a, w are fp32.  TMR_MATH_F16: a, w are fp16 (K a multiple of 64); bias / out fp32. */
+int tmr_linear_fwd(const void* a, const void* w, const float* bias, int64_t M, int N, int K,
                    float* out, int relu, int math_mode, void* stream);
 
 #ifdef __cplusplus

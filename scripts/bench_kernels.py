@@ -31,13 +31,13 @@ def timeit(fn, reps=10):
     return a.elapsed_time(b) / reps
 
 rows = {}
-rows["lstm_last_frames (proj + 10 steps)"] = (timeit(lambda: ops.lstm_last_frames(packs[0], feats, starts, seq, "tf32")), (n_frames * 2 * 2048 * 2048 + 9 * B * 2 * 512 * 2048) / 1e9)
-rows["linear 8201x2048x2048 (projection)"] = (timeit(lambda: ops.linear(feats, m.lstm.weight_ih_l0, None, math_mode="tf32")), n_frames * 2 * 2048 * 2048 / 1e9)
+rows["lstm_last_frames (proj + 10 steps)"] = (timeit(lambda: ops.lstm_last_frames(packs[0], feats, starts, seq, "f16")), (n_frames * 2 * 2048 * 2048 + 9 * B * 2 * 512 * 2048) / 1e9)
+rows["linear 8201x2048x2048 (projection)"] = (timeit(lambda: ops.linear(feats, m.lstm.weight_ih_l0, None, math_mode="f16")), n_frames * 2 * 2048 * 2048 / 1e9)
 h = torch.from_numpy(synth.bank(B, seed=7)).to(dev)
-rows["linear 8192x2048x512 (recurrent GEMM, plain epilogue)"] = (timeit(lambda: ops.linear(h, m.lstm.weight_hh_l0, None, math_mode="tf32")), B * 2 * 512 * 2048 / 1e9)
-rows["timeconv general"] = (timeit(lambda: ops.timeconv_max(packs[1], win, "tf32"), 5), B * L * 2 * 512 * 512 * 15 / 1e9)
+rows["linear 8192x2048x512 (recurrent GEMM, plain epilogue)"] = (timeit(lambda: ops.linear(h, m.lstm.weight_hh_l0, None, math_mode="f16")), B * 2 * 512 * 2048 / 1e9)
+rows["timeconv general"] = (timeit(lambda: ops.timeconv_max(packs[1], win, "f16"), 5), B * L * 2 * 512 * 512 * 15 / 1e9)
 rows["bankconv (8222 rows)"] = (timeit(lambda: ops.bankconv(packs[1], bank, 0, B + 30)), (B + 30) * 2 * 512 * 512 * 15 / 1e9)
-rows["nlblock"] = (timeit(lambda: ops.nlblock(packs[2], St, win, "tf32")), B * 4 * 2 * 512 * 512 / 1e9)
-rows["fc_argmax"] = (timeit(lambda: ops.fc_argmax(packs[3], St, St, 7, "tf32")), B * 2 * 1024 * 512 / 1e9)
+rows["nlblock"] = (timeit(lambda: ops.nlblock(packs[2], St, win, "f16")), B * 4 * 2 * 512 * 512 / 1e9)
+rows["fc_argmax"] = (timeit(lambda: ops.fc_argmax(packs[3], St, St, 7, "f16")), B * 2 * 1024 * 512 / 1e9)
 for k, (ms, gf) in rows.items():
     print(f"{k:55s} {ms*1e3:9.1f} us  {gf/ms:8.1f} TFLOP/s")

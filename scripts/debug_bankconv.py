@@ -23,7 +23,7 @@ r0s = np.arange(100, 600)
 rows = r0s[:, None] - np.arange(L)[None, :]
 win = torch.from_numpy(bank[rows])                               # (B, L, 512)
 ref64 = orc.timeconv(win, sd, dtype=torch.float64)
-gen = ops.timeconv_max(pk, win.to(dev), "tf32").cpu()
+gen = ops.timeconv_max(pk, win.to(dev), "f16").cpu()
 gen32 = ops.timeconv_max(pk, win.to(dev), "fp32").cpu()
 k = np.arange(L)
 v = np.where(k <= 2, k + 1, np.where(L - 1 - k <= 2, 4 + (L - 1 - k), 0))

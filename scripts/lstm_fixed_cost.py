@@ -18,6 +18,6 @@ for B in (256, 2368, 4736, 9472, 18944):
     seq = 10
     feats = torch.from_numpy(synth.features(B + seq - 1, seed=1)).to(dev)
     st = torch.arange(B, device=dev)
-    t10 = timeit(lambda: ops.lstm_last_frames(pk, feats, st, 10, "tf32"))
-    t2 = timeit(lambda: ops.lstm_last_frames(pk, feats, st, 2, "tf32"))
+    t10 = timeit(lambda: ops.lstm_last_frames(pk, feats, st, 10, "f16"))
+    t2 = timeit(lambda: ops.lstm_last_frames(pk, feats, st, 2, "f16"))
     print(f"B={B:6d}: per recurrent step {(t10 - t2) / 8:7.1f} us   (10-step {t10:8.1f} us, 2-step {t2:8.1f} us)")

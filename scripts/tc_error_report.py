@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-stage error of the tensor-core (TF32) and fp32 CUDA paths against the fp64 oracle on a
+"""Per-stage error of the tensor-core (fp16 operands) and fp32 CUDA paths against the fp64 oracle on a
 config-4-shaped batch (run on the GPU box).  max|d|/max|ref| per stage."""
 import os
 import sys
@@ -40,7 +40,7 @@ def main():
     m = m.to(dev).eval()
     packs = m.packs()
     xd, lfd = torch.from_numpy(x).to(dev), torch.from_numpy(lf).to(dev)
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "f16"):
         St = ops.lstm_last(packs[0], xd, mode)
         Lt = ops.timeconv_max(packs[1], lfd, mode)
         y1 = ops.nlblock(packs[2], St, Lt, mode)

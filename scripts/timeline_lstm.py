@@ -10,7 +10,7 @@ feats = torch.from_numpy(synth.features(B + seq - 1, seed=1)).to(dev)
 sd = synth.head_state_dict(seed=1234)
 m = tb.resnet_lstm(); m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m = m.to(dev).eval()
 st = torch.arange(B, device=dev)
-for _ in range(3): ops.lstm_last_frames(m.packs()[0], feats, st, seq, "tf32")
+for _ in range(3): ops.lstm_last_frames(m.packs()[0], feats, st, seq, "f16")
 torch.cuda.synchronize()
 lib = _lib.load()
 n = 148 * 16 * 6

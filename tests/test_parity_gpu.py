@@ -3,7 +3,7 @@ fixtures.  Run on the B200 box: python -m pytest tests -m gpu.
 
 Tolerances (BASELINE.json north_star): window indices / gathered values / argmax bit-exact;
 logits within 1e-3 relative (max|d| / max|ref|), fp32 accumulate.  The fp32 CUDA-core mode is
-held to 2e-5; the TF32 tensor-core mode to 1e-3."""
+held to 2e-5; the tensor-core mode (fp16 operands, fp32 accumulate) to 1e-3."""
 import os
 
 import numpy as np
@@ -16,8 +16,8 @@ from tmrnet_b200 import ops, synth
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp32", "tf32"]
-TOL = {"fp32": 2e-5, "tf32": 1e-3}
+MODES = ["fp32", "f16"]
+TOL = {"fp32": 2e-5, "f16": 1e-3}
 
 
 def _dev():
@@ -32,15 +32,15 @@ def rel_err(got, ref):
 
 
 def _need_mode(mode):
-    if mode == "tf32":
+    if mode == "f16":
         from tmrnet_b200 import _lib
         x = torch.zeros(1, 1, 512, device=_dev())
         try:
             m = _model(7)
-            ops.timeconv_max(m.time_conv.packed(), x, "tf32")
+            ops.timeconv_max(m.time_conv.packed(), x, "f16")
         except _lib.TmrError as e:
             if "tcgen05" in str(e):
-                pytest.fail(f"TF32 tensor-core path unavailable on the GPU box: {e}")
+                pytest.fail(f"tensor-core path unavailable on the GPU box: {e}")
             raise
 
 
@@ -319,7 +319,7 @@ def test_head_matches_golden(golden_dir, mode, C):
     assert torch.equal(logits, l2)
     assert rel_err(logits, z[f"logits_c{C}"]) < TOL[mode]
     assert np.array_equal(pred.cpu().numpy(), z[f"pred_c{C}"])
-    assert np.allclose(score.cpu().numpy(), z[f"score_c{C}"], atol=2e-3 if mode == "tf32" else 1e-5)
+    assert np.allclose(score.cpu().numpy(), z[f"score_c{C}"], atol=2e-3 if mode == "f16" else 1e-5)
     mn = _model(C, use_timeconv=False)
     mn.math_mode = mode
     with torch.no_grad():
@@ -382,31 +382,31 @@ def test_linear_generic():
 # ------------------------------------------------------------------------------------------
 # tcgen05 GEMM engine in isolation
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 512), (1, 8, 32), (4, 512, 512), (130, 512, 1024),
-                                   (300, 2048, 2048), (1000, 260, 64), (20000, 512, 512)])
-def test_tf32_gemm_exact_on_small_integers(M, N, K):
-    """Integer-valued operands are exact in TF32 and their dot products exact in fp32, so any
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (1, 8, 64), (4, 512, 512), (130, 512, 1024),
+                                   (300, 2048, 2048), (1000, 260, 128), (20000, 512, 512)])
+def test_f16_gemm_exact_on_small_integers(M, N, K):
+    """Small-integer operands are exact in fp16 and their dot products exact in fp32, so any
     layout / swizzle / descriptor / pipeline mistake shows up as a bit mismatch."""
-    _need_mode("tf32")
+    _need_mode("f16")
     dev = _dev()
     rng = np.random.default_rng(M + N + K)
     a = torch.from_numpy(rng.integers(-4, 5, size=(M, K)).astype(np.float32))
     w = torch.from_numpy(rng.integers(-4, 5, size=(N, K)).astype(np.float32))
     b = torch.from_numpy(rng.integers(-9, 10, size=(N,)).astype(np.float32))
     ref = (a.double() @ w.double().T + b.double()).float()
-    got = ops.linear(a.to(dev), w.to(dev), b.to(dev), math_mode="tf32").cpu()
+    got = ops.linear(a.to(dev), w.to(dev), b.to(dev), math_mode="f16").cpu()
     bad = (got != ref).nonzero()
     assert bad.numel() == 0, f"{bad.shape[0]} mismatches, first at {bad[0].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-def test_tf32_gemm_random_precision():
-    _need_mode("tf32")
+def test_f16_gemm_random_precision():
+    _need_mode("f16")
     dev = _dev()
     rng = np.random.default_rng(1)
     a = torch.from_numpy(rng.standard_normal((513, 2048), dtype=np.float32))
     w = torch.from_numpy(rng.standard_normal((512, 2048), dtype=np.float32))
     ref = a.double() @ w.double().T
-    got = ops.linear(a.to(dev), w.to(dev), None, math_mode="tf32")
+    got = ops.linear(a.to(dev), w.to(dev), None, math_mode="f16")
     assert rel_err(got, ref) < 2e-3
     got32 = ops.linear(a.to(dev), w.to(dev), None, math_mode="fp32")
     assert rel_err(got32, ref) < 1e-5
@@ -475,9 +475,9 @@ def test_video_sharded_inference_is_bit_identical_to_unsharded(mode):
 @pytest.mark.parametrize("L", [6, 7, 10, 30, 60])
 def test_bankconv_variants_match_per_clip_timeconv(L):
     """Bank-level TimeConv (convolutions once per bank row, 7 edge variants) against the per-clip
-    tcgen05 kernel on windows that are contiguous runs of bank rows: same TF32 operands, only the
+    tcgen05 kernel on windows that are contiguous runs of bank rows: same fp16 operands, only the
     fp32 summation order differs."""
-    _need_mode("tf32")
+    _need_mode("f16")
     dev = _dev()
     n_rows = 500
     bank = synth.bank(n_rows, seed=3)
@@ -492,9 +492,9 @@ def test_bankconv_variants_match_per_clip_timeconv(L):
     k = np.arange(L)
     v = np.where(k <= 2, k + 1, np.where(L - 1 - k <= 2, 4 + (L - 1 - k), 0))
     ded = pb[torch.from_numpy(rows), torch.from_numpy(np.broadcast_to(v, rows.shape).copy())]
-    gen = ops.timeconv_max(pk, win.to(dev), "tf32").cpu()
+    gen = ops.timeconv_max(pk, win.to(dev), "f16").cpu()
     assert rel_err(ded, gen) < 2e-5
-    assert rel_err(ded, orc.timeconv(win, _sd(7), dtype=torch.float64)) < TOL["tf32"]
+    assert rel_err(ded, orc.timeconv(win, _sd(7), dtype=torch.float64)) < TOL["f16"]
 
 
 @pytest.mark.parametrize("L", [6, 10, 30, 60])
@@ -502,12 +502,12 @@ def test_bankconv_variants_match_per_clip_timeconv(L):
 @pytest.mark.parametrize("irr_from_rows", [False, True])
 def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode, irr_from_rows):
     """tmr_head_frames_dedup_fwd against the oracle (1e-3) and against the per-clip path.  The two
-    CUDA paths use identical TF32 operands; their TimeConv outputs differ by ~1e-5 (summation order),
-    which the TF32 re-rounding of later GEMM operands can amplify to the TF32 noise level, so they are
+    CUDA paths use identical fp16 operands; their TimeConv outputs differ by ~1e-5 (summation order),
+    which the fp16 conversion of later GEMM operands can amplify to the fp16 noise level, so they are
     held to the same 1e-3 as the oracle comparison.  Irregular clips (first L of every video) must agree
     exactly when they go through the per-clip TimeConv (irr_from_rows=False); assembled from per-row tap
     products (default) they differ by summation order only."""
-    _need_mode("tf32")
+    _need_mode("f16")
     from tmrnet_b200.infer import BankInference
     dev = _dev()
     lengths = [57, 12, 140, 9, 33, 210, 45, 400]
@@ -517,18 +517,18 @@ def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode, irr
     m = _model(7)
     idx = tb.LFBIndex.from_lengths(lengths, seq)
     f, b = torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)
-    ref = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=False, pad_mode=pad_mode).run(f, b)
-    eng = BankInference(m, idx, seq, L, batch_clips=300, math_mode="tf32", dedup=True, pad_mode=pad_mode,
+    ref = BankInference(m, idx, seq, L, batch_clips=300, math_mode="f16", dedup=False, pad_mode=pad_mode).run(f, b)
+    eng = BankInference(m, idx, seq, L, batch_clips=300, math_mode="f16", dedup=True, pad_mode=pad_mode,
                         irr_from_rows=irr_from_rows)
     assert eng._use_dedup()
     assert all((len(d["irr_rows"]) > 0) == (irr_from_rows and len(d["irr"]) > 0) for d in eng.dedup_plan())
     src = np.concatenate([d["src"] for d in eng.dedup_plan()])
     assert 0 < (src < 0).sum() < len(idx)
     got = eng.run(f, b)
-    assert rel_err(got["logits"], ref["logits"]) < TOL["tf32"]
+    assert rel_err(got["logits"], ref["logits"]) < TOL["f16"]
     irr = torch.from_numpy(src < 0).to(dev)
     if irr_from_rows:
-        assert rel_err(got["logits"][irr], ref["logits"][irr]) < TOL["tf32"]
+        assert rel_err(got["logits"][irr], ref["logits"][irr]) < TOL["f16"]
     else:
         assert torch.equal(got["logits"][irr], ref["logits"][irr])
     if pad_mode == "repeat":
@@ -536,9 +536,9 @@ def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode, irr
         x = np.stack([feats[s:s + seq] for s in starts])
         lf = orc.get_long_feature(starts, orc.build_start_dict(starts.tolist()), bank, L)
         ref_logits = orc.head(x, lf, _sd(7))[0]
-        assert rel_err(got["logits"], ref_logits) < TOL["tf32"]
+        assert rel_err(got["logits"], ref_logits) < TOL["f16"]
         top2 = torch.topk(ref_logits, 2, dim=1).values
-        safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL["tf32"] * float(ref_logits.abs().max())
+        safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL["f16"] * float(ref_logits.abs().max())
         assert torch.equal(got["pred"].cpu()[safe], ref_logits.argmax(1)[safe])
 
 
@@ -582,7 +582,7 @@ def test_bank_builder_is_self_consistent_with_the_head():
     out = BankInference(m, idx, seq, L, batch_clips=64, math_mode="fp32").run(torch.from_numpy(feats).to(dev), bank)
     lf = orc.get_long_feature(starts, orc.build_start_dict(starts.tolist()), ref_bank.numpy(), L)
     ref_logits = orc.head(x, lf, _sd(7))[0]
-    assert rel_err(out["logits"], ref_logits) < 2e-3      # bank itself came from the TF32 path
+    assert rel_err(out["logits"], ref_logits) < 2e-3      # bank itself came from the tensor-core path
 
 
 # ------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libtmr_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "tmr_b200.h")
 
 TMR_MATH_FP32 = 0
-TMR_MATH_TF32 = 1
+TMR_MATH_F16 = 1
 TMR_PAD_REPEAT = 0
 TMR_PAD_ZERO = 1
 

@@ -25,9 +25,9 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 static int check_mode(int math_mode) {
-  TMR_CHECK_ARG(math_mode == TMR_MATH_FP32 || math_mode == TMR_MATH_TF32, "unknown math_mode %d", math_mode);
-  if (math_mode == TMR_MATH_TF32 && !umma_available())
-    return set_error(TMR_ERR_UNSUPPORTED, "TMR_MATH_TF32 needs the tcgen05 kernels (sm_100a device + build)");
+  TMR_CHECK_ARG(math_mode == TMR_MATH_FP32 || math_mode == TMR_MATH_F16, "unknown math_mode %d", math_mode);
+  if (math_mode == TMR_MATH_F16 && !umma_available())
+    return set_error(TMR_ERR_UNSUPPORTED, "TMR_MATH_F16 needs the tcgen05 kernels (sm_100a device + build)");
   return TMR_OK;
 }
 static int check_dims(int D, int F = kF) {
@@ -36,11 +36,12 @@ static int check_dims(int D, int F = kF) {
   return TMR_OK;
 }
 static int do_linear(const LinearArgs& g, int mode, cudaStream_t st) {
-  if (mode != TMR_MATH_TF32) return simt_linear(g, st);
+  if (mode != TMR_MATH_F16) return simt_linear(g, st);
   LinearArgs h = g;
-  if (g.a_scratch) {       // A operand is raw fp32: round it to TF32 (RN) once, then feed the MMA
-    TMR_TRY(launch_round_concat(g.a, g.lda, g.a2, g.lda2, g.k_split, g.K, g.M, g.a_scratch, st, g.a2_plus_a));
-    h.a = g.a_scratch; h.lda = g.K; h.a2 = nullptr; h.lda2 = 0; h.k_split = 0;
+  if (!g.a16) {            // A operand is raw fp32: convert it to fp16 once, then feed the MMA
+    TMR_CHECK_ARG(g.a_scratch, "linear: tensor-core mode needs an fp16 A operand or a scratch buffer");
+    TMR_TRY(launch_half_concat(g.a, g.lda, g.a2, g.lda2, g.k_split, g.K, g.M, g.a_scratch, st, g.a2_plus_a));
+    h.a16 = g.a_scratch; h.lda = g.K;
   }
   return umma_linear(h, st);
 }
@@ -57,23 +58,25 @@ struct Carver {
 static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof(float), 256); }
 
 // ---- stage implementations on carved workspaces -------------------------------------------------
-// In TF32 mode every tensor that feeds a tensor-core GEMM is rounded to TF32 (round-to-nearest) by
-// its producer (epilogue flag) or by a rounding pass into `scratch`; weights come from the rounded
-// mirror of the pack.  fp32 mode touches neither.
+// In tensor-core mode every tensor that feeds a GEMM is converted to fp16 (round-to-nearest) by its
+// producer (which then writes fp16 instead of fp32) or by a conversion pass into `scratch`; weights come
+// from the fp16 mirror of the pack.  fp32 mode touches neither.  Workspace buffers keep their fp32 sizes.
 struct NLWs { float* w0; float* w1; float* s; };
 struct PbSrc { const float* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output
 // defer_residual (tensor-core head paths): `out` gets W4 r + b4 only; the consumer (classifier_impl with
-// y1_plus_St) adds St while it rounds [St || y1] for its GEMM
+// y1_plus_St) adds St while it converts [St || y1] for its GEMM
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
                         NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr, bool defer_residual = false) {
-  const bool tc = mode == TMR_MATH_TF32;
-  const float* w = pk + (tc ? NLBlockPacked::fp32_total : 0);
+  const bool tc = mode == TMR_MATH_F16;
+  const float* w = pk;
+  const half_t* w16 = mirror16<NLBlockPacked>(pk);
+  half_t* w0h = reinterpret_cast<half_t*>(ws.w0);      // tensor-core mode: attention / LayerNorm write fp16 here
   LinearArgs g;
   if (tc) {
     // u = W2^T (W1 St + b1) = W21 St + bu: the query linear and the phi fold in ONE GEMM (W21, bu built at pack time)
-    g = LinearArgs(); g.a = St; g.lda = kD; g.w = w + NLBlockPacked::w21_off; g.ldw = kD;
+    g = LinearArgs(); g.a = St; g.lda = kD; g.w16 = w16 + NLBlockPacked::w21_off; g.ldw = kD;
     g.bias = pk + NLBlockPacked::bu_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
-    g.a_scratch = ws.s;
+    g.a_scratch = reinterpret_cast<half_t*>(ws.s);
     TMR_TRY(do_linear(g, mode, st));
   } else {
     // q = St W1^T + b1                                   (NLB:26-27)
@@ -90,12 +93,14 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
   else TMR_TRY(launch_attention(ws.w1, Lt, B, L, ws.w0, tc, st));
   // v = W3 a + b3  (g folded after the weighted sum: sum_k p_k = 1)         (NLB:33-34)
   g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w3_off; g.ldw = kD;
+  if (tc) { g.a16 = w0h; g.w16 = w16 + NLBlockPacked::w3_off; }
   g.bias = pk + NLBlockPacked::b3_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
   TMR_TRY(do_linear(g, mode, st));
   // r = relu(LayerNorm(v))                                                 (NLB:35-36)
   TMR_TRY(launch_layernorm_relu(ws.w1, pk + NLBlockPacked::lnw_off, pk + NLBlockPacked::lnb_off, B, ws.w0, tc, st));
   // out = St + W4 r + b4   (dropout is the identity in eval)               (NLB:37-40)
   g = LinearArgs(); g.a = ws.w0; g.lda = kD; g.w = w + NLBlockPacked::w4_off; g.ldw = kD;
+  if (tc) { g.a16 = w0h; g.w16 = w16 + NLBlockPacked::w4_off; }
   g.bias = pk + NLBlockPacked::b4_off; g.out = out; g.ldo = kD;
   if (!(defer_residual && tc)) { g.residual = St; g.ldr = kD; }
   g.M = B; g.N = kD; g.K = kD;
@@ -105,29 +110,38 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
 struct LstmWs { float* xp; float* xr; float* h0; float* h1; float* c; };
 static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
                      int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0) {
-  const bool tc = mode == TMR_MATH_TF32;
-  const float* w = pk + (tc ? LstmPacked::fp32_total : 0);
+  const bool tc = mode == TMR_MATH_F16;
+  const float* w = pk;
+  const half_t* w16 = mirror16<LstmPacked>(pk);
   // input projection for every row of x once: xp = x Wih'^T + (b_ih + b_hh)', gate-interleaved
   LinearArgs g;
   g.a = x; g.lda = kF; g.w = w + LstmPacked::wih_off; g.ldw = kF; g.bias = pk + LstmPacked::bias_off;
   g.out = ws.xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
-  g.a_scratch = tc ? ws.xr : nullptr;
+  g.w16 = w16 + LstmPacked::wih_off;
+  g.a_scratch = tc ? reinterpret_cast<half_t*>(ws.xr) : nullptr;
   TMR_TRY(do_linear(g, mode, st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
   // (Running the recurrence in L2-sized sub-batches - all steps of one before the next, so that the projected
   // rows consecutive clips share stay in L2 - was measured slower at every size: the extra pipeline ramps
   // cost more than the HBM re-reads; profiles/r1_final_ncu.md.)
-  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (never rounded)
+  // t = 0 from zero state, then seq-1 recurrent steps; the last one writes `out` (always fp32).  In tensor-core
+  // mode the intermediate h only feeds the next step's MMA and lives in fp16 (h0 / h1 hold half_t[B,512]).
+  if (tc) {
+    half_t* h16[2] = {reinterpret_cast<half_t*>(ws.h0), reinterpret_cast<half_t*>(ws.h1)};
+    TMR_TRY(launch_lstm_cell0(xp, starts, seq, out, seq > 1 ? h16[0] : nullptr, ws.c, B, st, true));
+    for (int t = 1; t < seq; ++t) {
+      const bool last = (t == seq - 1);
+      TMR_TRY(umma_lstm_step(w16 + LstmPacked::whh_off, xp, starts, seq, t, h16[(t - 1) & 1], last ? nullptr : h16[t & 1],
+                             out, ws.c, B, st, ws.xp, n_rows_x, frame0));
+    }
+    return TMR_OK;
+  }
   float* hcur = (seq == 1) ? out : ws.h0;
-  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, ws.c, B, tc && seq > 1, st, tc));
+  TMR_TRY(launch_lstm_cell0(xp, starts, seq, hcur, nullptr, ws.c, B, st, false));
   for (int t = 1; t < seq; ++t) {
     const bool last = (t == seq - 1);
     float* hnext = last ? out : (hcur == ws.h0 ? ws.h1 : ws.h0);
-    if (tc)
-      TMR_TRY(umma_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, !last, st,
-                             ws.xp, n_rows_x, frame0));
-    else
-      TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, st));
+    TMR_TRY(simt_lstm_step(w + LstmPacked::whh_off, xp, starts, seq, t, hcur, hnext, ws.c, B, st));
     hcur = hnext;
   }
   return TMR_OK;
@@ -137,12 +151,13 @@ struct ClsWs { float* z; float* s; };
 static int classifier_impl(const float* pk, const float* St, const float* y1, int B, int C,
                            float* logits, int64_t* pred, float* score, ClsWs ws, int mode,
                            cudaStream_t st, bool y1_plus_St = false) {
-  const bool tc = mode == TMR_MATH_TF32;
-  const float* w = pk + (tc ? ClassifierPacked::fp32_total : 0);
+  const bool tc = mode == TMR_MATH_F16;
+  const float* w = pk;
   LinearArgs g;   // z = relu(fc_h_c([St || y1]))   (TRAIN:249-251, eval: dropout = identity)
   g.a = St; g.lda = kD; g.a2 = y1; g.lda2 = kD; g.k_split = kD; g.w = w + ClassifierPacked::wh_off;
   g.ldw = 2 * kD; g.bias = pk + ClassifierPacked::bh_off; g.out = ws.z; g.ldo = kD; g.M = B; g.N = kD;
-  g.K = 2 * kD; g.relu = 1; g.a_scratch = tc ? ws.s : nullptr; g.a2_plus_a = tc && y1_plus_St;
+  g.K = 2 * kD; g.relu = 1; g.a_scratch = tc ? reinterpret_cast<half_t*>(ws.s) : nullptr; g.a2_plus_a = tc && y1_plus_St;
+  g.w16 = mirror16<ClassifierPacked>(pk) + ClassifierPacked::wh_off;
   TMR_TRY(do_linear(g, mode, st));
   // fc_c (512 -> C) + softmax score + argmax stay fp32 on CUDA cores
   return launch_fc_argmax(ws.z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
@@ -151,9 +166,10 @@ static int classifier_impl(const float* pk, const float* St, const float* y1, in
 
 static int timeconv_impl(const float* pk, const float* x, int B, int L, float* out, float* xr, int mode,
                          cudaStream_t st) {
-  if (mode != TMR_MATH_TF32) return simt_timeconv(pk, x, B, L, out, st);
-  TMR_TRY(launch_round_tf32(x, xr, (int64_t)B * L * kD, st));
-  return umma_timeconv(pk, x, xr, B, L, out, st);
+  if (mode != TMR_MATH_F16) return simt_timeconv(pk, x, B, L, out, st);
+  half_t* x16 = reinterpret_cast<half_t*>(xr);
+  TMR_TRY(launch_to_half(x, x16, (int64_t)B * L * kD, st));
+  return umma_timeconv(pk, x, x16, B, L, out, st);
 }
 
 }  // namespace tmr
@@ -267,8 +283,8 @@ int tmr_timeconv_max_fwd(const void* packed, const float* x, int B, int L, int D
   TMR_CHECK_ARG(aligned16(x) && aligned16(out) && aligned16(packed), "timeconv: pointers must be 16-byte aligned");
   TMR_CHECK_ARG(x != out, "timeconv: in-place not supported");
   float* xr = nullptr;
-  if (math_mode == TMR_MATH_TF32) {
-    TMR_CHECK_ARG(workspace && aligned16(workspace), "timeconv: TF32 mode needs a workspace");
+  if (math_mode == TMR_MATH_F16) {
+    TMR_CHECK_ARG(workspace && aligned16(workspace), "timeconv: TMR_MATH_F16 needs a workspace");
     Carver cv(workspace, workspace_bytes);
     xr = cv.take((size_t)B * L * kD);
     TMR_CHECK_ARG(xr, "timeconv: workspace too small (%zu < %zu)", workspace_bytes, tmr_timeconv_workspace_bytes(B, L, D));
@@ -452,7 +468,7 @@ size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D) { return fbytes((siz
 int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
                      int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream) {
   TMR_TRY(check_dims(D));
-  TMR_TRY(check_mode(TMR_MATH_TF32));
+  TMR_TRY(check_mode(TMR_MATH_F16));
   TMR_CHECK_ARG(pb_rows >= 0 && row_base >= 0 && row_base + pb_rows <= n_rows, "bankconv: row range outside the bank");
   if (pb_rows == 0) return TMR_OK;
   TMR_CHECK_ARG(timeconv_packed && bank && pb && workspace, "bankconv: null pointer");
@@ -463,8 +479,9 @@ int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_r
   const int64_t r_lo = row_base - 3 > 0 ? row_base - 3 : 0;
   const int64_t r_hi = row_base + pb_rows + 4 < n_rows ? row_base + pb_rows + 4 : n_rows;
   cudaStream_t st = (cudaStream_t)stream;
-  TMR_TRY(launch_round_tf32(bank + r_lo * kD, bank_r, (r_hi - r_lo) * kD, st));
-  return umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows, pb, st);
+  half_t* bank16 = reinterpret_cast<half_t*>(bank_r);
+  TMR_TRY(launch_to_half(bank + r_lo * kD, bank16, (r_hi - r_lo) * kD, st));
+  return umma_bankconv((const float*)timeconv_packed, bank, bank16, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows, pb, st);
 }
 
 size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int n_irregular_rows,
@@ -489,7 +506,7 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
                               int64_t pb_rows, int seq, int L, int F, int D, int C, int pad_mode,
                               float* logits, int64_t* pred, float* score, float* St_out, void* workspace,
                               size_t workspace_bytes, void* stream) {
-  const int mode = TMR_MATH_TF32;
+  const int mode = TMR_MATH_F16;
   TMR_TRY(check_dims(D, F));
   TMR_TRY(check_mode(mode));
   TMR_CHECK_ARG(B >= 0 && seq >= 1 && n_feat_frames >= 0 && frame0 >= 0 && n_irregular >= 0 && pb_rows >= 0,
@@ -510,7 +527,7 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   Carver cv(workspace, workspace_bytes);
   LstmWs lw;
   bool ok = carve_lstm(cv, n_feat_frames, B, lw);
-  const int64_t r_lo = pb_row_base - 3 > 0 ? pb_row_base - 3 : 0;                       // rounded-bank slice
+  const int64_t r_lo = pb_row_base - 3 > 0 ? pb_row_base - 3 : 0;                       // fp16 bank slice
   const int64_t r_hi = pb_row_base + pb_rows + 4 < n_rows ? pb_row_base + pb_rows + 4 : n_rows;
   float* bank_r = cv.take((size_t)(pb_rows + 8) * kD);
   float* pb = cv.take((size_t)(pb_rows > 0 ? pb_rows : 1) * 7 * kD);
@@ -536,9 +553,10 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   float* St = St_out ? St_out : St_ws;
   TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0));
   if (pb_rows > 0) {
-    // TF32 (RN) copy of the bank rows the convolutions touch, then one pass of tap products per row
-    TMR_TRY(launch_round_tf32(bank + r_lo * kD, bank_r, (r_hi - r_lo) * kD, st));
-    TMR_TRY(umma_bankconv((const float*)timeconv_packed, bank, bank_r, n_rows, r_lo, r_hi - r_lo, pb_row_base,
+    // fp16 copy of the bank rows the convolutions touch, then one pass of tap products per row
+    half_t* bank16 = reinterpret_cast<half_t*>(bank_r);
+    TMR_TRY(launch_to_half(bank + r_lo * kD, bank16, (r_hi - r_lo) * kD, st));
+    TMR_TRY(umma_bankconv((const float*)timeconv_packed, bank, bank16, n_rows, r_lo, r_hi - r_lo, pb_row_base,
                           pb_rows, pb, st));
   }
   if (irr_rows) {
@@ -547,8 +565,9 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
     const float* tp = (const float*)timeconv_packed;
     TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, irregular_starts, n_irregular, L,
                           pad_mode, nullptr, wrows_i, st));
-    TMR_TRY(launch_compact_rows_round(bank, irregular_rows, n_irregular_rows, xc_i, st));
-    TMR_TRY(umma_bankconv_raw(tp, xc_i, n_irregular_rows, q_i, st));
+    half_t* xc16 = reinterpret_cast<half_t*>(xc_i);
+    TMR_TRY(launch_compact_rows_half(bank, irregular_rows, n_irregular_rows, xc16, st));
+    TMR_TRY(umma_bankconv_raw(tp, xc16, n_irregular_rows, q_i, st));
     TMR_TRY(launch_irr_assemble(q_i, irregular_rows, n_irregular_rows, wrows_i, bank, tp + TimeConvPacked::b3_off,
                                 tp + TimeConvPacked::b5_off, tp + TimeConvPacked::b7_off, n_irregular, L, lt_i, st));
   } else if (n_irregular > 0) {      // no row list given: per-clip gather + TimeConv
@@ -561,18 +580,20 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, mode, st, true);
 }
 
-int tmr_linear_fwd(const float* a, const float* w, const float* bias, int64_t M, int N, int K,
+int tmr_linear_fwd(const void* a, const void* w, const float* bias, int64_t M, int N, int K,
                    float* out, int relu, int math_mode, void* stream) {
-  // Exposed for tests of the GEMM engines: in TF32 mode the operands are consumed as given (the
-  // tensor core ignores the low 13 mantissa bits); callers wanting RN semantics pre-round them.
+  // Exposed for tests of the GEMM engines.  TMR_MATH_F16: `a` [M,K] and `w` [N,K] point to fp16 data (the
+  // caller converts; this entry point has no workspace), fp32 accumulate, fp32 bias / out.
   TMR_TRY(check_mode(math_mode));
   TMR_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, "linear: bad sizes");
   if (M == 0) return TMR_OK;
   TMR_CHECK_ARG(a && w && out, "linear: null pointer");
   TMR_CHECK_ARG(aligned16(a) && aligned16(w) && aligned16(out), "linear: pointers must be 16-byte aligned");
   LinearArgs g;
-  g.a = a; g.lda = K; g.w = w; g.ldw = K; g.bias = bias; g.out = out; g.ldo = N; g.M = M; g.N = N; g.K = K;
+  g.lda = K; g.ldw = K; g.bias = bias; g.out = out; g.ldo = N; g.M = M; g.N = N; g.K = K;
   g.relu = relu;
+  if (math_mode == TMR_MATH_F16) { g.a16 = reinterpret_cast<const half_t*>(a); g.w16 = reinterpret_cast<const half_t*>(w); }
+  else { g.a = reinterpret_cast<const float*>(a); g.w = reinterpret_cast<const float*>(w); }
   return do_linear(g, math_mode, (cudaStream_t)stream);
 }
 

@@ -89,27 +89,26 @@ int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const i
 // -------------------------------------------------------------------------------------------
 // Irregular clips of the bank-level path (windows that repeat-fill / leak across a video start): their
 // TimeConv is assembled from UNSHIFTED per-row tap products instead of a per-clip implicit GEMM.
-//   compact_rows_round: xc[i] = round_tf32(bank[rows[i]])        (the distinct rows those windows touch)
+//   compact_rows_half : xc[i] = fp16(bank[rows[i]])              (the distinct rows those windows touch)
 //   umma_bankconv_raw : q[i][tap] = W_tap . xc[i]                (15 taps x 512 per row, once per row)
 //   irr_assemble      : Lt[b,k] = max(x[k], k>0 ? x[k-1] : 0, conv3, conv5, conv7),
 //                       conv_K[k] = b_K + sum_{t, 0<=k+t<L} q[row(slot k+t)][tap(K,t)]      (NLB:55-68)
 // A clip's 236 MFLOP become ~34 KB of L2 reads per slot; only fp32 summation order changes.
 // -------------------------------------------------------------------------------------------
-__global__ void compact_rows_round_kernel(const float* __restrict__ bank, const int32_t* __restrict__ rows, int n,
-                                          float* __restrict__ out) {
+__global__ void compact_rows_half_kernel(const float* __restrict__ bank, const int32_t* __restrict__ rows, int n,
+                                         half_t* __restrict__ out) {
   const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // float4 index
   if (i4 >= (int64_t)n * (kD / 4)) return;
   const int i = (int)(i4 / (kD / 4));
   const int c4 = (int)(i4 - (int64_t)i * (kD / 4));
   float4 v = __ldg(reinterpret_cast<const float4*>(bank + (int64_t)rows[i] * kD) + c4);
-  v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-  reinterpret_cast<float4*>(out)[i4] = v;
+  reinterpret_cast<uint2*>(out)[i4] = pack_h4(v);
 }
-int launch_compact_rows_round(const float* bank, const int32_t* rows, int n, float* out, cudaStream_t st) {
+int launch_compact_rows_half(const float* bank, const int32_t* rows, int n, half_t* out, cudaStream_t st) {
   if (n <= 0) return TMR_OK;
   const int64_t total = (int64_t)n * (kD / 4);
-  compact_rows_round_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bank, rows, n, out);
-  TMR_LAUNCH_CHECK("compact_rows_round_kernel");
+  compact_rows_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bank, rows, n, out);
+  TMR_LAUNCH_CHECK("compact_rows_half_kernel");
   return TMR_OK;
 }
 
@@ -194,7 +193,8 @@ __device__ __forceinline__ float rcpf_approx(float x) { float y; asm("rcp.approx
 // FAST (tensor-core mode): MUFU ex2/rcp gates like the recurrent-step epilogue; fp32 mode keeps expf/tanhf.
 template <bool FAST>
 __global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* __restrict__ starts,
-                                  int seq, float* __restrict__ h, float* __restrict__ c, int64_t total4, int round_h) {
+                                  int seq, float* __restrict__ h, half_t* __restrict__ h16, float* __restrict__ c,
+                                  int64_t total4) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (clip, unit quad)
   if (idx >= total4) return;
   const int64_t m = idx / (kD / 4);
@@ -216,19 +216,19 @@ __global__ void lstm_cell0_kernel(const float* __restrict__ xp, const int64_t* _
       cn[k] = sigmoidf_(p.x) * tanhf(p.z);
       hn[k] = sigmoidf_(p.w) * tanhf(cn[k]);
     }
-    if (round_h) hn[k] = round_tf32(hn[k]);
   }
   *reinterpret_cast<float4*>(c + m * kD + u4) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-  *reinterpret_cast<float4*>(h + m * kD + u4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  if (h16) *reinterpret_cast<uint2*>(h16 + m * kD + u4) = pack_h4(hn[0], hn[1], hn[2], hn[3]);
+  else *reinterpret_cast<float4*>(h + m * kD + u4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
 }
 
-int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      int round_h, cudaStream_t st, bool fast_math) {
+int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, half_t* h16, float* c, int B,
+                      cudaStream_t st, bool fast_math) {
   const int64_t total4 = (int64_t)B * (kD / 4);
   if (total4 == 0) return TMR_OK;
   const unsigned blocks = (unsigned)((total4 + 255) / 256);
-  if (fast_math) lstm_cell0_kernel<true><<<blocks, 256, 0, st>>>(xp, starts, seq, h, c, total4, round_h);
-  else lstm_cell0_kernel<false><<<blocks, 256, 0, st>>>(xp, starts, seq, h, c, total4, round_h);
+  if (fast_math) lstm_cell0_kernel<true><<<blocks, 256, 0, st>>>(xp, starts, seq, h, h16, c, total4);
+  else lstm_cell0_kernel<false><<<blocks, 256, 0, st>>>(xp, starts, seq, h, h16, c, total4);
   TMR_LAUNCH_CHECK("lstm_cell0_kernel");
   return TMR_OK;
 }
@@ -245,7 +245,7 @@ constexpr int KB = 6;
 // Body shared by the two attention kernels; rowptr(k) yields the 512-float row of memory slot k.
 template <class RowPtr>
 __device__ __forceinline__ void attention_body(const float* __restrict__ u, int b, int L, float scale,
-                                               float* __restrict__ a, int round_out, RowPtr rowptr) {
+                                               void* __restrict__ a, int half_out, RowPtr rowptr) {
   const int lane = threadIdx.x & 31;
   float4 uq[4];
 #pragma unroll
@@ -305,22 +305,21 @@ __device__ __forceinline__ void attention_body(const float* __restrict__ u, int 
     run_max = new_max;
   }
   const float inv = 1.f / run_sum;
-  float4* dst = reinterpret_cast<float4*>(a + (int64_t)b * kD);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float4 o = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
-    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    dst[i * 32 + lane] = o;
+    const float4 o = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+    if (half_out) reinterpret_cast<uint2*>(reinterpret_cast<half_t*>(a) + (int64_t)b * kD)[i * 32 + lane] = pack_h4(o);
+    else reinterpret_cast<float4*>(reinterpret_cast<float*>(a) + (int64_t)b * kD)[i * 32 + lane] = o;
   }
 }
 
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
-                 float* __restrict__ a, int round_out) {
+                 void* __restrict__ a, int half_out) {
   const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const float4* base = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
-  attention_body(u, b, L, scale, a, round_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
+  attention_body(u, b, L, scale, a, half_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
 }
 
 // Attention over the bank-level TimeConv output PB[row][7][512] (umma_bankconv.cu).  src[b] >= 0:
@@ -330,35 +329,35 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
 // per clip by the general kernel.
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attention_pb_kernel(const float* __restrict__ u, const float* __restrict__ pb, const float* __restrict__ lt_irr,
-                    const int32_t* __restrict__ src, int B, int L, float scale, float* __restrict__ a,
-                    int round_out) {
+                    const int32_t* __restrict__ src, int B, int L, float scale, void* __restrict__ a,
+                    int half_out) {
   const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const int s = src[b];
   if (s >= 0) {
-    attention_body(u, b, L, scale, a, round_out, [&](int k) {
+    attention_body(u, b, L, scale, a, half_out, [&](int k) {
       const int v = (k <= 2) ? k + 1 : ((L - 1 - k <= 2) ? 4 + (L - 1 - k) : 0);
       return reinterpret_cast<const float4*>(pb + ((int64_t)(s - k) * 7 + v) * kD);
     });
   } else {
     const float4* base = reinterpret_cast<const float4*>(lt_irr + (int64_t)(-1 - s) * L * kD);
-    attention_body(u, b, L, scale, a, round_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
+    attention_body(u, b, L, scale, a, half_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
   }
 }
 
-int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st) {
+int launch_attention(const float* u, const float* Lt, int B, int L, void* a, int half_out, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   const float scale = (float)0.044194173824159216;   // (1/512)**0.5 as python computes it (NLB:31)
-  attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a, round_out);
+  attention_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, Lt, B, L, scale, a, half_out);
   TMR_LAUNCH_CHECK("attention_kernel");
   return TMR_OK;
 }
 
 int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
-                        float* a, int round_out, cudaStream_t st) {
+                        void* a, int half_out, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   const float scale = (float)0.044194173824159216;
-  attention_pb_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, pb, lt_irr, src, B, L, scale, a, round_out);
+  attention_pb_kernel<<<(B + kAttnWarps - 1) / kAttnWarps, kAttnWarps * 32, 0, st>>>(u, pb, lt_irr, src, B, L, scale, a, half_out);
   TMR_LAUNCH_CHECK("attention_pb_kernel");
   return TMR_OK;
 }
@@ -368,7 +367,7 @@ int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, co
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
-                      const float* __restrict__ bsh, int B, float* __restrict__ y, int round_out) {
+                      const float* __restrict__ bsh, int B, void* __restrict__ y, int half_out) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -385,7 +384,6 @@ layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
     q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / kD) + 1e-5f);
-  float4* dst = reinterpret_cast<float4*>(y + (int64_t)b * kD);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
@@ -395,15 +393,15 @@ layernorm_relu_kernel(const float* __restrict__ v, const float* __restrict__ w,
     o.y = fmaxf((x[i].y - mean) * rstd * g.y + be.y, 0.f);
     o.z = fmaxf((x[i].z - mean) * rstd * g.z + be.z, 0.f);
     o.w = fmaxf((x[i].w - mean) * rstd * g.w + be.w, 0.f);
-    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-    dst[i * 32 + lane] = o;
+    if (half_out) reinterpret_cast<uint2*>(reinterpret_cast<half_t*>(y) + (int64_t)b * kD)[i * 32 + lane] = pack_h4(o);
+    else reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (int64_t)b * kD)[i * 32 + lane] = o;
   }
 }
 
-int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y, int round_out,
+int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, void* y, int half_out,
                           cudaStream_t st) {
   if (B == 0) return TMR_OK;
-  layernorm_relu_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, w, b, B, y, round_out);
+  layernorm_relu_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, w, b, B, y, half_out);
   TMR_LAUNCH_CHECK("layernorm_relu_kernel");
   return TMR_OK;
 }
@@ -494,48 +492,50 @@ __global__ void interleave_bias_kernel(const float* __restrict__ bih, const floa
   dst[r] = bih[gate * kD + unit] + bhh[gate * kD + unit];
 }
 
-__global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = __ldg(src + i);
-    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-    dst[i] = v;
-  }
+__global__ void to_half_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = pack_h4(__ldg(src + i));
 }
-int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st) {
+int launch_to_half(const float* src, half_t* dst, int64_t n, cudaStream_t st) {
   if (n == 0) return TMR_OK;
-  TMR_CHECK_ARG(n % 4 == 0, "round_tf32: n must be a multiple of 4");
+  TMR_CHECK_ARG(n % 4 == 0, "to_half: n must be a multiple of 4");
   int64_t b = (n / 4 + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
-  round_tf32_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n / 4);
-  TMR_LAUNCH_CHECK("round_tf32_kernel");
+  to_half_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+  TMR_LAUNCH_CHECK("to_half_kernel");
   return TMR_OK;
 }
-// dst[m] = round_tf32([a[m] || a2[m]]); a2_plus_a: the second half is round(a2[m] + a[m]) (the non-local
-// block's residual St + W4 r, added here instead of in the GEMM epilogue, which pays ~30 us per batch for it)
-__global__ void round_concat_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ a2, int64_t lda2,
-                                    int k_split, int K, int64_t M, float* __restrict__ dst, int a2_plus_a) {
-  const int64_t n4 = M * (K / 4);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / (K / 4);
-    const int k = (int)(i - m * (K / 4)) * 4;
+// dst[m] = fp16([a[m] || a2[m]]); a2_plus_a: the second half is fp16(a2[m] + a[m]) (the non-local block's
+// residual St + W4 r, added here instead of in the GEMM epilogue, which pays ~30 us per batch for it).
+// A thread converts 8 consecutive floats (two 128-bit loads, one 128-bit store).
+__global__ void half_concat_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ a2, int64_t lda2,
+                                   int k_split, int K, int64_t M, half_t* __restrict__ dst, int a2_plus_a) {
+  const int64_t n8 = M * (K / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / (K / 8);
+    const int k = (int)(i - m * (K / 8)) * 8;
     const float* src = (k < k_split) ? a + m * lda + k : a2 + m * lda2 + (k - k_split);
     float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    float4 w = __ldg(reinterpret_cast<const float4*>(src) + 1);
     if (a2_plus_a && k >= k_split) {
       const float4 e = __ldg(reinterpret_cast<const float4*>(a + m * lda + (k - k_split)));
+      const float4 f = __ldg(reinterpret_cast<const float4*>(a + m * lda + (k - k_split)) + 1);
       v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      w.x += f.x; w.y += f.y; w.z += f.z; w.w += f.w;
     }
-    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-    *reinterpret_cast<float4*>(dst + m * K + k) = v;
+    const uint2 lo = pack_h4(v), hi = pack_h4(w);
+    *reinterpret_cast<uint4*>(dst + m * K + k) = make_uint4(lo.x, lo.y, hi.x, hi.y);
   }
 }
-int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
-                        int64_t M, float* dst, cudaStream_t st, bool a2_plus_a) {
+int launch_half_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
+                       int64_t M, half_t* dst, cudaStream_t st, bool a2_plus_a) {
   if (M == 0) return TMR_OK;
-  int64_t b = (M * (K / 4) + 255) / 256;
+  TMR_CHECK_ARG(K % 8 == 0 && (!a2 || k_split % 8 == 0), "half_concat: K and the split must be multiples of 8");
+  int64_t b = (M * (K / 8) + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
-  round_concat_kernel<<<(unsigned)b, 256, 0, st>>>(a, lda, a2, lda2, a2 ? k_split : K, K, M, dst,
-                                                   (a2 && a2_plus_a && K == 2 * k_split) ? 1 : 0);
-  TMR_LAUNCH_CHECK("round_concat_kernel");
+  half_concat_kernel<<<(unsigned)b, 256, 0, st>>>(a, lda, a2, lda2, a2 ? k_split : K, K, M, dst,
+                                                  (a2 && a2_plus_a && K == 2 * k_split) ? 1 : 0);
+  TMR_LAUNCH_CHECK("half_concat_kernel");
   return TMR_OK;
 }
 
@@ -550,7 +550,7 @@ int launch_pack_timeconv(const float* w3, const float* b3, const float* w5, cons
   copy_kernel<<<2, 256, 0, st>>>(b5, packed + TimeConvPacked::b5_off, kD);
   copy_kernel<<<2, 256, 0, st>>>(b7, packed + TimeConvPacked::b7_off, kD);
   TMR_LAUNCH_CHECK("pack_timeconv");
-  return launch_round_tf32(packed, packed + TimeConvPacked::fp32_total, TimeConvPacked::fp32_total, st);
+  return launch_to_half(packed, reinterpret_cast<half_t*>(packed + TimeConvPacked::fp32_total), TimeConvPacked::fp32_total, st);
 }
 
 int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const float* w3,
@@ -569,7 +569,7 @@ int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const
   TMR_LAUNCH_CHECK("pack_nlblock");
   {
     // W21[j][i] = sum_k W2T[j][k] W1[k][i] and bu[j] = sum_k W2T[j][k] b1[k], fp32; W1^T is staged in the
-    // mirror half, which the rounding pass below overwrites
+    // mirror half, which the fp16 conversion below overwrites
     float* w1t = packed + NLBlockPacked::fp32_total;
     transpose_kernel<<<dim3(kD / 32, kD / 32), dim3(32, 8), 0, st>>>(w1, w1t, kD);
     LinearArgs g;
@@ -581,7 +581,7 @@ int launch_pack_nlblock(const float* w1, const float* b1, const float* w2, const
     b.out = packed + NLBlockPacked::bu_off; b.ldo = kD; b.M = 1; b.N = kD; b.K = kD;
     TMR_TRY(simt_linear(b, st));
   }
-  return launch_round_tf32(packed, packed + NLBlockPacked::fp32_total, NLBlockPacked::fp32_total, st);
+  return launch_to_half(packed, reinterpret_cast<half_t*>(packed + NLBlockPacked::fp32_total), NLBlockPacked::fp32_total, st);
 }
 
 int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const float* bhh,
@@ -590,7 +590,7 @@ int launch_pack_lstm(const float* wih, const float* whh, const float* bih, const
   interleave_gates_kernel<<<blocks_for((int64_t)4 * kD * kD), 256, 0, st>>>(whh, packed + LstmPacked::whh_off, kD);
   interleave_bias_kernel<<<(4 * kD + 255) / 256, 256, 0, st>>>(bih, bhh, packed + LstmPacked::bias_off);
   TMR_LAUNCH_CHECK("pack_lstm");
-  return launch_round_tf32(packed, packed + LstmPacked::fp32_total, LstmPacked::fp32_total, st);
+  return launch_to_half(packed, reinterpret_cast<half_t*>(packed + LstmPacked::fp32_total), LstmPacked::fp32_total, st);
 }
 
 int launch_pack_classifier(const float* wh, const float* bh, const float* wc, const float* bc, int C,
@@ -603,7 +603,7 @@ int launch_pack_classifier(const float* wh, const float* bh, const float* wc, co
   copy_kernel<<<blocks_for((int64_t)C * kD), 256, 0, st>>>(wc, packed + ClassifierPacked::wc_off, (int64_t)C * kD);
   copy_kernel<<<1, 256, 0, st>>>(bc, packed + ClassifierPacked::bc_off, C);
   TMR_LAUNCH_CHECK("pack_classifier");
-  return launch_round_tf32(packed, packed + ClassifierPacked::fp32_total, ClassifierPacked::fp32_total, st);
+  return launch_to_half(packed, reinterpret_cast<half_t*>(packed + ClassifierPacked::fp32_total), ClassifierPacked::fp32_total, st);
 }
 
 }  // namespace tmr

@@ -45,18 +45,21 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int kD = 512;   // bank row width / LSTM hidden (reference hard-codes 512, NLB:26,17)
 constexpr int kF = 2048;  // backbone feature width
 
-// Round-to-nearest fp32 -> TF32 (10-bit mantissa).  tcgen05.mma.kind::tf32 ignores the low 13
-// mantissa bits of its operands (truncation, a systematic shrink of every product); operands of
-// the tensor-core path are therefore rounded once, by their producer, with cvt.rna.
-__device__ __forceinline__ float round_tf32(float v) {
+// Tensor-core operands are fp16 (tcgen05.mma kind::f16, fp32 accumulate): the same 10 explicit mantissa bits as
+// TF32, converted ONCE by the producer of each operand, round-to-nearest-even, saturating at +-65504
+// (one F2FP.SATFINITE.F16.F32.PACK_AB per pair).  Values below 2^-14 keep an absolute error <= 2^-25.
+typedef uint16_t half_t;          // raw fp16 bits; only ever produced by pack_h2 and consumed by the MMA
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
+__device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d) { return make_uint2(pack_h2(a, b), pack_h2(c, d)); }
+__device__ __forceinline__ uint2 pack_h4(const float4& v) { return pack_h4(v.x, v.y, v.z, v.w); }
 
 // ---- packed weight layouts (floats) ---------------------------------------------------------
-// Every pack holds the fp32 layout below followed by a mirror of it rounded to TF32 (same offsets
-// + fp32_total) that the tcgen05 path reads.
+// Every pack holds the fp32 layout below followed by an fp16 mirror of it (a half_t array that starts at float
+// offset fp32_total and uses the same ELEMENT offsets) that the tcgen05 path reads.
 // TimeConv: Wp_K[o][tap][c] = w_K[o][c][tap]  (K-major rows of length K*D), then biases.
 struct TimeConvPacked {
   static constexpr size_t w3_off = 0;
@@ -66,7 +69,7 @@ struct TimeConvPacked {
   static constexpr size_t b5_off = b3_off + kD;
   static constexpr size_t b7_off = b5_off + kD;
   static constexpr size_t fp32_total = b7_off + kD;
-  static constexpr size_t total = 2 * fp32_total;   // + TF32-rounded (RN) mirror for the tensor-core path
+  static constexpr size_t total = 2 * fp32_total;   // + fp16 mirror for the tensor-core path (half of it unused)
 };
 // NLBlock: W1[n][k], W2T[n][k] = W2[k][n], W3[n][k], W4[n][k], b1, b3, b4, ln_w, ln_b, then the query fold
 // W21 = W2^T W1 ([n][k]) and bu = W2^T b1, so the tensor-core path gets u = W2^T (W1 St + b1) from ONE GEMM.
@@ -105,5 +108,9 @@ struct ClassifierPacked {
   static constexpr size_t fp32_total = bc_off + kMaxC;
   static constexpr size_t total = 2 * fp32_total;
 };
+
+template <class P> inline const half_t* mirror16(const float* packed) {
+  return reinterpret_cast<const half_t*>(packed + P::fp32_total);
+}
 
 }  // namespace tmr

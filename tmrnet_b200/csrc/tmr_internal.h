@@ -14,9 +14,12 @@ struct LinearArgs {
   const float* residual = nullptr; int64_t ldr = 0;
   float* out = nullptr; int64_t ldo = 0;
   int64_t M = 0; int N = 0; int K = 0; int relu = 0;
-  int round_out = 0;            // round outputs to TF32 (they only feed another tensor-core GEMM)
-  float* a_scratch = nullptr;   // TF32 path: [M,K] buffer; A (|a2) is RN-rounded into it first
-  bool a2_plus_a = false;       // with a_scratch and a2: the a2 half becomes round(a2 + a) (deferred residual)
+  // tensor-core path: fp16 operands.  w16 = the pack's fp16 mirror (ldw elements).  A is either already fp16
+  // (a16, lda elements: its producer converted it) or raw fp32 in a (| a2), converted into a_scratch [M,K] first.
+  const half_t* w16 = nullptr;
+  const half_t* a16 = nullptr;
+  half_t* a_scratch = nullptr;
+  bool a2_plus_a = false;       // with a_scratch and a2: the a2 half becomes fp16(a2 + a) (deferred residual)
 };
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) ----
@@ -27,18 +30,20 @@ int simt_timeconv(const float* packed, const float* x, int B, int L, float* out,
 int simt_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
                    const float* h_prev, float* h_out, float* c, int B, cudaStream_t st);
 
-// ---- tcgen05 TF32 path (umma_*.cu); same contracts ----
+// ---- tcgen05 path, fp16 operands / fp32 accumulate (umma_*.cu); same contracts ----
 int umma_linear(const LinearArgs& g, cudaStream_t st);
-// x_r = x rounded to TF32 (MMA operand); x = exact values for the identity / pool branches
-int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, int L, float* out, cudaStream_t st);
+// x16 = fp16 copy of x (MMA operand); x = exact values for the identity / pool branches
+int umma_timeconv(const float* packed, const float* x, const half_t* x16, int B, int L, float* out, cudaStream_t st);
 // xp_base/xp_rows/xp_row0: the projected matrix itself ([xp_rows][4D], its row 0 = projected-row index
 // xp_row0) so that warps whose 32 clips read 32 consecutive projected rows can fetch them by TMA
-int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t,
-                   const float* h_prev, float* h_out, float* c, int B, int round_h, cudaStream_t st,
+// h_prev is fp16; the step writes h as fp16 into h_out16 (it only feeds the next step's MMA) or, for the last
+// step (h_out16 == nullptr), as fp32 into h_out.
+int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, int seq, int t,
+                   const half_t* h_prev, half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st,
                    const float* xp_base = nullptr, int64_t xp_rows = 0, int64_t xp_row0 = 0);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
-int umma_bankconv(const float* packed, const float* bank, const float* bank_r, int64_t n_rows, int64_t r_lo,
+int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,
                   int64_t r_cnt, int64_t row_base, int64_t pb_rows, float* pb, cudaStream_t st);
 
 // ---- memory-bound kernels (kernels_mem.cu) ----
@@ -47,27 +52,28 @@ int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const i
                   int32_t* rows_out, cudaStream_t st);
 // irregular clips of the bank-level path: compact + round the rows their windows touch, assemble their
 // TimeConv from unshifted per-row tap products (umma_bankconv_raw)
-int launch_compact_rows_round(const float* bank, const int32_t* rows, int n, float* out, cudaStream_t st);
+int launch_compact_rows_half(const float* bank, const int32_t* rows, int n, half_t* out, cudaStream_t st);
 int launch_irr_assemble(const float* q, const int32_t* crows, int n_c, const int32_t* wrows, const float* bank,
                         const float* b3, const float* b5, const float* b7, int n_clips, int L, float* out,
                         cudaStream_t st);
-int umma_bankconv_raw(const float* packed, const float* rows_r, int64_t n, float* q, cudaStream_t st);
+int umma_bankconv_raw(const float* packed, const half_t* rows16, int64_t n, float* q, cudaStream_t st);
 // step 0 of the LSTM from zero state: c = sig(i)*tanh(g), h = sig(o)*tanh(c) from xp rows.
-int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, float* c, int B,
-                      int round_h, cudaStream_t st, bool fast_math = false);
-// a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]
-int launch_attention(const float* u, const float* Lt, int B, int L, float* a, int round_out, cudaStream_t st);
+// h16 != nullptr: h goes out as fp16 (operand of the next step's MMA) instead of fp32 into h.
+int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h, half_t* h16, float* c, int B,
+                      cudaStream_t st, bool fast_math = false);
+// a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]; half_out: `a` receives fp16 (half_t[B,512])
+int launch_attention(const float* u, const float* Lt, int B, int L, void* a, int half_out, cudaStream_t st);
 // same attention over the bank-level TimeConv output (see umma_bankconv.cu)
 int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
-                        float* a, int round_out, cudaStream_t st);
-// y = relu(layer_norm(v) * w + b) over rows of 512
-int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, float* y,
-                          int round_out, cudaStream_t st);
-// dst[n] = round_tf32(src[n])
-int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st);
-// dst[M,K] = round_tf32([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))
-int launch_round_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
-                        int64_t M, float* dst, cudaStream_t st, bool a2_plus_a = false);
+                        void* a, int half_out, cudaStream_t st);
+// y = relu(layer_norm(v) * w + b) over rows of 512; half_out: y receives fp16
+int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, void* y,
+                          int half_out, cudaStream_t st);
+// dst[n] = fp16(src[n])
+int launch_to_half(const float* src, half_t* dst, int64_t n, cudaStream_t st);
+// dst[M,K] = fp16([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))
+int launch_half_concat(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, int K,
+                       int64_t M, half_t* dst, cudaStream_t st, bool a2_plus_a = false);
 // logits = z . Wc^T + bc ; score = max softmax prob ; pred = first argmax
 int launch_fc_argmax(const float* z, const float* wc, const float* bc, int B, int C, float* logits,
                      int64_t* pred, float* score, cudaStream_t st);

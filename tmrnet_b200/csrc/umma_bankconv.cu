@@ -1,4 +1,4 @@
-// Bank-level TimeConv (TMR_MATH_TF32): the multi-scale temporal convolutions computed ONCE PER BANK
+// Bank-level TimeConv (TMR_MATH_F16): the multi-scale temporal convolutions computed ONCE PER BANK
 // ROW instead of once per (clip, slot).
 //
 // For a clip whose window is a contiguous run of bank rows (every clip at least L clips into its
@@ -9,14 +9,14 @@
 // function of rho; at the three slots next to either edge the taps that fall outside the window
 // are dropped (zero "same" padding, NLB:55-65).  This kernel accumulates the 15 tap products of a
 // 128-row x 16-channel tile in TMEM (7 shift groups: 16/32/48/48/48/32/16 columns = 240, two buffers) with
-// tcgen05.mma.kind::tf32, and its epilogue assembles, per row, the SEVEN variants a window can ask
+// tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulate), and its epilogue assembles, per row, the SEVEN variants a window can ask
 // of that row:
 //     v0: interior      v1..v3: slot k = 0,1,2 (left-clipped)      v4..v6: slot k = L-1,L-2,L-3
 // each = max(bank[rho], pool, conv3, conv5, conv7) with pool = bank[rho+1] (slot k-1) or 0 for v1
 // (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512]; attention_pb_kernel consumes it.
 // 236 MFLOP/clip become 7.9 MFLOP/row; only summation order changes.
 //
-// The SM's ingest from L2 (about 55 B/cycle) bounds tcgen05 kernels with fp32 operands, so the seven time
+// The SM's ingest from L2 (about 55 B/cycle) is dear, so the seven time
 // shifts are NOT taken as seven shifted activation loads: the MMAs multiply the tile's rows unshifted
 // and the epilogue applies the shift by exchanging accumulator rows through shared memory (3-row halo,
 // 122 of 128 rows emitted per tile).  (Taking the shifts as row-offset descriptor views of one smem
@@ -31,12 +31,12 @@ namespace umma {
 constexpr int BC_BM = 128;                 // bank rows whose tap products one tile computes
 constexpr int BC_OUT = BC_BM - 6;          // rows it emits: the 3-row halo on either side feeds the shifts
 constexpr int BC_NCH = 16;                 // output channels per tile: 15 taps x 16 = 240 TMEM columns, double-buffered
-constexpr int BC_BK = 32;
+constexpr int BC_BK = 64;                  // fp16 input channels per k-step = one 128-byte swizzle row
 constexpr int BC_STAGES = 3;
-constexpr int BC_A_BYTES = BC_BM * BC_BK * 4;                  // 16 KB: the tile's rows for one channel chunk
-constexpr int BC_W7_BYTES = 7 * BC_NCH * BC_BK * 4;            // 14 KB: rows ordered [channel][tap]
-constexpr int BC_W5_BYTES = 5 * BC_NCH * BC_BK * 4;            // 10 KB
-constexpr int BC_W3_BYTES = 3 * BC_NCH * BC_BK * 4;            //  6 KB
+constexpr int BC_A_BYTES = BC_BM * BC_BK * 2;                  // 16 KB: the tile's rows for one channel chunk
+constexpr int BC_W7_BYTES = 7 * BC_NCH * BC_BK * 2;            // 14 KB: rows ordered [channel][tap]
+constexpr int BC_W5_BYTES = 5 * BC_NCH * BC_BK * 2;            // 10 KB
+constexpr int BC_W3_BYTES = 3 * BC_NCH * BC_BK * 2;            //  6 KB
 constexpr int BC_W_BYTES = BC_W7_BYTES + BC_W5_BYTES + BC_W3_BYTES;   // 30 KB = 240 rows: ONE MMA of N = 240 per k-step
 constexpr int BC_STAGE_BYTES = BC_A_BYTES + BC_W_BYTES;        // 46 KB
 constexpr int BC_EX_BYTES = 15 * BC_BM * 8 * 4;        // epilogue exchange: 15 taps x 128 rows x 8 channels
@@ -131,7 +131,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BC_BM, BC_N);
+      constexpr uint32_t idesc = make_idesc_f16(BC_BM, BC_N);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -146,8 +146,8 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + BC_A_BYTES);             // 240 stacked weight rows
 #pragma unroll
-          for (int k = 0; k < BC_BK / 8; ++k)
-            mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (chunk | k) != 0);
+          for (int k = 0; k < BC_BK / 16; ++k)
+            mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (chunk | k) != 0);
           mma_commit(&empty_bar[stage]);
           if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -323,25 +323,25 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
 }  // namespace umma
 
-static int launch_bankconv(const float* packed, const float* bank_r, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st);
+static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st);
 
-// Unshifted tap products of `n` (TF32-rounded) rows: q[(row*15 + tap)][512], taps 0..6 = conv7 t=-3..3,
+// Unshifted tap products of `n` fp16 rows: q[(row*15 + tap)][512], taps 0..6 = conv7 t=-3..3,
 // 7..11 = conv5 t=-2..2, 12..14 = conv3 t=-1..1.  The TimeConv of ANY window over these rows is
 // conv_K[k] = b_K + sum_t q[row(slot k+t)][tap(K,t)] (irr_assemble_kernel).
-int umma_bankconv_raw(const float* packed, const float* rows_r, int64_t n, float* q, cudaStream_t st) {
+int umma_bankconv_raw(const float* packed, const half_t* rows16, int64_t n, float* q, cudaStream_t st) {
   using namespace umma;
   if (n <= 0) return TMR_OK;
   BankConvParams p{};
   p.bank = nullptr; p.pb = nullptr; p.q_out = q; p.raw = 1;
   p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
   p.n_rows = n; p.row_base = 0; p.pb_rows = n; p.r_lo = 0;
-  return launch_bankconv(packed, rows_r, n, p, st);
+  return launch_bankconv(packed, rows16, n, p, st);
 }
 
 // pb[(row - row_base)*7 + v][512] for bank rows row_base .. row_base + pb_rows - 1.
-// bank = exact values (identity / pool branches); bank_r = rows r_lo .. r_lo + r_cnt - 1 of the bank
-// rounded to TF32 (MMA operand) — must cover row_base - 3 .. row_base + pb_rows + 2 where they exist.
-int umma_bankconv(const float* packed, const float* bank, const float* bank_r, int64_t n_rows, int64_t r_lo,
+// bank = exact values (identity / pool branches); bank16 = rows r_lo .. r_lo + r_cnt - 1 of the bank
+// in fp16 (MMA operand) — must cover row_base - 3 .. row_base + pb_rows + 2 where they exist.
+int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,
                   int64_t r_cnt, int64_t row_base, int64_t pb_rows, float* pb, cudaStream_t st) {
   using namespace umma;
   if (pb_rows <= 0) return TMR_OK;
@@ -350,10 +350,10 @@ int umma_bankconv(const float* packed, const float* bank, const float* bank_r, i
   p.bank = bank; p.pb = pb;
   p.bias3 = packed + TimeConvPacked::b3_off; p.bias5 = packed + TimeConvPacked::b5_off; p.bias7 = packed + TimeConvPacked::b7_off;
   p.n_rows = n_rows; p.row_base = row_base; p.pb_rows = pb_rows; p.r_lo = r_lo;
-  return launch_bankconv(packed, bank_r, r_cnt, p, st);
+  return launch_bankconv(packed, bank16, r_cnt, p, st);
 }
 
-static int launch_bankconv(const float* packed, const float* bank_r, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
+static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
   using namespace umma;
   p.num_tiles = ((p.pb_rows + BC_OUT - 1) / BC_OUT) * (kD / BC_NCH);
   static const int abl = [] { const char* e = getenv("TMR_BC_ABL"); return e ? atoi(e) : 0; }();
@@ -361,18 +361,18 @@ static int launch_bankconv(const float* packed, const float* bank_r, int64_t r_c
   CUtensorMap tx, tw3, tw5, tw7;
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
-    uint64_t str[1] = {(uint64_t)kD * 4};
+    uint64_t str[1] = {(uint64_t)kD * 2};
     uint32_t box[2] = {BC_BK, BC_BM};
-    TMR_TRY(make_tmap(&tx, bank_r, 2, dims, str, box));
-    const float* pr = packed + TimeConvPacked::fp32_total;
-    const float* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
+    TMR_TRY(make_tmap(&tx, bank16, 2, dims, str, box, 2));
+    const half_t* pr = mirror16<TimeConvPacked>(packed);
+    const half_t* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
     CUtensorMap* tw[3] = {&tw3, &tw5, &tw7};
     for (int i = 0; i < 3; ++i) {      // packed Wp_K[o][tap][c] viewed as (c, tap, o): a box = 16 channels x K taps x 32 c
       const int taps = 3 + 2 * i;
       uint64_t dw[3] = {(uint64_t)kD, (uint64_t)taps, (uint64_t)kD};
-      uint64_t sw[2] = {(uint64_t)kD * 4, (uint64_t)taps * kD * 4};
+      uint64_t sw[2] = {(uint64_t)kD * 2, (uint64_t)taps * kD * 2};
       uint32_t bw[3] = {BC_BK, (uint32_t)taps, BC_NCH};
-      TMR_TRY(make_tmap(tw[i], w[i], 3, dw, sw, bw));
+      TMR_TRY(make_tmap(tw[i], w[i], 3, dw, sw, bw, 2));
     }
   }
   TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));

@@ -1,5 +1,5 @@
 // sm_100a building blocks for the tensor-core path: mbarrier, TMA (cp.async.bulk.tensor), TMEM
-// allocation, tcgen05.mma kind::tf32 issue/commit, tcgen05.ld, and the shared-memory / instruction
+// allocation, tcgen05.mma kind::f16 issue/commit, tcgen05.ld, and the shared-memory / instruction
 // descriptors.  Inline PTX only; bit layouts follow the PTX ISA "tcgen05" matrix/instruction
 // descriptor tables (as also encoded in CUTLASS cute/arch/mma_sm100_desc.hpp).
 #pragma once
@@ -133,7 +133,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ------------------------------------------------------------------------------
-// K-major operand tile staged by TMA with SWIZZLE_128B: rows of 128 bytes (32 fp32 along K), 8-row
+// K-major operand tile staged by TMA with SWIZZLE_128B: rows of 128 bytes (64 fp16 along K), 8-row
 // swizzle atoms of 1024 bytes stacked along M/N (SBO = 1024).  LBO is unused for swizzled K-major.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -144,27 +144,29 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                          // [61,64) SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, dense.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+// kind::f16 with fp16 A and B (K-major, dense), fp32 accumulate.  fp16 carries the same 10 explicit mantissa
+// bits as TF32 at twice the tensor-core rate and half the operand bytes; every operand of the head (|w| < 1,
+// |h| < 1, backbone features of O(1..10)) sits far inside its range.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4)                 // [4,6)   D format  = F32
-         | (2u << 7)               // [7,10)  A format  = TF32
-         | (2u << 10)              // [10,13) B format  = TF32
+         | (0u << 7)               // [7,10)  A format  = F16
+         | (0u << 10)              // [10,13) B format  = F16
          | ((uint32_t)(N >> 3) << 17)   // [17,23) N >> 3
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
-// D[tmem] (+)= A[smem] . B[smem]^T ; issued by one thread for the whole CTA.
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+// D[tmem] (+)= A[smem] . B[smem]^T (K = 16 fp16 = 32 bytes per instruction); issued by one thread for the whole CTA.
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 // 2-SM MMA: M = 256 over a CTA pair (each CTA's smem holds its 128 rows of A and its half of B's N rows,
 // each CTA's TMEM receives its 128 accumulator rows); issued by ONE thread of the leader CTA.
-__device__ __forceinline__ void mma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit_2sm_mcast(uint64_t* bar, uint16_t mask) {
@@ -183,9 +185,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------
-// fp32 tensor of rank 2 or 3, innermost dimension contiguous, 128-byte swizzle, zero OOB fill.
-int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box);
+// fp16 (elem_bytes 2) or fp32 (4) tensor of rank 2 or 3, innermost dimension contiguous, 128-byte swizzle,
+// zero OOB fill.
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int elem_bytes);
 
 }  // namespace umma
 }  // namespace tmr

@@ -1,7 +1,7 @@
-// TMR_MATH_TF32 GEMM engine: persistent, warp-specialised tcgen05 kernel.
-//   C[M,N] = A[M,K] . W[N,K]^T   (both K-major fp32 in HBM, consumed as TF32, fp32 accumulate in TMEM)
-// Tile 128 x 256 x 32: TMA (SWIZZLE_128B) stages A (16 KB) + W (32 KB) per k-block through a 4-deep
-// mbarrier ring; one elected thread issues four tcgen05.mma.kind::tf32 (K=8) per stage; accumulators
+// TMR_MATH_F16 GEMM engine: persistent, warp-specialised tcgen05 kernel.
+//   C[M,N] = A[M,K] . W[N,K]^T   (both K-major fp16 in HBM, fp32 accumulate in TMEM)
+// Tile 128 x 256 x 64: TMA (SWIZZLE_128B) stages A (16 KB) + W (32 KB) per k-block through a 4-deep
+// mbarrier ring; one elected thread issues four tcgen05.mma.kind::f16 (K=16) per stage; accumulators
 // are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1.  Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (tcgen05.ld; two
 // warps per TMEM lane quarter, one per 128-column half, so every SM sub-partition has two warps to
@@ -17,8 +17,8 @@
 namespace tmr {
 namespace umma {
 
-int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int elem_bytes) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -37,7 +37,8 @@ int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dim
   cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdims, gstr, gbox, estr,
+  const CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = encode(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -47,7 +48,7 @@ int make_tmap(CUtensorMap* out, const float* base, int rank, const uint64_t* dim
   return TMR_OK;
 }
 
-constexpr int BM = 128, BN = 256, BK = 32;           // BK fp32 = 128 bytes = one swizzle row
+constexpr int BM = 128, BN = 256, BK = 64;           // BK fp16 = 128 bytes = one swizzle row
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 // Per-epilogue configuration.  The LSTM-cell epilogue, not the MMAs, bounds the recurrent step, so it gets
 // 16 epilogue warps (4 per SM sub-partition) and pays for their 32x32 fp32 smem tiles (TMEM transpose
@@ -62,8 +63,8 @@ template <int EPI> struct Cfg {
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_TILES * 4096;
   static constexpr int COLS_PER_WARP = 1024 / EPI_WARPS;         // 4 warps per TMEM lane quarter share 256 columns
 };
-constexpr int A_BYTES = BM * BK * 4;                 // 16 KB
-constexpr int B_BYTES = BN * BK * 4;                 // 32 KB
+constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+constexpr int B_BYTES = BN * BK * 2;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 template <int EPI, bool TWOSM = false> constexpr int smem_bytes() {
   return (TWOSM ? Cfg<EPI>::STAGES_2SM * (A_BYTES + B_BYTES / 2) : Cfg<EPI>::STAGES * STAGE_BYTES) +
@@ -80,9 +81,9 @@ __device__ long long g_timeline_warps[16 * 16 * 4];   // CTA 0: [tile][epilogue 
 struct GemmParams {
   int64_t M; int N; int K; int k_split;
   // EPI_LINEAR
-  const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu; int round_out;
+  const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
-  const float* xp; const int64_t* starts; int seq; int t; float* h_out; float* c; int round_h;
+  const float* xp; const int64_t* starts; int seq; int t; float* h_out; half_t* h_out16; float* c;
   int x_tma; int64_t x_row0;          // tma_x covers the projected rows; its row 0 is projected row x_row0
   const float* xp_base; int64_t xp_rows;   // host side only: what tma_x is built over
   int timeline;
@@ -218,7 +219,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && (!TWOSM || crank == 0)) {                 // 2-SM: only the leader CTA issues
-      constexpr uint32_t idesc = make_idesc_tf32(TWOSM ? 2 * BM : BM, BN);
+      constexpr uint32_t idesc = make_idesc_f16(TWOSM ? 2 * BM : BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
@@ -238,9 +239,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sb);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {            // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-            if (TWOSM) mma_tf32_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {           // UMMA_K = 16 fp16 = 32 bytes inside the swizzle row
+            if (TWOSM) mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           if (CL == 1) mma_commit(&empty_bar[stage]);   // frees the smem stage when these MMAs retire
           else if (TWOSM) mma_commit_2sm_mcast(&empty_bar[stage], kMask);
@@ -333,8 +334,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         xr[1] = __shfl_sync(0xffffffffu, xrow, (lane >> 1) + 16);
         const float* xp0 = p.xp + n0 + 16 * half;
         const int64_t c0 = (m_base + (lane >> 1)) * kD + (n0 >> 2) + 4 * half;   // + 16*kD for the second row, + cc/4 per chunk
-        // h only feeds the next step's MMA: round to nearest TF32 ((bits + half ulp) & mask, |h| < 1 is finite)
-        const uint32_t h_add = p.round_h ? 0x1000u : 0u, h_mask = p.round_h ? 0xffffe000u : 0xffffffffu;
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 3] = clock64();
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
@@ -407,11 +406,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               for (int k = 0; k < 4; ++k) {
                 const float4 v = g[4 * i + k];
                 lstm_cell_fast(v.x, v.y, v.z, v.w, cin[k], cn[k], hn[k]);
-                hn[k] = __uint_as_float((__float_as_uint(hn[k]) + h_add) & h_mask);
               }
               const int64_t o = c0 + (int64_t)i * (16 * kD) + (cc >> 2);
               *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-              *reinterpret_cast<float4*>(p.h_out + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+              // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
+              if (p.h_out16) *reinterpret_cast<uint2*>(p.h_out16 + o) = pack_h4(hn[0], hn[1], hn[2], hn[3]);
+              else *reinterpret_cast<float4*>(p.h_out + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             }
           }
         };
@@ -457,7 +457,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
                 }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
                 *reinterpret_cast<float4*>(p.out + mr * p.ldo + n) = v;
               }
             }
@@ -491,33 +490,33 @@ static int num_sms() {
 }
 
 template <int EPI>
-static int launch_gemm(const float* a, int64_t lda, const float* a2, int64_t lda2, int k_split, const float* w,
+static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t lda2, int k_split, const half_t* w,
                        int64_t ldw, const GemmParams& p, cudaStream_t st) {
   CUtensorMap ta, ta2, tb, tx;
   {
     const int ka = a2 ? k_split : p.K;
     uint64_t dims[2] = {(uint64_t)ka, (uint64_t)p.M};
-    uint64_t str[1] = {(uint64_t)lda * 4};
+    uint64_t str[1] = {(uint64_t)lda * 2};
     uint32_t box[2] = {BK, BM};
-    TMR_TRY(make_tmap(&ta, a, 2, dims, str, box));
+    TMR_TRY(make_tmap(&ta, a, 2, dims, str, box, 2));
     if (a2) {
       uint64_t d2[2] = {(uint64_t)(p.K - k_split), (uint64_t)p.M};
-      uint64_t s2[1] = {(uint64_t)lda2 * 4};
-      TMR_TRY(make_tmap(&ta2, a2, 2, d2, s2, box));
+      uint64_t s2[1] = {(uint64_t)lda2 * 2};
+      TMR_TRY(make_tmap(&ta2, a2, 2, d2, s2, box, 2));
     } else {
       ta2 = ta;
     }
     uint64_t dw[2] = {(uint64_t)p.K, (uint64_t)p.N};
-    uint64_t sw[1] = {(uint64_t)ldw * 4};
+    uint64_t sw[1] = {(uint64_t)ldw * 2};
     uint32_t bw[2] = {BK, BN / 2};                 // W tiles are fetched as two 128-row halves
-    TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw));
+    TMR_TRY(make_tmap(&tb, w, 2, dw, sw, bw, 2));
     tx = ta;
     const_cast<GemmParams&>(p).x_tma = 0;
     if (EPI == EPI_LSTM && p.xp_base && p.xp_rows > 0) {   // projected rows [xp_rows][N], 32 x 32 boxes per epilogue warp
       uint64_t dx[2] = {(uint64_t)p.N, (uint64_t)p.xp_rows};
       uint64_t sx[1] = {(uint64_t)p.N * 4};
       uint32_t bx[2] = {32, 32};
-      TMR_TRY(make_tmap(&tx, p.xp_base, 2, dx, sx, bx));
+      TMR_TRY(make_tmap(&tx, p.xp_base, 2, dx, sx, bx, 4));
       const_cast<GemmParams&>(p).x_tma = 1;
     }
   }
@@ -583,28 +582,27 @@ bool umma_available() {
 }
 
 int umma_linear(const LinearArgs& g, cudaStream_t st) {
-  TMR_CHECK_ARG(g.K % umma::BK == 0 && g.K > 0, "tf32 linear: K=%d must be a multiple of %d", g.K, umma::BK);
-  TMR_CHECK_ARG(g.N % 4 == 0, "tf32 linear: N=%d must be a multiple of 4", g.N);
-  TMR_CHECK_ARG(g.lda % 4 == 0 && g.ldw % 4 == 0 && g.ldo % 4 == 0, "tf32 linear: leading dims must be multiples of 4");
-  TMR_CHECK_ARG(!g.a2 || (g.k_split % umma::BK == 0 && g.lda2 % 4 == 0), "tf32 linear: bad split");
-  TMR_CHECK_ARG(g.M < (int64_t)INT32_MAX, "tf32 linear: M too large");
+  TMR_CHECK_ARG(g.K % umma::BK == 0 && g.K > 0, "f16 linear: K=%d must be a multiple of %d", g.K, umma::BK);
+  TMR_CHECK_ARG(g.N % 4 == 0, "f16 linear: N=%d must be a multiple of 4", g.N);
+  TMR_CHECK_ARG(g.a16 && g.w16, "f16 linear: fp16 operands missing");
+  TMR_CHECK_ARG(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldo % 4 == 0, "f16 linear: leading dims must be multiples of 8 (A, W) / 4 (out)");
+  TMR_CHECK_ARG(g.M < (int64_t)INT32_MAX, "f16 linear: M too large");
   if (g.M == 0) return TMR_OK;
   umma::GemmParams p{};
-  p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.a2 ? g.k_split : g.K;
-  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu; p.round_out = g.round_out;
-  return umma::launch_gemm<umma::EPI_LINEAR>(g.a, g.lda, g.a2, g.lda2, g.k_split, g.w, g.ldw, p, st);
+  p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.K;
+  p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu;
+  return umma::launch_gemm<umma::EPI_LINEAR>(g.a16, g.lda, nullptr, 0, 0, g.w16, g.ldw, p, st);
 }
 
-int umma_lstm_step(const float* whh, const float* xp, const int64_t* starts, int seq, int t, const float* h_prev,
-                   float* h_out, float* c, int B, int round_h, cudaStream_t st, const float* xp_base,
+int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, int seq, int t, const half_t* h_prev,
+                   half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st, const float* xp_base,
                    int64_t xp_rows, int64_t xp_row0) {
   if (B == 0) return TMR_OK;
   umma::GemmParams p{};
-  p.round_h = round_h;
   p.xp_base = xp_base; p.xp_rows = xp_rows; p.x_row0 = xp_row0;
   p.M = B; p.N = 4 * kD; p.K = kD; p.k_split = kD;
-  p.xp = xp; p.starts = starts; p.seq = seq; p.t = t; p.h_out = h_out; p.c = c;
-  return umma::launch_gemm<umma::EPI_LSTM>(h_prev, kD, nullptr, 0, 0, whh, kD, p, st);
+  p.xp = xp; p.starts = starts; p.seq = seq; p.t = t; p.h_out = h_out; p.h_out16 = h_out16; p.c = c;
+  return umma::launch_gemm<umma::EPI_LSTM>(h_prev, kD, nullptr, 0, 0, whh16, kD, p, st);
 }
 
 }  // namespace tmr

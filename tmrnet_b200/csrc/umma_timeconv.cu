@@ -1,12 +1,12 @@
-// TMR_MATH_TF32 TimeConv (NLB:43-79): the three zero-padded temporal convolutions (k=3/5/7,
+// TMR_MATH_F16 TimeConv (NLB:43-79): the three zero-padded temporal convolutions (k=3/5/7,
 // 512->512) as ONE implicit GEMM on tcgen05 with a fused 5-way-max epilogue.
 //
 // Tile: up to 128 window rows (nb = 128/L whole windows when L <= 128, else a 128-slot chunk of one
 // window) x 128 output channels.  Three fp32 accumulators (conv3/conv5/conv7, 128 columns each) live
-// in TMEM.  The K loop walks (input-channel chunk of 32) x (time shift d = -3..3): for each pair one
+// in TMEM.  The K loop walks (input-channel chunk of 64 fp16) x (time shift d = -3..3): for each pair one
 // TMA load brings the window rows shifted by d — a rank-3 tensor map (D, L, B) whose out-of-bounds
 // fill supplies the zero "same" padding at both window edges — plus the weight tap tiles of every
-// conv that has that shift (3, 2 or 1 tiles).  One elected thread issues the tcgen05.mma.kind::tf32
+// conv that has that shift (3, 2 or 1 tiles).  One elected thread issues the tcgen05.mma.kind::f16
 // instructions; four epilogue warps then read the accumulators with tcgen05.ld, add the biases and
 // take max(conv3, conv5, conv7, x[k], k>0 ? x[k-1] : 0).
 #include "tmr_internal.h"
@@ -17,10 +17,10 @@ namespace umma {
 
 constexpr int TC_BM = 128;          // window rows per tile (TMEM lanes)
 constexpr int TC_BN = 128;          // output channels per tile
-constexpr int TC_BK = 32;           // input channels per k-block (128-byte swizzle row)
+constexpr int TC_BK = 64;           // fp16 input channels per k-block (128-byte swizzle row)
 constexpr int TC_STAGES = 3;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;            // 16 KB
-constexpr int TC_W_BYTES = TC_BN * TC_BK * 4;            // 16 KB per tap tile
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;            // 16 KB
+constexpr int TC_W_BYTES = TC_BN * TC_BK * 2;            // 16 KB per tap tile
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + 3 * TC_W_BYTES;   // 64 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;
 constexpr int TC_THREADS = 192;
@@ -66,7 +66,7 @@ umma_timeconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t x_bytes = (uint32_t)(p.nb * p.box_l * TC_BK * 4);
+  const uint32_t x_bytes = (uint32_t)(p.nb * p.box_l * TC_BK * 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -92,7 +92,7 @@ umma_timeconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      constexpr uint32_t idesc = make_idesc_f16(TC_BM, TC_BN);
       int stage = 0; uint32_t phase = 0;
       for (int chunk = 0; chunk < kD / TC_BK; ++chunk) {
         for (int d = -3; d <= 3; ++d) {
@@ -111,8 +111,8 @@ umma_timeconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
               const uint64_t db = make_smem_desc_sw128(sa + TC_A_BYTES + w * TC_W_BYTES);
               const bool first = (chunk == 0) && (d == -half);       // first contribution to this accumulator
 #pragma unroll
-              for (int k = 0; k < TC_BK / 8; ++k)
-                mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, !(first && k == 0));
+              for (int k = 0; k < TC_BK / 16; ++k)
+                mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, !(first && k == 0));
             }
           }
           mma_commit(&empty_bar[stage]);
@@ -170,7 +170,7 @@ umma_timeconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
 }  // namespace umma
 
-int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, int L, float* out, cudaStream_t st) {
+int umma_timeconv(const float* packed, const float* x, const half_t* x16, int B, int L, float* out, cudaStream_t st) {
   using namespace umma;
   if (B == 0) return TMR_OK;
   TimeConvParams p{};
@@ -185,18 +185,18 @@ int umma_timeconv(const float* packed, const float* x, const float* x_r, int B, 
   CUtensorMap tx, tw3, tw5, tw7;
   {
     uint64_t dims[3] = {(uint64_t)kD, (uint64_t)L, (uint64_t)B};
-    uint64_t str[2] = {(uint64_t)kD * 4, (uint64_t)L * kD * 4};
+    uint64_t str[2] = {(uint64_t)kD * 2, (uint64_t)L * kD * 2};
     uint32_t box[3] = {TC_BK, (uint32_t)p.box_l, (uint32_t)p.nb};
-    TMR_TRY(make_tmap(&tx, x_r, 3, dims, str, box));
-    const float* pr = packed + TimeConvPacked::fp32_total;      // TF32-rounded weight mirror
-    const float* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
+    TMR_TRY(make_tmap(&tx, x16, 3, dims, str, box, 2));
+    const half_t* pr = mirror16<TimeConvPacked>(packed);        // fp16 weight mirror
+    const half_t* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
     CUtensorMap* tw[3] = {&tw3, &tw5, &tw7};
     for (int i = 0; i < 3; ++i) {
       const int taps = 3 + 2 * i;
       uint64_t dw[2] = {(uint64_t)taps * kD, (uint64_t)kD};
-      uint64_t sw[1] = {(uint64_t)taps * kD * 4};
+      uint64_t sw[1] = {(uint64_t)taps * kD * 2};
       uint32_t bw[2] = {TC_BK, TC_BN};
-      TMR_TRY(make_tmap(tw[i], w[i], 2, dw, sw, bw));
+      TMR_TRY(make_tmap(tw[i], w[i], 2, dw, sw, bw, 2));
     }
   }
   TMR_CUDA(cudaFuncSetAttribute(umma_timeconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));

@@ -80,7 +80,7 @@ class BankInference:
 
     def _use_dedup(self):
         mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
-        return self.dedup and mode == ops.TMR_MATH_TF32
+        return self.dedup and mode == ops.TMR_MATH_F16
 
     def dedup_plan(self):
         """Per batch: which clips are regular (window = contiguous run of bank rows), the PB row range
@@ -305,7 +305,7 @@ class BankInference:
         tc = 1 if self.model.time_conv is not None else 0
         lstm = 1 + 1 + (self.seq - 1)
         tail = 6 + 2
-        if mode != ops.TMR_MATH_TF32:
+        if mode != ops.TMR_MATH_F16:
             return (lstm + 1 + tc + tail) * len(self.plan())
         tail -= 1                                      # u = W21 St + bu: one GEMM for q and u
         if not self._use_dedup():

@@ -9,17 +9,18 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import TMR_MATH_FP32, TMR_MATH_TF32, TMR_PAD_REPEAT, TMR_PAD_ZERO, check
+from ._lib import TMR_MATH_FP32, TMR_MATH_F16, TMR_PAD_REPEAT, TMR_PAD_ZERO, check
 
 D = 512
 F = 2048
 
-_default_math = [TMR_MATH_TF32]      # tensor cores by default; 'fp32' = CUDA-core exact-order mode
-_MATH_NAMES = {"fp32": TMR_MATH_FP32, "tf32": TMR_MATH_TF32}
+_default_math = [TMR_MATH_F16]      # tensor cores by default; 'fp32' = CUDA-core exact-order mode
+_MATH_NAMES = {"fp32": TMR_MATH_FP32, "f16": TMR_MATH_F16}
 
 
 def set_math_mode(mode):
-    """'fp32' (CUDA-core FFMA, reference-order parity) or 'tf32' (tcgen05 tensor cores)."""
+    """'fp32' (CUDA-core FFMA, reference-order parity) or 'f16' (tcgen05 tensor cores: fp16 operands,
+    fp32 accumulate)."""
     _default_math[0] = _MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
 
 
@@ -145,7 +146,7 @@ def timeconv_max(packed, x, math_mode=None):
     out = torch.empty_like(x)
     lib = _lib.load()
     mode = _mode(math_mode)
-    ws = _ws(lib.tmr_timeconv_workspace_bytes(B, L, D), x.device) if mode == TMR_MATH_TF32 else None
+    ws = _ws(lib.tmr_timeconv_workspace_bytes(B, L, D), x.device) if mode == TMR_MATH_F16 else None
     with torch.cuda.device(x.device):
         check(lib.tmr_timeconv_max_fwd(_ptr(packed), _ptr(x), B, L, D, _ptr(out), _ptr(ws),
                                        ws.numel() if ws is not None else 0, mode, _stream()))
@@ -240,6 +241,8 @@ def linear(a, w, bias=None, relu=False, math_mode=None):
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if _mode(math_mode) == TMR_MATH_F16:      # the entry point takes fp16 operands in tensor-core mode
+        a, w = a.half().contiguous(), w.half().contiguous()
     with torch.cuda.device(a.device):
         check(_lib.load().tmr_linear_fwd(_ptr(a), _ptr(w), _ptr(bias), M, N, K, _ptr(out), int(relu), _mode(math_mode),
                                          _stream()))
