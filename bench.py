@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — TMRNet head frames/s at L=30, seq=10 (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math fp32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math fp32|f16]
 
 Workload (BASELINE.json configs[1]): train_non-local_mutiConv_resnet.py head — LSTM(2048->512, 10
 frames) + multi-scale TimeConv + non-local block + FCs, L=30 — over a synthetic 40-video
@@ -42,10 +42,11 @@ BYTES_GATHER = 2 * 30 * 512 * 4                  # 122 880 B
 BYTES_RELATION = 30 * 512 * 4 + 2 * 512 * 4      # 65 536 B
 FLOP_LSTM_STEP = 2 * 4 * 512 * 512               # 2.097 MFLOP per clip per recurrent step
 FLOP_BANKCONV_ROW = 2 * 512 * 512 * 15           # 7.864 MFLOP per bank row (TimeConv deduplicated per row)
-BYTES_LSTM_STEP = 4 * 512 * 4 + 4 * 512 * 4      # per clip and recurrent step: projected row 8 KB + c in/out + h in/out 4 x 2 KB
+# per clip and recurrent step: projected row (fp32) 8 KB + c in/out (fp32) 2 x 2 KB + h in/out (fp16) 2 x 1 KB
+BYTES_LSTM_STEP = 4 * 512 * 4 + 2 * 512 * 4 + 2 * 512 * 2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed
-# ncu --set full capture (profiles/r1_final_ncu.md): 516.5 MB read + 147.5 MB written at 41600 clips
-NCU_TRAFFIC_LSTM_STEP = (664.0e6, 41600)
+# ncu --set full capture (profiles/r1_f16_ncu.md): 471.2 MB read + 106.4 MB written at 41600 clips
+NCU_TRAFFIC_LSTM_STEP = (577.6e6, 41600)
 
 
 def peaks():
@@ -311,9 +312,9 @@ def run_ours(args):
             return {"achieved": kern[k]["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
                     "frac": kern[k]["tflops"] / pk["tensor"], "algorithmic_flop_per_unit": unit_flop,
                     "units_per_launch": units, "ms_per_launch": kern[k]["ms"]}
-        # The recurrent step moves 16 KB per clip for 2.1 MFLOP: against the measured peaks the HBM time (2.5 ns
-        # per clip) is the longer one (tensor: 1.25 ns at the bf16 figure, 2.5 ns at the TF32 rate), so the
-        # kernel is judged on the HBM roofline; its tensor-core rate is reported beside it.
+        # The recurrent step moves 14 KB per clip for 2.1 MFLOP: against the measured peaks the HBM time (2.2 ns
+        # per clip) is the longer one (tensor: 1.25 ns at the measured bf16/fp16 rate), so the kernel is judged
+        # on the HBM roofline; its tensor-core rate is reported beside it.
         step_gbs = BYTES_LSTM_STEP * ls["clips"] / ls["ms"] / 1e6
         roof = {"kernel": "umma_gemm_kernel<EPI_LSTM> (recurrent step h.Whh^T + LSTM cell epilogue; 9 launches per batch, "
                           "largest share of the step, see profiles/)",
@@ -325,7 +326,7 @@ def run_ours(args):
                 "how": "CUDA events: (10-step LSTM - 1-step LSTM) / 9 on one batch",
                 "tensor": {"achieved": ls["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ls["tflops"] / pk["tensor"],
                            "algorithmic_flop_per_clip": FLOP_LSTM_STEP,
-                           "note": "peak = measured bf16 burst; TF32 issues at half that rate (0.5 is the TF32 ceiling)"},
+                           "note": "peak = measured bf16 burst (fp16 operands issue at the same rate)"},
                 "tensor_kernels": {"bankconv": tens("bankconv", FLOP_BANKCONV_ROW, kern["bankconv"]["rows"]),
                                    "timeconv_per_clip": tens("timeconv_per_clip", FLOP_TIMECONV, kern["timeconv_per_clip"]["clips"])},
                 "hbm_kernels": {"gather": hbm("gather", BYTES_GATHER), "attention": hbm("attention", BYTES_RELATION)}}

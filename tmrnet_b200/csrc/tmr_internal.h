@@ -41,6 +41,9 @@ int umma_timeconv(const float* packed, const float* x, const half_t* x16, int B,
 int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, int seq, int t,
                    const half_t* h_prev, half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st,
                    const float* xp_base = nullptr, int64_t xp_rows = 0, int64_t xp_row0 = 0);
+int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* starts, int seq, int t,
+                      const half_t* h_prev, half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st,
+                      const float* xp_base, int64_t xp_rows, int64_t xp_row0);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,

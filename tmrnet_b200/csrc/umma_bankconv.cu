@@ -41,7 +41,8 @@ constexpr int BC_W_BYTES = BC_W7_BYTES + BC_W5_BYTES + BC_W3_BYTES;   // 30 KB =
 constexpr int BC_STAGE_BYTES = BC_A_BYTES + BC_W_BYTES;        // 46 KB
 constexpr int BC_EX_BYTES = 15 * BC_BM * 8 * 4;        // epilogue exchange: 15 taps x 128 rows x 8 channels
 constexpr int BC_SMEM_BYTES = BC_STAGES * BC_STAGE_BYTES + BC_EX_BYTES + 1024 + 512;
-constexpr int BC_THREADS = 192;
+constexpr int BC_EPI_WARPS = 8;            // two per TMEM lane quarter
+constexpr int BC_THREADS = 64 + 32 * BC_EPI_WARPS;
 constexpr int BC_TMEM_COLS = 512;          // 2 accumulator buffers of 256 columns (240 used)
 constexpr int BC_N = 15 * BC_NCH;          // 240
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 // TMEM column of tap t of conv K for channel ch of the tile: the weight rows are staged [channel][tap]
 // per conv (conv7 | conv5 | conv3), so a channel's taps are consecutive columns.
@@ -69,8 +70,9 @@ struct BankConvParams {
   int ablate;      // timing experiments (WRONG results), env TMR_BC_ABL: 1 = epilogue only hands the accumulator back, 2 = no global stores
 };
 
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 =
-// epilogue.  The MMAs compute UNSHIFTED products Q_{K,t}[r] = W_K[:,:,t+h] . bank[r] for the tile's 128
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
+// epilogue (two per TMEM lane quarter: one moves the conv7 taps to the exchange buffer, the other conv5 + conv3;
+// then each assembles the variants of 16 of the quarter's 32 rows).  The MMAs compute UNSHIFTED products Q_{K,t}[r] = W_K[:,:,t+h] . bank[r] for the tile's 128
 // rows: one activation tile per channel chunk feeds all 15 taps, whose weight rows (rank-3 TMA boxes
 // over [in-channel][tap][out-channel]) are stacked into ONE 240-row B operand — a single N = 240
 // tcgen05.mma per k-step instead of seven narrow ones (a narrow MMA costs ~100 cycles whatever its N).
@@ -100,7 +102,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
     for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], BC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, BC_TMEM_COLS);
@@ -156,6 +158,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     }
   } else {
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;                               // which of the quarter's two warps
     const int r = q * 32 + lane;                                    // phase 1: row inside the tile = TMEM lane
     // exchange layout: ex[tap][row][8 channels]; taps 0..6 = conv7 t=-3..3, 7..11 = conv5 t=-2..2, 12..14 =
     // conv3 t=-1..1.  The two 16-byte halves of a row swap places in rows with bit 2 set, so 128-bit accesses
@@ -163,33 +166,28 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     auto exh = [&](int tap, int row, int h) -> float4* {
       return reinterpret_cast<float4*>(ex + ((size_t)tap * BC_BM + row) * 8 + ((h ^ ((row >> 2) & 1)) << 2));
     };
-    // phase 2: a lane owns FOUR channels (half = lane & 1 of the 8-channel chunk) of rows 32q + lane/2 and
-    // 32q + lane/2 + 16, so every global load / store instruction covers whole 32-byte sectors (16 rows x
-    // 32 B) instead of 32 half-filled ones (row per thread).
+    // phase 2: a lane owns FOUR channels (half = lane & 1 of the 8-channel chunk) of row 32q + 16 part + lane/2,
+    // so every global load / store instruction covers whole 32-byte sectors (16 rows x 32 B) instead of 32
+    // half-filled ones (row per thread).
     const int half = lane & 1;
+    const int r2 = q * 32 + 16 * part + (lane >> 1);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int n0 = (int)(tile % N_TILES) * BC_NCH;
       const int64_t q0 = p.row_base + (tile / N_TILES) * BC_OUT - 3;
-      bool valid[2];
-      int64_t prow[2];
-      // exact bank values of the lane's rows and of the next ones (identity / pool branches): requested before
+      // exact bank values of the lane's row and of the next one (identity / pool branches): requested before
       // the accumulator is ready so their latency hides behind the main loop
-      float4 x0v[2][2], x1v[2][2];                                  // [pass][8-channel chunk]
+      const int64_t rho = q0 + r2;                                  // bank row
+      const int64_t prow = rho - p.row_base;
+      const bool valid = r2 >= 3 && r2 < 3 + BC_OUT && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
+      const bool has_next = valid && (rho + 1 < p.n_rows);
+      float4 x0v[2], x1v[2];                                        // [8-channel chunk]
 #pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        const int r2 = q * 32 + (lane >> 1) + 16 * ps;
-        const int64_t rho = q0 + r2;                                // bank row
-        prow[ps] = rho - p.row_base;
-        valid[ps] = r2 >= 3 && r2 < 3 + BC_OUT && prow[ps] >= 0 && prow[ps] < p.pb_rows && rho < p.n_rows;
-        const bool has_next = valid[ps] && (rho + 1 < p.n_rows);
-#pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-          const float* src = p.bank + rho * kD + n0 + 8 * c8 + 4 * half;
-          x0v[ps][c8] = (valid[ps] && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x1v[ps][c8] = (has_next && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int c8 = 0; c8 < 2; ++c8) {
+        const float* src = p.bank + rho * kD + n0 + 8 * c8 + 4 * half;
+        x0v[c8] = (valid && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1v[c8] = (has_next && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -207,39 +205,41 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           // run of 56 / 40 / 24 columns: a few wide tcgen05.ld instead of 24 narrow load + wait pairs, and
           // the row goes to the exchange buffer as two 128-bit stores per tap (8 channels).
           uint32_t v[32], w[32];
-          tmem_ld32(t_row + col7(cc), v);
-          tmem_ld32(t_row + col7(cc) + 32, w);           // 56 used; the rest belongs to the next channels / conv5
-          tmem_ld_wait();
+          if (part == 0) {
+            tmem_ld32(t_row + col7(cc), v);
+            tmem_ld32(t_row + col7(cc) + 32, w);           // 56 used; the rest belongs to the next channels / conv5
+            tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 7; ++t)
+            for (int t = 0; t < 7; ++t)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t e[4];
+              for (int h = 0; h < 2; ++h) {
+                uint32_t e[4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 7 + t; e[c] = idx < 32 ? v[idx] : w[idx - 32]; }
-              *reinterpret_cast<uint4*>(exh(t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
-            }
-          float f8[8];
-          tmem_ld32(t_row + col5(cc), v);
-          tmem_ld8(t_row + col5(cc) + 32, f8);
-          tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 7 + t; e[c] = idx < 32 ? v[idx] : w[idx - 32]; }
+                *reinterpret_cast<uint4*>(exh(t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
+              }
+          } else {
+            float f8[8];
+            tmem_ld32(t_row + col5(cc), v);
+            tmem_ld8(t_row + col5(cc) + 32, f8);
+            tmem_ld32(t_row + col3(cc), w);                // 24 used (columns up to 247 of the 256-column buffer)
+            tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < 5; ++t)
+            for (int t = 0; t < 5; ++t)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t e[4];
+              for (int h = 0; h < 2; ++h) {
+                uint32_t e[4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 5 + t; e[c] = idx < 32 ? v[idx] : __float_as_uint(f8[idx - 32]); }
-              *reinterpret_cast<uint4*>(exh(7 + t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
-            }
-          tmem_ld32(t_row + col3(cc), v);                // 24 used (columns up to 247 of the 256-column buffer)
-          tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 5 + t; e[c] = idx < 32 ? v[idx] : __float_as_uint(f8[idx - 32]); }
+                *reinterpret_cast<uint4*>(exh(7 + t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
+              }
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
+            for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-              *reinterpret_cast<uint4*>(exh(12 + t, r, h)) =
-                  make_uint4(v[(4 * h) * 3 + t], v[(4 * h + 1) * 3 + t], v[(4 * h + 2) * 3 + t], v[(4 * h + 3) * 3 + t]);
+              for (int h = 0; h < 2; ++h)
+                *reinterpret_cast<uint4*>(exh(12 + t, r, h)) =
+                    make_uint4(w[(4 * h) * 3 + t], w[(4 * h + 1) * 3 + t], w[(4 * h + 2) * 3 + t], w[(4 * h + 3) * 3 + t]);
+          }
         }
         if (cc + 8 >= BC_NCH) {                         // last TMEM read of this tile: hand the buffer back early
           tc_fence_before();
@@ -248,24 +248,18 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         }
         epi_barrier();
         if (p.raw) {            // Q_{K,t}[rho] = W_K[:,:,t+h] . x[rho] as computed: any window can be assembled from these
-#pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            if (!valid[ps]) continue;
-            const int r2 = q * 32 + (lane >> 1) + 16 * ps;
-            float* dst = p.q_out + prow[ps] * (15 * kD) + n0 + cc + 4 * half;
+          if (valid) {
+            float* dst = p.q_out + prow * (15 * kD) + n0 + cc + 4 * half;
 #pragma unroll
             for (int tap = 0; tap < 15; ++tap) *reinterpret_cast<float4*>(dst + tap * kD) = *exh(tap, r2, half);
           }
           epi_barrier();
           continue;
         }
-        const float4 bb3 = __ldg(reinterpret_cast<const float4*>(p.bias3 + n0 + cc + 4 * half));
-        const float4 bb5 = __ldg(reinterpret_cast<const float4*>(p.bias5 + n0 + cc + 4 * half));
-        const float4 bb7 = __ldg(reinterpret_cast<const float4*>(p.bias7 + n0 + cc + 4 * half));
-#pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-          if (!valid[ps]) continue;
-          const int r2 = q * 32 + (lane >> 1) + 16 * ps;
+        if (valid) {
+          const float4 bb3 = __ldg(reinterpret_cast<const float4*>(p.bias3 + n0 + cc + 4 * half));
+          const float4 bb5 = __ldg(reinterpret_cast<const float4*>(p.bias5 + n0 + cc + 4 * half));
+          const float4 bb7 = __ldg(reinterpret_cast<const float4*>(p.bias7 + n0 + cc + 4 * half));
           // P_{K,t}[rho] = Q_{K,t}[rho - t]: row r2 - t of the exchange buffer
           float P7[7][4], P5[5][4], P3[3][4];
 #pragma unroll
@@ -282,7 +276,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
             }
           }
           const float b3[4] = {bb3.x, bb3.y, bb3.z, bb3.w}, b5[4] = {bb5.x, bb5.y, bb5.z, bb5.w}, b7[4] = {bb7.x, bb7.y, bb7.z, bb7.w};
-          const float4 xa = x0v[ps][cc / 8], xb = x1v[ps][cc / 8];
+          const float4 xa = x0v[cc / 8], xb = x1v[cc / 8];
           const float x0[4] = {xa.x, xa.y, xa.z, xa.w}, x1[4] = {xb.x, xb.y, xb.z, xb.w};
           float out[7][4];
 #pragma unroll
@@ -305,7 +299,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
             out[6][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_2, full5), full3), idp);               // k = L-3
           }
           if (!(p.ablate & 2) || out[0][0] == 123.456f) {
-            float* dst = p.pb + prow[ps] * (7 * kD) + n0 + cc + 4 * half;
+            float* dst = p.pb + prow * (7 * kD) + n0 + cc + 4 * half;
 #pragma unroll
             for (int v = 0; v < 7; ++v)
               *reinterpret_cast<float4*>(dst + v * kD) = make_float4(out[v][0], out[v][1], out[v][2], out[v][3]);

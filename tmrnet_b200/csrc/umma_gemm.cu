@@ -51,24 +51,25 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 constexpr int BM = 128, BN = 256, BK = 64;           // BK fp16 = 128 bytes = one swizzle row
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 // Per-epilogue configuration.  The LSTM-cell epilogue, not the MMAs, bounds the recurrent step, so it gets
-// 16 epilogue warps (4 per SM sub-partition) and pays for their 32x32 fp32 smem tiles (TMEM transpose
-// staging, and the landing zone of each warp's own TMA loads of projected rows) with one pipeline stage;
-// the plain epilogue keeps 8 warps and 4 / 6 stages.
-template <int EPI> struct Cfg {
+// 16 epilogue warps (4 per SM sub-partition), each with XBUF 32x32 fp32 smem tiles: the landing zones of the
+// warp's own TMA loads of projected rows.  With fp16 operands a 32 KB stage covers K = 64, so the main loop
+// needs fewer stages than the epilogue needs prefetch depth: XBUF = 2 trades two stages for a second tile.
+// The plain epilogue keeps 8 warps (one 4 KB transpose tile each) and 4 / 6 stages.
+template <int EPI, int XBUF = 1> struct Cfg {
   static constexpr int STAGES = (EPI == EPI_LSTM) ? 3 : 4;
-  static constexpr int STAGES_2SM = (EPI == EPI_LSTM) ? 5 : 6;      // 32 KB stages in 2-SM mode
+  static constexpr int STAGES_2SM = (EPI == EPI_LSTM) ? (XBUF == 2 ? 3 : 5) : 6;      // 32 KB stages in 2-SM mode
   static constexpr int EPI_WARPS = (EPI == EPI_LSTM) ? 16 : 8;
   static constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
-  static constexpr int EPI_TILES = 1;                              // 32x32 fp32 smem tiles per epilogue warp
+  static constexpr int EPI_TILES = (EPI == EPI_LSTM) ? XBUF : 1;   // 32x32 fp32 smem tiles per epilogue warp
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_TILES * 4096;
   static constexpr int COLS_PER_WARP = 1024 / EPI_WARPS;         // 4 warps per TMEM lane quarter share 256 columns
 };
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
 constexpr int B_BYTES = BN * BK * 2;                 // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-template <int EPI, bool TWOSM = false> constexpr int smem_bytes() {
-  return (TWOSM ? Cfg<EPI>::STAGES_2SM * (A_BYTES + B_BYTES / 2) : Cfg<EPI>::STAGES * STAGE_BYTES) +
-         Cfg<EPI>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+template <int EPI, bool TWOSM = false, int XBUF = 1> constexpr int smem_bytes() {
+  return (TWOSM ? Cfg<EPI, XBUF>::STAGES_2SM * (A_BYTES + B_BYTES / 2) : Cfg<EPI, XBUF>::STAGES * STAGE_BYTES) +
+         Cfg<EPI, XBUF>::EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 constexpr int TMEM_COLS = 512;
 
@@ -88,35 +89,9 @@ struct GemmParams {
   const float* xp_base; int64_t xp_rows;   // host side only: what tma_x is built over
   int timeline;
   int stages;      // > 0: use only this many pipeline stages (experiments)
+  int ablate;      // timing experiments (WRONG results), env TMR_LSTM_ABL: 1 no c loads, 2 no c/h stores, 4 no projected rows, 8 no cell math, 16 epilogue only hands the accumulator back
 };
 
-// Gate non-linearities of the tensor-core path: MUFU ex2/rcp approximations (2 ulp / 1 ulp), four
-// instructions per sigmoid.  The precise expf/tanhf versions — and even __expf + __frcp_rn, whose
-// round-to-nearest reciprocal expands to ~10 instructions and a slow-path branch — made the gate math
-// of the LSTM epilogue the bottleneck of the whole recurrence (measured: 1007 us -> 694 us per
-// 8192-clip batch with the math stubbed out).
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_sigmoid(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
-__device__ __forceinline__ float fast_tanh(float v) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * v)), -1.f); }
-// LSTM cell with 7 MUFU operations instead of 10 (the epilogue is bound by the MIO queue that feeds the
-// MUFU and shared-memory pipes): sigmoid(i)*tanh(g) and f share ONE reciprocal of the product of their
-// denominators, o*tanh(c') another.  With a = e^-i, b = e^-f, d = e^-2g:
-//   sigmoid(i) tanh(g) = (1-d) / ((1+a)(1+d)),  sigmoid(f) = 1 / (1+b).
-// Exponent arguments are clamped to 2^40 so the three-term product stays finite (a gate at -27 is 0 in
-// fp32 anyway); for d = 2^40 the quotient (1-d)/(1+d) is exactly -1.
-__device__ __forceinline__ void lstm_cell_fast(float gi, float gf, float gg, float go, float c, float& cn, float& hn) {
-  const float a = ex2_approx(fminf(-1.4426950408889634f * gi, 40.f));
-  const float b = ex2_approx(fminf(-1.4426950408889634f * gf, 40.f));
-  const float d = ex2_approx(fminf(-2.8853900817779268f * gg, 40.f));
-  const float e = ex2_approx(fminf(-1.4426950408889634f * go, 40.f));
-  const float pa = 1.f + a, pb = 1.f + b, pd = 1.f + d;
-  const float pad = pa * pd;
-  const float r = rcp_approx(pad * pb);
-  cn = (pad * c + (1.f - d) * pb) * r;                     // f*c + i*g
-  const float f2 = ex2_approx(fminf(-2.8853900817779268f * cn, 40.f));
-  hn = (1.f - f2) * rcp_approx((1.f + e) * (1.f + f2));    // o * tanh(c')
-}
 __device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
   return (mr < p.M) ? (int)((p.starts ? p.starts[mr] : mr * p.seq) + p.t) : -1;
 }
@@ -130,27 +105,27 @@ __device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
 // leader CTA's thread issues the MMAs for both; both CTAs' TMA loads complete on the leader's full
 // barrier; tcgen05.commit multicasts stage releases and accumulator-ready signals to both CTAs; both
 // CTAs' epilogues report to the leader's accumulator-empty barrier.
-template <int EPI, int CL>
+template <int EPI, int CL, int XBUF = 1>
 __global__ void __launch_bounds__(Cfg<EPI>::NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_a2,
                  const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_x,
                  const GemmParams p) {
   constexpr bool TWOSM = (CL == 3);
   constexpr int CSIZE = (CL == 1) ? 1 : 2;                       // CTAs per cluster
-  constexpr int STAGES = TWOSM ? Cfg<EPI>::STAGES_2SM : Cfg<EPI>::STAGES;
+  constexpr int STAGES = TWOSM ? Cfg<EPI, XBUF>::STAGES_2SM : Cfg<EPI, XBUF>::STAGES;
   constexpr int STAGE_BYTES = TWOSM ? (A_BYTES + B_BYTES / 2) : (A_BYTES + B_BYTES);
   constexpr int EPI_WARPS = Cfg<EPI>::EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the __shared__ array (no integer round trip) keeps the shared address space, so the
   // epilogue staging compiles to STS/LDS instead of generic ST.E/LD.E
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + Cfg<EPI>::EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + Cfg<EPI, XBUF>::EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  uint64_t* xfull = bars + 2 * STAGES + 6;   // [EPI_WARPS]  EPI_LSTM: a warp's own projected-row tile has landed
+  uint64_t* xfull = bars + 2 * STAGES + 6;   // [EPI_WARPS][XBUF]  EPI_LSTM: a warp's own projected-row tile has landed
 
   const int NST = (p.stages > 0 && p.stages < STAGES) ? p.stages : STAGES;
   if (p.timeline && threadIdx.x == 0 && blockIdx.x < 148) g_timeline_cta[blockIdx.x * 4 + 0] = clock64();
@@ -171,7 +146,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // empty: CL=2 both consumers release a stage (2 arrivals); 2-SM: one multicast commit per CTA
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL == 2 ? 2 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TWOSM ? 2 * EPI_WARPS : EPI_WARPS); }
-    if (EPI == EPI_LSTM) { tma_prefetch_desc(&tma_x); for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&xfull[i], 1); }
+    if (EPI == EPI_LSTM) { tma_prefetch_desc(&tma_x); for (int i = 0; i < EPI_WARPS * XBUF; ++i) mbar_init(&xfull[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { if (TWOSM) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
@@ -254,184 +229,154 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    // TMEM hands every thread one accumulator ROW (lane = row), but a row-per-thread global access
-    // pattern touches 32 different cache lines per warp instruction and made the epilogue, not the
-    // MMAs, bound these kernels (measured: recurrent GEMM 48 us with, 30 us without epilogue I/O).
-    // So each 32x32 chunk goes TMEM -> registers -> a 4 KB XOR-swizzled smem tile (phase A), and all
-    // element-wise work + global I/O happens in a COALESCED layout (phase B): per instruction 8 lanes
-    // cover the 128 contiguous bytes of one row, 4 rows per warp instruction.
+    // ===================== epilogue warps =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     constexpr int WCOLS = Cfg<EPI>::COLS_PER_WARP;      // accumulator columns owned by this warp (128 or 64)
     const int colq = (warp - 2) >> 2;                   // which WCOLS-wide slice of the 256 columns
-    float* sbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * 1024;   // 32 rows x 32 floats
-    const int prow = lane >> 3;                         // phase B: row within a group of 4
-    const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
-    int it = 0;
-    // EPI_LSTM state: projected-row index of row (m_base + lane) for the next tile; whether the current
-    // chunk's projected rows are in flight by TMA; parity of this warp's mbarrier
-    int xrow_next = -1;
-    uint32_t xpar = 0;
-    bool x_pend = false;
-    uint64_t* my_xfull = xfull + (warp - 2);
-    // rows x0 .. x0+31 of the projected matrix, columns col .. col+31 -> this warp's tile (same
-    // SWIZZLE_128B layout as the TMEM staging: row = lane, 16-byte chunk j at j ^ (lane & 7))
-    auto issue_x = [&](int x0, int col) {
-      if (lane == 0) {
-        mbar_expect_tx(my_xfull, 4096);
-        tma_load_2d(sbuf, &tma_x, my_xfull, col, (int)(x0 - p.x_row0));
-      }
-    };
-    if (EPI == EPI_LSTM && item0 < num_items) {
-      xrow_next = lstm_xrow(p, ((item0 / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
-      const int x0 = __shfl_sync(0xffffffffu, xrow_next, 0);
-      if (p.x_tma && __all_sync(0xffffffffu, xrow_next == x0 + lane)) {
-        issue_x(x0, (int)(item0 % n_tiles) * BN + colq * Cfg<EPI>::COLS_PER_WARP);
-        x_pend = true;
-      }
-    }
-    for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int64_t m_base = ((item / n_tiles) * CSIZE + crank) * BM + q * 32;  // first row of this warp
-      const int n0 = (int)(item % n_tiles) * BN + colq * WCOLS;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + colq * WCOLS;
-
-      // phase A helper: this thread's row of the chunk -> swizzled smem (conflict-free 128-bit stores)
-      auto stage_rows = [&](const uint32_t (&r)[32]) {
+    if constexpr (EPI == EPI_LSTM) {
+      // LSTM cell on gate-interleaved columns.  TMEM hands every thread one accumulator ROW (lane = clip) and a
+      // 32-column chunk = the (i,f,g,o) gates of 8 hidden units, so the whole cell update of those units is
+      // thread-private: no transpose through shared memory.  What the thread needs beside the accumulator:
+      //  * its clip's projected row (bias folded), 128 contiguous bytes per chunk: when the warp's 32 clips read
+      //    32 CONSECUTIVE projected rows (every warp except those straddling a video boundary or the end of the
+      //    batch) the 32x32 tile arrives by the warp's OWN TMA load, XBUF chunks ahead, in a SWIZZLE_128B tile
+      //    the thread reads back with eight conflict-free 128-bit loads; otherwise eight LDG.128 of its own row;
+      //  * c of the 8 units: ONE 256-bit load (a whole 32-byte sector per thread), fetched a chunk ahead;
+      //  * c out: one 256-bit store; h out: 8 fp16 = one 128-bit store (fp32 / 256-bit for the last step).
+      // The epilogue, not the MMAs, bounds this kernel; its cost is latency (HBM round trips), so everything it
+      // reads is requested one chunk (c) or XBUF chunks (projected rows) before it is used.
+      constexpr int NCH = WCOLS / 32;                   // chunks per tile and warp (2)
+      float* sbuf0 = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * (XBUF * 1024);
+      uint64_t* my_xfull = xfull + (warp - 2) * XBUF;
+      uint32_t x_pend = 0, x_par = 0;                   // bit b: buffer b has a TMA load in flight / its barrier parity
+      auto issue_x = [&](int b, int x0, int col) {      // rows x0 .. x0+31, columns col .. col+31 -> tile b
+        if (lane == 0) {
+          mbar_expect_tx(my_xfull + b, 4096);
+          tma_load_2d(sbuf0 + b * 1024, &tma_x, my_xfull + b, col, (int)(x0 - p.x_row0));
+        }
+      };
+      auto tile_rows = [&](int64_t it_item) -> int64_t { return ((it_item / n_tiles) * CSIZE + crank) * BM + q * 32; };
+      // per-tile state of the NEXT tile, computed a tile ahead: projected-row index of this lane's clip
+      int xrow_next = -1;
+      float cpre[8];                                     // c of the next chunk (prefetched)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-      };
-      auto staged = [&](int i) -> float4 {     // phase B read: row 4i+prow, columns 4*pch..4*pch+3
-        const int row = 4 * i + prow;
-        return *reinterpret_cast<const float4*>(sbuf + row * 32 + ((pch ^ (row & 7)) << 2));
-      };
-
-      if (EPI == EPI_LSTM) {
-        // 32 gate columns = 8 hidden units x (i,f,g,o): in phase B a lane owns ONE unit of one row per
-        // step i.  This epilogue, not the MMAs, bounds the recurrent step (device timeline TMR_TIMELINE=1,
-        // scripts/timeline_lstm.py: ~14.5 k cycles per 128x256 tile against a ~10 k-cycle main loop when
-        // every lane fetched its projected rows with LDG).  Timing ablations: cell math and the TMEM load
-        // are free, the LSU traffic is not - projected-row loads cost 27 of 94 us per 18944-clip step, the
-        // c/h loads and stores another 30.  So when the warp's 32 clips read 32 CONSECUTIVE projected rows
-        // (every warp except those straddling a video boundary or the end of the batch) the rows arrive by
-        // TMA, one chunk ahead, in the warp's own swizzled tile, and phase A ADDS the accumulator onto them.
-        const bool full = m_base + 32 <= p.M;           // warp-uniform: only the last M tile has rows >= M
-        // projected-row index of row m_base + lane: ONE coalesced load per warp, fetched a tile ahead
+      for (int k = 0; k < 8; ++k) cpre[k] = 0.f;
+      if (item0 < num_items) {
+        const int64_t mb = tile_rows(item0);
+        xrow_next = lstm_xrow(p, mb + lane);
+        const int x0 = __shfl_sync(0xffffffffu, xrow_next, 0);
+        const int ncol = (int)(item0 % n_tiles) * BN + colq * WCOLS;
+        if (p.x_tma && __all_sync(0xffffffffu, xrow_next == x0 + lane)) {
+#pragma unroll
+          for (int b = 0; b < XBUF; ++b) { issue_x(b, x0, ncol + 32 * b); x_pend |= 1u << b; }
+        }
+        if (mb + lane < p.M && !(p.ablate & 1)) ldg256(p.c + (mb + lane) * kD + (ncol >> 2), cpre);
+      }
+      if (p.ablate & 4) x_pend = 0;
+      int it = 0;
+      for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int64_t m_base = tile_rows(item);
+        const int n0 = (int)(item % n_tiles) * BN + colq * WCOLS;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + colq * WCOLS;
+        const int64_t mrow = m_base + lane;
+        const bool rvalid = mrow < p.M;
         const int xrow = xrow_next;
-        const int64_t nitem = item + item_stride;
-        if (nitem < num_items) xrow_next = lstm_xrow(p, ((nitem / n_tiles) * CSIZE + crank) * BM + q * 32 + lane);
         const int x0 = __shfl_sync(0xffffffffu, xrow, 0);
         const bool contig = p.x_tma && __all_sync(0xffffffffu, xrow == x0 + lane);
-        // phase B: a lane owns FOUR consecutive hidden units (16 gate columns) of rows lane/2 and lane/2 + 16,
-        // so c / h move as 128-bit accesses, one full 32-byte sector per row and instruction (a quarter of
-        // the LSU instructions of a unit-per-lane mapping; timing ablation: the c/h traffic, not the cell
-        // math, is what this epilogue pays for)
-        const int half = lane & 1;
-        int xr[2];                                      // projected-row index of the lane's two rows (-1: row >= M)
-        xr[0] = __shfl_sync(0xffffffffu, xrow, lane >> 1);
-        xr[1] = __shfl_sync(0xffffffffu, xrow, (lane >> 1) + 16);
-        const float* xp0 = p.xp + n0 + 16 * half;
-        const int64_t c0 = (m_base + (lane >> 1)) * kD + (n0 >> 2) + 4 * half;   // + 16*kD for the second row, + cc/4 per chunk
+        // the next tile of this warp
+        const int64_t nitem = item + item_stride;
+        const bool has_next = nitem < num_items;
+        int64_t nm_base = 0; int nn0 = 0; int nx0 = 0; bool ncontig = false;
+        if (has_next) {
+          nm_base = tile_rows(nitem);
+          nn0 = (int)(nitem % n_tiles) * BN + colq * WCOLS;
+          xrow_next = lstm_xrow(p, nm_base + lane);
+          nx0 = __shfl_sync(0xffffffffu, xrow_next, 0);
+          ncontig = p.x_tma && __all_sync(0xffffffffu, xrow_next == nx0 + lane);
+        }
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 3] = clock64();
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
         if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 4] = clock64();
-        // FULL: straight-line code for the eight cells of a chunk, so their MUFU chains interleave.
-        // XSMEM: the chunk's projected rows are (being) written into this warp's tile by TMA.
-        // nx_ok: the FOLLOWING chunk's rows can come by TMA too (rows nx_x0.., columns nx_col..): issued as
-        // soon as this chunk's gates have left the tile, so the load flies during the cell math and stores.
-        auto chunk = [&](int cc, auto full_tag, auto xsmem_tag, bool nx_ok, int nx_x0, int nx_col) {
-          constexpr bool FULL = decltype(full_tag)::value;
-          constexpr bool XSMEM = decltype(xsmem_tag)::value;
-          float4 x4[XSMEM ? 1 : 8];
-          float4 c4[2];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {                   // issue the chunk's global loads first ...
-            c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!XSMEM) {
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int cc = 32 * ch;
+          const int b = (XBUF == 2) ? ch : 0;
+          float* sb = sbuf0 + b * 1024;
+          uint32_t r[32];
+          tmem_ld32(t_row + cc, r);
+          float cin[8];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) x4[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (FULL || xr[i] >= 0) {
-              if (!XSMEM) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  x4[4 * i + k] = __ldg(reinterpret_cast<const float4*>(xp0 + (int64_t)xr[i] * (4 * kD) + cc + 4 * k));
-              }
-              c4[i] = *reinterpret_cast<const float4*>(p.c + c0 + (int64_t)i * (16 * kD) + (cc >> 2));
-            }
+          for (int k = 0; k < 8; ++k) cin[k] = cpre[k];
+          // c of the chunk after this one
+          if (!(p.ablate & 1)) {
+            if (ch + 1 < NCH) { if (rvalid) ldg256(p.c + mrow * kD + ((n0 + cc + 32) >> 2), cpre); }
+            else if (has_next && nm_base + lane < p.M) ldg256(p.c + (nm_base + lane) * kD + (nn0 >> 2), cpre);
           }
-          {
-            uint32_t r[32];                               // ... then move the accumulator chunk through smem
-            tmem_ld32(t_row + cc, r);
-            tmem_ld_wait();
-            if (XSMEM) {                                  // gates = projected rows (TMA) + accumulator
-              mbar_wait(my_xfull, xpar);
-              xpar ^= 1u;
+          // the chunk whose projected rows go into tile b once this chunk has read it: XBUF chunks ahead
+          bool nx_ok; int nx_x0, nx_col;
+          if (XBUF == 1 && ch + 1 < NCH) { nx_ok = contig; nx_x0 = x0; nx_col = n0 + cc + 32; }
+          else { nx_ok = has_next && ncontig; nx_x0 = nx0; nx_col = nn0 + ((XBUF == 2) ? cc : 0); }
+          if (p.ablate & 4) nx_ok = false;
+          float4 g[8];                                    // (i,f,g,o) of the chunk's 8 units, projected row first
+          if (x_pend & (1u << b)) {
+            mbar_wait(my_xfull + b, (x_par >> b) & 1u);
+            x_par ^= 1u << b;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4* a4 = reinterpret_cast<float4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2));
-                float4 v = *a4;
-                v.x += __uint_as_float(r[4 * j]); v.y += __uint_as_float(r[4 * j + 1]);
-                v.z += __uint_as_float(r[4 * j + 2]); v.w += __uint_as_float(r[4 * j + 3]);
-                *a4 = v;
-              }
+            for (int j = 0; j < 8; ++j) g[j] = *reinterpret_cast<const float4*>(sb + lane * 32 + ((j ^ (lane & 7)) << 2));
+            fence_proxy_async_smem();                     // the tile's generic reads before its next TMA write
+          } else {
+            const float* xr = p.xp + (int64_t)(rvalid ? xrow : 0) * (4 * kD) + n0 + cc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              g[j] = (rvalid && !(p.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          __syncwarp();
+          if (nx_ok) { issue_x(b, nx_x0, nx_col); x_pend |= 1u << b; } else { x_pend &= ~(1u << b); }
+          tmem_ld_wait_dep(r);
+          if (ch + 1 == NCH) {                            // last TMEM read of this tile: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (TWOSM) mbar_arrive_remote(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
+          }
+          if (rvalid && !(p.ablate & 16)) {
+            float cn[8], hn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (p.ablate & 8) { cn[j] = g[j].x + __uint_as_float(r[4 * j]) + g[j].y + __uint_as_float(r[4 * j + 1]); hn[j] = g[j].z + __uint_as_float(r[4 * j + 2]) + g[j].w + __uint_as_float(r[4 * j + 3]) + cin[j]; }
+              else lstm_cell_fast(g[j].x + __uint_as_float(r[4 * j]), g[j].y + __uint_as_float(r[4 * j + 1]),
+                             g[j].z + __uint_as_float(r[4 * j + 2]), g[j].w + __uint_as_float(r[4 * j + 3]), cin[j], cn[j], hn[j]);
+            const int64_t o = mrow * kD + ((n0 + cc) >> 2);
+            if ((p.ablate & 2) && cn[0] != 123.456f) continue;
+            stg256(p.c + o, cn);
+            // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
+            if (p.h_out16) {
+              const uint2 lo = pack_h4(hn[0], hn[1], hn[2], hn[3]), hi = pack_h4(hn[4], hn[5], hn[6], hn[7]);
+              *reinterpret_cast<uint4*>(p.h_out16 + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
             } else {
-              stage_rows(r);
+              stg256(p.h_out + o, hn);
             }
           }
-          __syncwarp();
-          float4 g[8];                                    // the lane's 2 rows x 4 units x (i,f,g,o)
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int row = (lane >> 1) + 16 * i;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                 // unit 4*half + k of the chunk = 16-byte chunk 4*half + k of the row
-              float4 v = *reinterpret_cast<const float4*>(sbuf + row * 32 + (((4 * half + k) ^ (row & 7)) << 2));
-              if (!XSMEM) { v.x += x4[4 * i + k].x; v.y += x4[4 * i + k].y; v.z += x4[4 * i + k].z; v.w += x4[4 * i + k].w; }
-              g[4 * i + k] = v;
-            }
-          }
-          fence_proxy_async_smem();                       // the tile's generic accesses before its next TMA write
-          __syncwarp();
-          if (nx_ok) issue_x(nx_x0, nx_col);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (FULL || xr[i] >= 0) {
-              const float cin[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
-              float cn[4], hn[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 v = g[4 * i + k];
-                lstm_cell_fast(v.x, v.y, v.z, v.w, cin[k], cn[k], hn[k]);
-              }
-              const int64_t o = c0 + (int64_t)i * (16 * kD) + (cc >> 2);
-              *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-              // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
-              if (p.h_out16) *reinterpret_cast<uint2*>(p.h_out16 + o) = pack_h4(hn[0], hn[1], hn[2], hn[3]);
-              else *reinterpret_cast<float4*>(p.h_out + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            }
-          }
-        };
-#pragma unroll 1
-        for (int cc = 0; cc < WCOLS; cc += 32) {
-          bool nx_ok = false;
-          int nx_x0 = 0, nx_col = 0;
-          if (cc + 32 < WCOLS) {
-            nx_ok = contig; nx_x0 = x0; nx_col = n0 + cc + 32;
-          } else if (nitem < num_items) {
-            nx_x0 = __shfl_sync(0xffffffffu, xrow_next, 0);
-            nx_ok = p.x_tma && __all_sync(0xffffffffu, xrow_next == nx_x0 + lane);
-            nx_col = (int)(nitem % n_tiles) * BN + colq * WCOLS;
-          }
-          if (x_pend) chunk(cc, std::true_type{}, std::true_type{}, nx_ok, nx_x0, nx_col);
-          else if (full) chunk(cc, std::true_type{}, std::false_type{}, nx_ok, nx_x0, nx_col);
-          else chunk(cc, std::false_type{}, std::false_type{}, nx_ok, nx_x0, nx_col);
-          x_pend = nx_ok;
         }
-      } else {
+        if (p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 5] = clock64();
+      }
+    } else {
+      // Plain epilogue.  A row-per-thread global access pattern touches 32 different cache lines per warp
+      // instruction, so each 32x32 chunk goes TMEM -> registers -> a 4 KB XOR-swizzled smem tile (phase A) and
+      // the bias / residual / relu + global I/O happen in a COALESCED layout (phase B): per instruction 8 lanes
+      // cover the 128 contiguous bytes of one row, 4 rows per warp instruction.
+      float* sbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * 1024;   // 32 rows x 32 floats
+      const int prow = lane >> 3;                         // phase B: row within a group of 4
+      const int pch = lane & 7;                           // phase B: 16-byte chunk (4 columns) of the row
+      int it = 0;
+      for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const int64_t m_base = ((item / n_tiles) * CSIZE + crank) * BM + q * 32;  // first row of this warp
+        const int n0 = (int)(item % n_tiles) * BN + colq * WCOLS;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + colq * WCOLS;
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -440,7 +385,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tmem_ld32(t_row + cc, r);
           tmem_ld_wait();
           __syncwarp();
-          stage_rows(r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)                     // phase A: this thread's row -> swizzled smem (conflict-free)
+            *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
           const int n = n0 + cc + 4 * pch;
           if (n < p.N) {                                  // N % 4 == 0
@@ -448,9 +395,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int64_t mr = m_base + 4 * i + prow;
+              const int row = 4 * i + prow;
+              const int64_t mr = m_base + row;
               if (mr < p.M) {
-                float4 v = staged(i);
+                float4 v = *reinterpret_cast<const float4*>(sbuf + row * 32 + ((pch ^ (row & 7)) << 2));
                 v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                 if (p.residual) {
                   const float4 e = __ldg(reinterpret_cast<const float4*>(p.residual + mr * p.ldr + n));
@@ -462,11 +410,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (TWOSM) mbar_arrive_remote(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (EPI == EPI_LSTM && p.timeline && it < 16 && warp == 2 && lane == 0) g_timeline[((int64_t)blockIdx.x * 16 + it) * 6 + 5] = clock64();
-      if (lane == 0) { if (TWOSM) mbar_arrive_remote(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
     }
   }
 
@@ -524,6 +471,8 @@ static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t l
   const_cast<GemmParams&>(p).timeline = tlflag;
   static const int lstm_stages = [] { const char* e = getenv("TMR_LSTM_STAGES"); return e ? atoi(e) : 0; }();
   const_cast<GemmParams&>(p).stages = (EPI == EPI_LSTM) ? lstm_stages : 0;
+  static const int lstm_abl = [] { const char* e = getenv("TMR_LSTM_ABL"); return e ? atoi(e) : 0; }();
+  const_cast<GemmParams&>(p).ablate = (EPI == EPI_LSTM) ? lstm_abl : 0;
   static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
@@ -537,7 +486,12 @@ static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t l
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cluster == 3) {
+    static const int xbuf = [] { const char* e = getenv("TMR_LSTM_XBUF"); return e ? atoi(e) : 1; }();
+    if (cluster == 3 && EPI == EPI_LSTM && xbuf == 2) {
+      cfg.dynamicSmemBytes = smem_bytes<EPI_LSTM, true, 2>();
+      TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_LSTM, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_LSTM, true, 2>()));
+      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI_LSTM, 3, 2>, ta, ta2, tb, tx, p));
+    } else if (cluster == 3) {
       cfg.dynamicSmemBytes = smem_bytes<EPI, true>();
       TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI, true>()));
       TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 3>, ta, ta2, tb, tx, p));
@@ -598,6 +552,11 @@ int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, 
                    half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st, const float* xp_base,
                    int64_t xp_rows, int64_t xp_row0) {
   if (B == 0) return TMR_OK;
+  // batches of at least one 256-clip tile: the weights-stationary kernel (umma_lstm_ws.cu); TMR_LSTM_WS=0 keeps
+  // the streamed GEMM engine below, which also serves small batches
+  static const int ws = [] { const char* e = getenv("TMR_LSTM_WS"); return e ? atoi(e) : 1; }();
+  if (ws && B >= 256)
+    return umma_lstm_step_ws(whh16, xp, starts, seq, t, h_prev, h_out16, h_out, c, B, st, xp_base, xp_rows, xp_row0);
   umma::GemmParams p{};
   p.xp_base = xp_base; p.xp_rows = xp_rows; p.x_row0 = xp_row0;
   p.M = B; p.N = 4 * kD; p.K = kD; p.k_split = kD;
