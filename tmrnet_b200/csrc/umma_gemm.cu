@@ -18,7 +18,7 @@ namespace tmr {
 namespace umma {
 
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes) {
+              const uint32_t* box, int elem_bytes, int swizzle_bytes) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -39,7 +39,8 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   const CUtensorMapDataType dt = (elem_bytes == 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = encode(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(TMR_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu,%llu box %u,%u,%u)",
@@ -89,7 +90,6 @@ struct GemmParams {
   const float* xp_base; int64_t xp_rows;   // host side only: what tma_x is built over
   int timeline;
   int stages;      // > 0: use only this many pipeline stages (experiments)
-  int ablate;      // timing experiments (WRONG results), env TMR_LSTM_ABL: 1 no c loads, 2 no c/h stores, 4 no projected rows, 8 no cell math, 16 epilogue only hands the accumulator back
 };
 
 __device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
@@ -101,7 +101,7 @@ __device__ __forceinline__ int lstm_xrow(const GemmParams& p, int64_t mr) {
 // BOTH consumers have released it: every tcgen05.commit on a stage arrives on both CTAs' empty barrier.
 // CL = 3: CTA PAIRS with 2-SM MMA (tcgen05 cta_group::2): the pair computes a 256 x 256 tile, each CTA
 // stages only its own 128 rows of A and its own 128 rows (N half) of W — 32 KB instead of 48 KB per
-// k-block through the SM's ~55 B/cycle ingest, which is what bounds these fp32-operand GEMMs.  The
+// k-block through the SM's ~55 B/cycle ingest.  The
 // leader CTA's thread issues the MMAs for both; both CTAs' TMA loads complete on the leader's full
 // barrier; tcgen05.commit multicasts stage releases and accumulator-ready signals to both CTAs; both
 // CTAs' epilogues report to the leader's accumulator-empty barrier.
@@ -270,9 +270,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int b = 0; b < XBUF; ++b) { issue_x(b, x0, ncol + 32 * b); x_pend |= 1u << b; }
         }
-        if (mb + lane < p.M && !(p.ablate & 1)) ldg256(p.c + (mb + lane) * kD + (ncol >> 2), cpre);
+        if (mb + lane < p.M) ldg256(p.c + (mb + lane) * kD + (ncol >> 2), cpre);
       }
-      if (p.ablate & 4) x_pend = 0;
       int it = 0;
       for (int64_t item = item0; item < num_items; item += item_stride, ++it) {
         const int acc = it & 1;
@@ -311,15 +310,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 8; ++k) cin[k] = cpre[k];
           // c of the chunk after this one
-          if (!(p.ablate & 1)) {
-            if (ch + 1 < NCH) { if (rvalid) ldg256(p.c + mrow * kD + ((n0 + cc + 32) >> 2), cpre); }
-            else if (has_next && nm_base + lane < p.M) ldg256(p.c + (nm_base + lane) * kD + (nn0 >> 2), cpre);
-          }
+          if (ch + 1 < NCH) { if (rvalid) ldg256(p.c + mrow * kD + ((n0 + cc + 32) >> 2), cpre); }
+          else if (has_next && nm_base + lane < p.M) ldg256(p.c + (nm_base + lane) * kD + (nn0 >> 2), cpre);
           // the chunk whose projected rows go into tile b once this chunk has read it: XBUF chunks ahead
           bool nx_ok; int nx_x0, nx_col;
           if (XBUF == 1 && ch + 1 < NCH) { nx_ok = contig; nx_x0 = x0; nx_col = n0 + cc + 32; }
           else { nx_ok = has_next && ncontig; nx_x0 = nx0; nx_col = nn0 + ((XBUF == 2) ? cc : 0); }
-          if (p.ablate & 4) nx_ok = false;
           float4 g[8];                                    // (i,f,g,o) of the chunk's 8 units, projected row first
           if (x_pend & (1u << b)) {
             mbar_wait(my_xfull + b, (x_par >> b) & 1u);
@@ -331,7 +327,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const float* xr = p.xp + (int64_t)(rvalid ? xrow : 0) * (4 * kD) + n0 + cc;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              g[j] = (rvalid && !(p.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              g[j] = rvalid ? __ldg(reinterpret_cast<const float4*>(xr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp();
           if (nx_ok) { issue_x(b, nx_x0, nx_col); x_pend |= 1u << b; } else { x_pend &= ~(1u << b); }
@@ -341,15 +337,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             __syncwarp();
             if (lane == 0) { if (TWOSM) mbar_arrive_remote(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
           }
-          if (rvalid && !(p.ablate & 16)) {
+          if (rvalid) {
             float cn[8], hn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (p.ablate & 8) { cn[j] = g[j].x + __uint_as_float(r[4 * j]) + g[j].y + __uint_as_float(r[4 * j + 1]); hn[j] = g[j].z + __uint_as_float(r[4 * j + 2]) + g[j].w + __uint_as_float(r[4 * j + 3]) + cin[j]; }
-              else lstm_cell_fast(g[j].x + __uint_as_float(r[4 * j]), g[j].y + __uint_as_float(r[4 * j + 1]),
+              lstm_cell_fast(g[j].x + __uint_as_float(r[4 * j]), g[j].y + __uint_as_float(r[4 * j + 1]),
                              g[j].z + __uint_as_float(r[4 * j + 2]), g[j].w + __uint_as_float(r[4 * j + 3]), cin[j], cn[j], hn[j]);
             const int64_t o = mrow * kD + ((n0 + cc) >> 2);
-            if ((p.ablate & 2) && cn[0] != 123.456f) continue;
             stg256(p.c + o, cn);
             // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
             if (p.h_out16) {
@@ -471,8 +465,6 @@ static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t l
   const_cast<GemmParams&>(p).timeline = tlflag;
   static const int lstm_stages = [] { const char* e = getenv("TMR_LSTM_STAGES"); return e ? atoi(e) : 0; }();
   const_cast<GemmParams&>(p).stages = (EPI == EPI_LSTM) ? lstm_stages : 0;
-  static const int lstm_abl = [] { const char* e = getenv("TMR_LSTM_ABL"); return e ? atoi(e) : 0; }();
-  const_cast<GemmParams&>(p).ablate = (EPI == EPI_LSTM) ? lstm_abl : 0;
   static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
@@ -486,12 +478,7 @@ static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t l
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    static const int xbuf = [] { const char* e = getenv("TMR_LSTM_XBUF"); return e ? atoi(e) : 1; }();
-    if (cluster == 3 && EPI == EPI_LSTM && xbuf == 2) {
-      cfg.dynamicSmemBytes = smem_bytes<EPI_LSTM, true, 2>();
-      TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI_LSTM, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI_LSTM, true, 2>()));
-      TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI_LSTM, 3, 2>, ta, ta2, tb, tx, p));
-    } else if (cluster == 3) {
+    if (cluster == 3) {
       cfg.dynamicSmemBytes = smem_bytes<EPI, true>();
       TMR_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<EPI, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<EPI, true>()));
       TMR_CUDA(cudaLaunchKernelEx(&cfg, umma_gemm_kernel<EPI, 3>, ta, ta2, tb, tx, p));

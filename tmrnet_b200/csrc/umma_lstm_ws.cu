@@ -11,8 +11,8 @@
 // grouped by slice (pair p -> slice p mod 8) and walk the clip tiles round-robin inside their group, so the
 // eight pairs that need the same h rows ask for them at about the same time (L2 hits).
 //
-// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two per TMEM lane quarter, 128 gate
-// columns each, in four 32-column chunks).  Epilogue as in umma_gemm.cu's EPI_LSTM: TMEM lane = clip, a chunk
+// Warps: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2.. = epilogue (four per TMEM lane quarter, 64 gate
+// columns each, in two 32-column chunks; or two per quarter with 128 columns).  Epilogue as in umma_gemm.cu's EPI_LSTM: TMEM lane = clip, a chunk
 // = (i,f,g,o) of 8 hidden units, thread-private cell update; projected rows by the warp's own TMA load one
 // chunk ahead; c by one 256-bit load one chunk ahead; c / h by 256 / 128-bit stores.
 #include <stdlib.h>
@@ -27,14 +27,12 @@ constexpr int WS_BM = 128;                    // rows per CTA (256 per pair)
 constexpr int WS_BN = 256;                    // gate columns per pair; each CTA holds 128 of the weight rows
 constexpr int WS_BK = 64;                     // fp16 per 128-byte swizzle row
 constexpr int WS_KB = kD / WS_BK;             // 8 k-blocks
-constexpr int WS_NA = 4;                      // stages of h rows
 constexpr int WS_A_BYTES = WS_BM * WS_BK * 2; // 16 KB
 constexpr int WS_B_BYTES = (WS_BN / 2) * WS_BK * 2;   // 16 KB per k-block per CTA
-constexpr int WS_EPI_WARPS = 8;
-constexpr int WS_THREADS = 64 + 32 * WS_EPI_WARPS;
-constexpr int WS_WCOLS = WS_BN * 4 / WS_EPI_WARPS;    // 128 columns per epilogue warp
-constexpr int WS_NCH = WS_WCOLS / 32;                  // 4 chunks
-constexpr int WS_SMEM_BYTES = WS_KB * WS_B_BYTES + WS_NA * WS_A_BYTES + WS_EPI_WARPS * 4096 + 1024 + 512;
+// Shared memory holds the resident weights (128 KB) plus 96 KB of landing zones to split between stages of h
+// rows (16 KB each) and the epilogue warps' projected-row tiles (4 KB each): EW epilogue warps, NA stages.
+// A tile holds 32 clips x CW gate columns (CW = 32: 4 KB, CW = 16: 2 KB).
+template <int EW, int NA, int CW> constexpr int ws_smem_bytes() { return WS_KB * WS_B_BYTES + NA * WS_A_BYTES + EW * 128 * CW + 1024 + 512; }
 constexpr int WS_N_SLICES = 4 * kD / WS_BN;   // 8
 
 struct LstmWsParams {
@@ -50,15 +48,19 @@ __device__ __forceinline__ int ws_xrow(const LstmWsParams& p, int64_t mr) {
   return (mr < p.M) ? (int)((p.starts ? p.starts[mr] : mr * p.seq) + p.t) : -1;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WS_THREADS, 1)
+template <int WS_EPI_WARPS, int WS_NA, int CW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * WS_EPI_WARPS, 1)
 umma_lstm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_x, const LstmWsParams p) {
+  constexpr int WS_WCOLS = WS_BN * 4 / WS_EPI_WARPS;    // gate columns per epilogue warp (128 or 64)
+  constexpr int WS_NCH = WS_WCOLS / CW;                 // chunks per warp and tile
+  constexpr int TILE_FLOATS = 32 * CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                   // [WS_KB][128 weight rows][64 fp16], resident
   uint8_t* sA = sB + WS_KB * WS_B_BYTES;                // [WS_NA][128 clips][64 fp16]
-  float* sX = reinterpret_cast<float*>(sA + WS_NA * WS_A_BYTES);   // [8 warps][32 x 32 fp32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + WS_EPI_WARPS * 4096);
+  float* sX = reinterpret_cast<float*>(sA + WS_NA * WS_A_BYTES);   // [epilogue warps][32 clips x CW fp32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + WS_EPI_WARPS * TILE_FLOATS * 4);
   uint64_t* a_full = bars;                    // [WS_NA]  TMA -> MMA (leader's barrier collects both CTAs' bytes)
   uint64_t* a_empty = bars + WS_NA;           // [WS_NA]  MMA -> TMA (multicast commit)
   uint64_t* b_full = bars + 2 * WS_NA;        // [1]
@@ -138,14 +140,14 @@ umma_lstm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
-    const int colq = (warp - 2) >> 2;                   // which 128-column half of the slice
-    float* sb = sX + (warp - 2) * 1024;
+    const int colq = (warp - 2) >> 2;                   // which WS_WCOLS-wide part of the slice
+    float* sb = sX + (warp - 2) * TILE_FLOATS;
     uint64_t* my_xfull = xfull + (warp - 2);
     bool x_pend = false;
     uint32_t x_par = 0;
-    auto issue_x = [&](int x0, int col) {               // rows x0 .. x0+31, columns col .. col+31 -> my tile
+    auto issue_x = [&](int x0, int col) {               // rows x0 .. x0+31, columns col .. col+CW-1 -> my tile
       if (lane == 0) {
-        mbar_expect_tx(my_xfull, 4096);
+        mbar_expect_tx(my_xfull, TILE_FLOATS * 4);
         tma_load_2d(sb, &tma_x, my_xfull, col, (int)(x0 - p.x_row0));
       }
     };
@@ -182,57 +184,73 @@ umma_lstm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < WS_NCH; ++ch) {
-        const int cc = 32 * ch;
-        const bool last = ch + 1 == WS_NCH;
-        uint32_t r[32];
-        tmem_ld32(t_row + cc, r);
-        float cin[8];
+      float cin[8], cn[8], hn[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cin[k] = cpre[k];
-        // c of the chunk after this one
-        if (!last) { if (rvalid) ldg256(p.c + mrow * kD + ((ncol0 + cc + 32) >> 2), cpre); }
-        else if (has_next && nmrow < p.M) ldg256(p.c + nmrow * kD + (ncol0 >> 2), cpre);
+      for (int ch = 0; ch < WS_NCH; ++ch) {
+        constexpr int U = CW / 4;                       // hidden units per chunk (8 or 4)
+        constexpr int CPG = 32 / CW;                    // chunks per 8-unit group: c / h move once per group
+        const int cc = CW * ch;
+        const int sub = ch % CPG;                       // position inside the group
+        const bool last = ch + 1 == WS_NCH;
+        uint32_t r[CW];
+        if constexpr (CW == 32) tmem_ld32(t_row + cc, r); else tmem_ld16(t_row + cc, r);
+        if (sub == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cin[k] = cpre[k];
+          // c of the group after this one
+          if (ch + CPG < WS_NCH) { if (rvalid) ldg256(p.c + mrow * kD + ((ncol0 + cc + 32) >> 2), cpre); }
+          else if (has_next && nmrow < p.M) ldg256(p.c + nmrow * kD + (ncol0 >> 2), cpre);
+        }
         const bool nx_ok = last ? (has_next && ncontig) : contig;
         const int nx_x0 = last ? nx0 : x0;
-        const int nx_col = last ? ncol0 : ncol0 + cc + 32;
-        float4 g[8];                                    // (i,f,g,o) of the chunk's 8 units, projected row first
+        const int nx_col = last ? ncol0 : ncol0 + cc + CW;
+        // gates = accumulator + projected row, summed in place in the accumulator registers
+        if constexpr (CW == 32) tmem_ld_wait_dep(r); else tmem_ld_wait_dep16(r);
+        float* gsum = reinterpret_cast<float*>(r);
         if (x_pend) {
           mbar_wait(my_xfull, x_par);
           x_par ^= 1u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = *reinterpret_cast<const float4*>(sb + lane * 32 + ((j ^ (lane & 7)) << 2));
+          for (int j = 0; j < U; ++j) {
+            // 32-column tiles: 128-byte rows, SWIZZLE_128B (16-byte chunk ^= row & 7); 16-column tiles: 64-byte
+            // rows, SWIZZLE_64B (chunk ^= (row >> 1) & 3).  Either way the 8 lanes of a quarter warp hit 8
+            // different 16-byte bank groups.
+            const float4 v = (CW == 32)
+                ? *reinterpret_cast<const float4*>(sb + lane * 32 + ((j ^ (lane & 7)) << 2))
+                : *reinterpret_cast<const float4*>(sb + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2));
+            gsum[4 * j] += v.x; gsum[4 * j + 1] += v.y; gsum[4 * j + 2] += v.z; gsum[4 * j + 3] += v.w;
+          }
           fence_proxy_async_smem();                     // the tile's generic reads before its next TMA write
-        } else {
-          const float* xr = p.xp + (int64_t)(rvalid ? xrow : 0) * (4 * kD) + ncol0 + cc;
+        } else if (rvalid) {
+          const float* xr = p.xp + (int64_t)xrow * (4 * kD) + ncol0 + cc;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            g[j] = rvalid ? __ldg(reinterpret_cast<const float4*>(xr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < U; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + j);
+            gsum[4 * j] += v.x; gsum[4 * j + 1] += v.y; gsum[4 * j + 2] += v.z; gsum[4 * j + 3] += v.w;
+          }
         }
         __syncwarp();
         if (nx_ok) issue_x(nx_x0, nx_col);
         x_pend = nx_ok;
-        tmem_ld_wait_dep(r);
         if (last) {                                     // last TMEM read of this tile: hand the accumulator back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
         }
         if (rvalid) {
-          float cn[8], hn[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            lstm_cell_fast(g[j].x + __uint_as_float(r[4 * j]), g[j].y + __uint_as_float(r[4 * j + 1]),
-                           g[j].z + __uint_as_float(r[4 * j + 2]), g[j].w + __uint_as_float(r[4 * j + 3]), cin[j], cn[j], hn[j]);
-          const int64_t o = mrow * kD + ((ncol0 + cc) >> 2);
-          stg256(p.c + o, cn);
-          // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
-          if (p.h_out16) {
-            const uint2 lo = pack_h4(hn[0], hn[1], hn[2], hn[3]), hi = pack_h4(hn[4], hn[5], hn[6], hn[7]);
-            *reinterpret_cast<uint4*>(p.h_out16 + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-          } else {
-            stg256(p.h_out + o, hn);
+          for (int j = 0; j < U; ++j)
+            lstm_cell_fast(gsum[4 * j], gsum[4 * j + 1], gsum[4 * j + 2], gsum[4 * j + 3], cin[U * sub + j], cn[U * sub + j], hn[U * sub + j]);
+          if (sub == CPG - 1) {
+            const int64_t o = mrow * kD + ((ncol0 + cc + CW - 32) >> 2);
+            stg256(p.c + o, cn);
+            // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
+            if (p.h_out16) {
+              const uint2 lo = pack_h4(hn[0], hn[1], hn[2], hn[3]), hi = pack_h4(hn[4], hn[5], hn[6], hn[7]);
+              *reinterpret_cast<uint4*>(p.h_out16 + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              stg256(p.h_out + o, hn);
+            }
           }
         }
       }
@@ -263,6 +281,7 @@ int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* start
   if (pps < 1) pps = 1;
   if ((int64_t)pps > p.m_pairs) pps = (int)p.m_pairs;
   p.pairs_per_slice = pps;
+  static const int cfg = [] { const char* e = getenv("TMR_LSTM_WS_CFG"); return e ? atoi(e) : 8; }();
   CUtensorMap ta, tb, tx;
   {
     uint64_t da[2] = {(uint64_t)kD, (uint64_t)B};
@@ -274,16 +293,21 @@ int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* start
     TMR_TRY(make_tmap(&tb, whh16, 2, dw, sa, bw, 2));
     tx = ta;
     p.x_tma = 0;
-    if (xp_base && xp_rows > 0) {                        // projected rows [xp_rows][4D], 32 x 32 fp32 boxes per epilogue warp
+    if (xp_base && xp_rows > 0) {                        // projected rows [xp_rows][4D], 32-clip x CW-column fp32 boxes per epilogue warp
       uint64_t dx[2] = {(uint64_t)4 * kD, (uint64_t)xp_rows};
       uint64_t sx[1] = {(uint64_t)4 * kD * 4};
-      uint32_t bx[2] = {32, 32};
-      TMR_TRY(make_tmap(&tx, xp_base, 2, dx, sx, bx, 4));
+      uint32_t bx[2] = {(uint32_t)(cfg == 8 ? 32 : 16), 32};
+      TMR_TRY(make_tmap(&tx, xp_base, 2, dx, sx, bx, 4, cfg == 8 ? 128 : 64));
       p.x_tma = 1;
     }
   }
-  TMR_CUDA(cudaFuncSetAttribute(umma_lstm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
-  umma_lstm_ws_kernel<<<2 * WS_N_SLICES * pps, WS_THREADS, WS_SMEM_BYTES, st>>>(ta, tb, tx, p);
+  if (cfg == 8) {          // 8 epilogue warps x 128 columns, 32-column chunks
+    TMR_CUDA(cudaFuncSetAttribute(umma_lstm_ws_kernel<8, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem_bytes<8, 4, 32>()));
+    umma_lstm_ws_kernel<8, 4, 32><<<2 * WS_N_SLICES * pps, 64 + 32 * 8, ws_smem_bytes<8, 4, 32>(), st>>>(ta, tb, tx, p);
+  } else {                 // 16 epilogue warps x 64 columns, 16-column chunks (2 KB tiles leave room for 4 stages)
+    TMR_CUDA(cudaFuncSetAttribute(umma_lstm_ws_kernel<16, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem_bytes<16, 4, 16>()));
+    umma_lstm_ws_kernel<16, 4, 16><<<2 * WS_N_SLICES * pps, 64 + 32 * 16, ws_smem_bytes<16, 4, 16>(), st>>>(ta, tb, tx, p);
+  }
   TMR_LAUNCH_CHECK("umma_lstm_ws_kernel");
   return TMR_OK;
 }
