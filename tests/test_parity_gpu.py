@@ -14,6 +14,8 @@ import tmr_oracle as orc
 import tmrnet_b200 as tb
 from tmrnet_b200 import ops, synth
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 MODES = ["fp32", "f16"]
@@ -250,6 +252,74 @@ def test_lstm_sweep_and_frame_dedup(mode, B, seq):
     assert rel_err(got_f, ref) < TOL[mode]
     if mode == "fp32":
         assert torch.equal(got, got_f)        # dedup only skips recomputation: same arithmetic
+
+
+@pytest.mark.parametrize("B,contiguous", [(256, True), (300, True), (700, True), (700, False), (1025, False)])
+def test_lstm_weights_stationary_step(B, contiguous):
+    """Batches of >= 256 clips take the weights-stationary recurrent-step kernel (umma_lstm_ws.cu): contiguous
+    clip starts read their projected rows by TMA, video boundaries / random picks by per-thread loads; the last
+    256-clip tile is partial.  Against the oracle, and the frame-deduplicated entry against the per-clip one."""
+    _need_mode("f16")
+    m = _model(7)
+    seq = 10
+    n_frames = 2 * B + seq
+    feats = torch.from_numpy(synth.features(n_frames, seed=B))
+    if contiguous:
+        starts = torch.arange(B)
+        if B > 400:                                   # a "video boundary": the second half starts seq frames later
+            starts[B // 2 + 3:] += seq
+    else:
+        starts = torch.from_numpy(np.sort(np.random.default_rng(B).choice(n_frames - seq, size=B, replace=False)))
+    x = torch.stack([feats[s:s + seq] for s in starts.tolist()])
+    ref = orc.lstm_last(x, _sd(7))
+    got_f = ops.lstm_last_frames(m.packs()[0], feats.to(_dev()), starts.to(_dev()), seq, "f16")
+    got = ops.lstm_last(m.packs()[0], x.to(_dev()), "f16")
+    assert rel_err(got_f, ref) < TOL["f16"]
+    assert rel_err(got, ref) < TOL["f16"]
+    assert torch.equal(got, got_f)                    # same fp16 operands and summation order on both routes
+
+
+def test_lstm_weights_stationary_equals_streamed_engine():
+    """TMR_LSTM_WS=0 routes the same step through the streamed GEMM engine (umma_gemm.cu, EPI_LSTM): same fp16
+    operands, same K order inside one accumulator -> bit-identical h_T.  The switch is read once per process,
+    so each variant runs in its own interpreter."""
+    _need_mode("f16")
+    import hashlib
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, torch, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import tmrnet_b200 as tb\n"
+        "from tmrnet_b200 import ops, synth\n"
+        "dev = torch.device('cuda:0')\n"
+        "B, seq = 600, 10\n"
+        "feats = torch.from_numpy(synth.features(B + seq + 20, seed=3)).to(dev)\n"
+        "starts = torch.arange(B); starts[301:] += 15\n"
+        "m = tb.resnet_lstm(); m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.head_state_dict(seed=1234).items()}); m = m.to(dev).eval()\n"
+        "h = ops.lstm_last_frames(m.packs()[0], feats, starts.to(dev), seq, 'f16')\n"
+        "print(hashlib.sha256(h.cpu().numpy().tobytes()).hexdigest())\n"
+    )
+    digests = []
+    for ws in ("1", "0"):
+        env = dict(os.environ, TMR_LSTM_WS=ws)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append(out.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
+
+
+def test_f16_operands_saturate_instead_of_overflowing():
+    """Operands beyond the fp16 range are clamped to +-65504 by their producer (cvt.rn.satfinite), never inf."""
+    _need_mode("f16")
+    dev = _dev()
+    m = _model(7)
+    x = torch.zeros(2, 1, 2048)
+    x[0, 0, 0] = 1e9
+    x[1, 0, 0] = 65504.0
+    got = ops.lstm_last(m.packs()[0], x.to(dev), "f16")
+    assert torch.isfinite(got).all()
+    assert torch.equal(got[0], got[1])
 
 
 def test_lstm_LFB_module_builds_bank_rows(golden_dir):
