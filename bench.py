@@ -316,8 +316,8 @@ def run_ours(args):
         # per clip) is the longer one (tensor: 1.25 ns at the measured bf16/fp16 rate), so the kernel is judged
         # on the HBM roofline; its tensor-core rate is reported beside it.
         step_gbs = BYTES_LSTM_STEP * ls["clips"] / ls["ms"] / 1e6
-        roof = {"kernel": "umma_gemm_kernel<EPI_LSTM> (recurrent step h.Whh^T + LSTM cell epilogue; 9 launches per batch, "
-                          "largest share of the step, see profiles/)",
+        roof = {"kernel": "umma_lstm_ws_kernel (weights-stationary recurrent step h.Whh^T + LSTM cell epilogue; 9 launches "
+                          "per batch, largest share of the step, see profiles/r1_f16_ncu.md)",
                 "bound": "hbm", "achieved": step_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": step_gbs / pk["hbm"],
                 "traffic": NCU_TRAFFIC_LSTM_STEP[0] * ls["clips"] / NCU_TRAFFIC_LSTM_STEP[1],
                 "traffic_source": f"ncu dram bytes of one launch at {NCU_TRAFFIC_LSTM_STEP[1]} clips, scaled to clips_per_launch",

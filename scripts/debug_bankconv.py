@@ -30,9 +30,9 @@ v = np.where(k <= 2, k + 1, np.where(L - 1 - k <= 2, 4 + (L - 1 - k), 0))
 ded = pb[torch.from_numpy(rows), torch.from_numpy(np.broadcast_to(v, rows.shape).copy())]   # (B, L, 512)
 scale = float(ref64.abs().max())
 print("max|ref|", scale)
-for name, t in (("general tf32", gen), ("general fp32", gen32), ("dedup tf32", ded)):
+for name, t in (("general f16", gen), ("general fp32", gen32), ("dedup f16", ded)):
     d = (t.double() - ref64).abs()
     print(f"{name:14s} vs fp64: max {float(d.max())/scale:.2e}  per-slot max:", " ".join(f"{float(d[:, kk].max())/scale:.1e}" for kk in range(L)))
 d = (ded.double() - gen.double()).abs()
-print("dedup vs general tf32: max %.2e" % (float(d.max()) / scale), " per-slot:", " ".join(f"{float(d[:, kk].max())/scale:.1e}" for kk in range(L)))
+print("dedup vs general f16: max %.2e" % (float(d.max()) / scale), " per-slot:", " ".join(f"{float(d[:, kk].max())/scale:.1e}" for kk in range(L)))
 print("mean signed (dedup-general)/scale per slot:", " ".join(f"{float((ded.double()-gen.double())[:, kk].mean())/scale:+.1e}" for kk in range(L)))

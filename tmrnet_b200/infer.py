@@ -297,7 +297,7 @@ class BankInference:
     def launches_per_run(self) -> int:
         """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
         projection + cell0 + (seq-1) steps | gather | timeconv | q, u, attention, v, layernorm, out |
-        fc_h_c, fc_c; TF32 mode adds the TF32 rounding passes (features, window, St, [St|y1]) and folds
+        fc_h_c, fc_c; tensor-core mode adds the fp16 conversion passes (features, window, St, [St|y1]) and folds
         q, u into one GEMM; the dedup path replaces gather+round+timeconv over all clips by round(bank rows)
         + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw bankconv +
         assemble (or gather+round+timeconv without the row list)."""
