@@ -185,6 +185,7 @@ umma_lstm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       float cin[8], cn[8], hn[8];
+      uint4 hpack = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int ch = 0; ch < WS_NCH; ++ch) {
         constexpr int U = CW / 4;                       // hidden units per chunk (8 or 4)
@@ -244,10 +245,16 @@ umma_lstm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (sub == CPG - 1) {
             const int64_t o = mrow * kD + ((ncol0 + cc + CW - 32) >> 2);
             stg256(p.c + o, cn);
-            // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32
+            // h only feeds the next step's MMA: fp16; the last step's h is the clip's St: fp32.  The step pays
+            // per L2 request, so the fp16 h of TWO 8-unit groups leaves as one 32-byte sector.
             if (p.h_out16) {
               const uint2 lo = pack_h4(hn[0], hn[1], hn[2], hn[3]), hi = pack_h4(hn[4], hn[5], hn[6], hn[7]);
-              *reinterpret_cast<uint4*>(p.h_out16 + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              if (((cc + CW - 32) >> 5) % 2 == 0) {
+                hpack = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              } else {
+                const uint32_t w8[8] = {hpack.x, hpack.y, hpack.z, hpack.w, lo.x, lo.y, hi.x, hi.y};
+                stg256u(p.h_out16 + o - 8, w8);
+              }
             } else {
               stg256(p.h_out + o, hn);
             }
