@@ -242,6 +242,14 @@ int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h,
 constexpr int kAttnWarps = 4;
 constexpr int KB = 6;
 
+// Packed fp32 pairs (FFMA2 / FMUL2 on sm_100): the attention kernels are bound by instruction issue, and the two
+// passes over a slot (dot product, weighted accumulation) are pure FMA streams - one instruction per two lanes of
+// a float4 halves them.  Packing a pair of adjacent registers is free.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // Body shared by the two attention kernels; rowptr(k) yields the 512-float row of memory slot k.
 template <class RowPtr>
 __device__ __forceinline__ void attention_body(const float* __restrict__ u, int b, int L, float scale,
@@ -250,9 +258,12 @@ __device__ __forceinline__ void attention_body(const float* __restrict__ u, int 
   float4 uq[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) uq[i] = __ldg(reinterpret_cast<const float4*>(u + (int64_t)b * kD) + i * 32 + lane);
-  float4 acc[4];
+  uint64_t u2[8], acc2[8];                              // (x,y) and (z,w) pairs of the lane's four float4
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 4; ++i) {
+    u2[2 * i] = pk2(uq[i].x, uq[i].y); u2[2 * i + 1] = pk2(uq[i].z, uq[i].w);
+    acc2[2 * i] = acc2[2 * i + 1] = pk2(0.f, 0.f);
+  }
   float run_max = -INFINITY, run_sum = 0.f;
 
   for (int k0 = 0; k0 < L; k0 += KB) {
@@ -271,13 +282,15 @@ __device__ __forceinline__ void attention_body(const float* __restrict__ u, int 
     }
 #pragma unroll
     for (int kk = 0; kk < KB; ++kk) {
-      float p = 0.f;
+      uint64_t p2 = pk2(0.f, 0.f);                      // two interleaved partial sums (even / odd channels)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        p = fmaf(x[kk][i].x, uq[i].x, p); p = fmaf(x[kk][i].y, uq[i].y, p);
-        p = fmaf(x[kk][i].z, uq[i].z, p); p = fmaf(x[kk][i].w, uq[i].w, p);
+        p2 = ffma2(pk2(x[kk][i].x, x[kk][i].y), u2[2 * i], p2);
+        p2 = ffma2(pk2(x[kk][i].z, x[kk][i].w), u2[2 * i + 1], p2);
       }
-      d[kk] = p;
+      float pe, po;
+      upk2(p2, pe, po);
+      d[kk] = pe + po;
     }
 #pragma unroll
     for (int kk = 0; kk < KB; ++kk) d[kk] = warp_sum(d[kk]);
@@ -290,16 +303,18 @@ __device__ __forceinline__ void attention_body(const float* __restrict__ u, int 
     const float new_max = fmaxf(run_max, cmax);
     const float corr = expf(run_max - new_max);          // 0 on the first chunk (run_max = -inf)
     run_sum *= corr;
+    const uint64_t corr2 = pk2(corr, corr);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i].x *= corr; acc[i].y *= corr; acc[i].z *= corr; acc[i].w *= corr; }
+    for (int i = 0; i < 8; ++i) acc2[i] = fmul2(acc2[i], corr2);
 #pragma unroll
     for (int kk = 0; kk < KB; ++kk) {
       const float p = expf(d[kk] - new_max);             // exp(-inf) = 0 for masked slots
       run_sum += p;
+      const uint64_t pp = pk2(p, p);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        acc[i].x = fmaf(p, x[kk][i].x, acc[i].x); acc[i].y = fmaf(p, x[kk][i].y, acc[i].y);
-        acc[i].z = fmaf(p, x[kk][i].z, acc[i].z); acc[i].w = fmaf(p, x[kk][i].w, acc[i].w);
+        acc2[2 * i] = ffma2(pp, pk2(x[kk][i].x, x[kk][i].y), acc2[2 * i]);
+        acc2[2 * i + 1] = ffma2(pp, pk2(x[kk][i].z, x[kk][i].w), acc2[2 * i + 1]);
       }
     }
     run_max = new_max;
@@ -307,7 +322,9 @@ __device__ __forceinline__ void attention_body(const float* __restrict__ u, int 
   const float inv = 1.f / run_sum;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 o = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+    float4 o;
+    upk2(acc2[2 * i], o.x, o.y); upk2(acc2[2 * i + 1], o.z, o.w);
+    o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
     if (half_out) reinterpret_cast<uint2*>(reinterpret_cast<half_t*>(a) + (int64_t)b * kD)[i * 32 + lane] = pack_h4(o);
     else reinterpret_cast<float4*>(reinterpret_cast<float*>(a) + (int64_t)b * kD)[i * 32 + lane] = o;
   }
