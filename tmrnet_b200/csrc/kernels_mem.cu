@@ -528,7 +528,32 @@ int launch_to_half(const float* src, half_t* dst, int64_t n, cudaStream_t st) {
 __global__ void half_concat_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ a2, int64_t lda2,
                                    int k_split, int K, int64_t M, half_t* __restrict__ dst, int a2_plus_a) {
   const int64_t n8 = M * (K / 8);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!a2) {
+    // plain conversion (the features of a batch: the one large instance): a thread converts one float4 per
+    // piece - fully coalesced 128-bit loads and 64-bit stores - eight independent pieces per iteration, all loads
+    // issued before the first store, so enough bytes are in flight per SM
+    const int64_t n4 = M * (K / 4);
+    int64_t i4 = i;
+    for (; i4 + 7 * stride < n4; i4 += 8 * stride) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t ij = i4 + j * stride;
+        const int64_t m = ij / (K / 4);
+        v[j] = ldg_nc(reinterpret_cast<const float4*>(a + m * lda) + (ij - m * (K / 4)));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) reinterpret_cast<uint2*>(dst)[i4 + j * stride] = pack_h4(v[j]);
+    }
+    for (; i4 < n4; i4 += stride) {
+      const int64_t m = i4 / (K / 4);
+      reinterpret_cast<uint2*>(dst)[i4] = pack_h4(ldg_nc(reinterpret_cast<const float4*>(a + m * lda) + (i4 - m * (K / 4))));
+    }
+    return;
+  }
+  for (; i < n8; i += stride) {
     const int64_t m = i / (K / 8);
     const int k = (int)(i - m * (K / 8)) * 8;
     const float* src = (k < k_split) ? a + m * lda + k : a2 + m * lda2 + (k - k_split);
