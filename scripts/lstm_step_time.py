@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Recurrent-step time of the LSTM on a bench-sized batch: (seq-step LSTM - 1-step LSTM) / (seq - 1), CUDA events.
-Usage: lstm_step_time.py [B]   (env TMR_LSTM_XBUF / TMR_LSTM_STAGES select kernel variants)"""
+Usage: lstm_step_time.py [B]   (env TMR_LSTM_WS=0: streamed GEMM engine; TMR_LSTM_WS_CFG=16: 16 epilogue warps)"""
 import os, sys
 import numpy as np
 import torch
@@ -33,6 +33,6 @@ def timeit(fn, reps=20):
 t10 = timeit(lambda: ops.lstm_last_frames(pk, feats, starts, seq, "f16"))
 t1 = timeit(lambda: ops.lstm_last_frames(pk, feats, starts, 1, "f16"))
 step = (t10 - t1) / (seq - 1)
-print(f"B={B} xbuf={os.environ.get('TMR_LSTM_XBUF', '1')} stages={os.environ.get('TMR_LSTM_STAGES', '-')}: "
+print(f"B={B} ws={os.environ.get('TMR_LSTM_WS', '1')} cfg={os.environ.get('TMR_LSTM_WS_CFG', '8')}: "
       f"10-step {t10*1e3:.1f} us, 1-step {t1*1e3:.1f} us, recurrent step {step*1e3:.1f} us "
-      f"= {B * 14336 / step / 1e6:.0f} GB/s (14 KB/clip), {B * 2.097152 / step / 1e6:.0f} TFLOP/s")
+      f"= {B * 14336 / step / 1e6:.0f} GB/s (14 KB/clip), {B * 2.097152e6 / (step * 1e-3) / 1e12:.0f} TFLOP/s")
