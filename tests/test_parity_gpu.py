@@ -612,6 +612,54 @@ def test_bank_level_dedup_head_matches_oracle_and_per_clip_path(L, pad_mode, irr
         assert torch.equal(got["pred"].cpu()[safe], ref_logits.argmax(1)[safe])
 
 
+def test_full_size_bank_pass_properties():
+    """BASELINE configs[1] at full size (40 Cholec80-shaped videos, ~83 k clips, L=30, seq=10: two ~41.5 k-clip batches,
+    every persistent kernel at its full grid) through size-independent properties: a sample of clips - the first
+    clips of videos (irregular windows), batch boundaries, random interior clips - against the oracle; a second and
+    third pass (CUDA-graph replay) bit-identical to the first; a different batch split agrees to fp32 noise."""
+    from tmrnet_b200.infer import BankInference
+    _need_mode("f16")
+    dev = _dev()
+    seq, L, C = 10, 30, 7
+    lengths = synth.video_lengths(40, seed=77)
+    index = tb.LFBIndex.from_lengths(lengths, seq)
+    n_frames, n_clips = int(sum(lengths)), len(index)
+    feats = synth.features(n_frames, seed=77)
+    bank = synth.bank(n_clips, seed=77)
+    m = _model(C)
+    fd, bd = torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)
+    eng = BankInference(m, index, seq, L, math_mode="f16")
+    out1 = {k: v.clone() for k, v in eng.run(fd, bd).items()}
+    for _ in range(2):                                    # eager pass, then graph replay
+        again = eng.run(fd, bd)
+        for key in ("logits", "pred", "score"):
+            assert torch.equal(again[key], out1[key]), key
+    assert out1["logits"].shape == (n_clips, C) and torch.isfinite(out1["logits"]).all()
+    # sample against the oracle
+    starts = np.asarray(eng.starts_host)
+    plan = eng.plan()
+    rng = np.random.default_rng(5)
+    first = np.cumsum([0] + [n - seq + 1 for n in lengths[:-1]])            # first clip of every video
+    pick = np.unique(np.concatenate([first[:6], first[:6] + 1, first[1:4] + L - 1, first[1:4] + L,
+                                     [plan[0][1] - 1, plan[0][1], n_clips - 1], rng.integers(0, n_clips, size=40)]))
+    s = starts[pick]
+    x = np.stack([feats[a:a + seq] for a in s])
+    lf = orc.get_long_feature(s, orc.build_start_dict(starts.tolist()), bank, L)
+    ref = orc.head(x, lf, _sd(C), dtype=torch.float64)[0]
+    got = out1["logits"][torch.from_numpy(pick).to(dev)]
+    assert rel_err(got, ref) < TOL["f16"]
+    top2 = torch.topk(ref, 2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * TOL["f16"] * float(ref.abs().max())
+    assert torch.equal(out1["pred"][torch.from_numpy(pick).to(dev)].cpu()[safe], ref.argmax(1)[safe])
+    # a different batch split: same per-clip arithmetic up to fp32 summation order in the bank-level TimeConv tiles
+    eng2 = BankInference(m, index, seq, L, batch_clips=9472, math_mode="f16")
+    out2 = eng2.run(fd, bd)
+    assert rel_err(out2["logits"], out1["logits"]) < 1e-4
+    margin = torch.topk(out1["logits"], 2, dim=1).values
+    clear = (margin[:, 0] - margin[:, 1]) > 1e-3
+    assert torch.equal(out2["pred"][clear], out1["pred"][clear])
+
+
 def test_host_buffer_pass_equals_resident_pass():
     """BankInference.run_host (double-buffered H2D of the features, D2H of preds/scores) must give
     exactly what run() gives on resident features."""
