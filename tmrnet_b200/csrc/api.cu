@@ -119,6 +119,14 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   g.out = ws.xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
   g.w16 = w16 + LstmPacked::wih_off;
   g.a_scratch = tc ? reinterpret_cast<half_t*>(ws.xr) : nullptr;
+  // tensor-core mode, seq > 1: step 0 of the recurrence (zero state) rides in the projection's epilogue.  The
+  // row -> clip table lives in the unused half of the fp16-feature slot (n_rows_x x 2048 x 2 of its 4 bytes used).
+  const bool fuse0 = tc && seq > 1;
+  if (fuse0) {
+    int32_t* row2clip = reinterpret_cast<int32_t*>(ws.xr + (size_t)n_rows_x * (kF / 2));
+    TMR_TRY(launch_row2clip(starts, seq, B, n_rows_x, frame0, row2clip, st));
+    g.row2clip = row2clip; g.c0 = ws.c; g.h0_16 = reinterpret_cast<half_t*>(ws.h0);
+  }
   TMR_TRY(do_linear(g, mode, st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
   // (Running the recurrence in L2-sized sub-batches - all steps of one before the next, so that the projected
@@ -128,7 +136,7 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   // mode the intermediate h only feeds the next step's MMA and lives in fp16 (h0 / h1 hold half_t[B,512]).
   if (tc) {
     half_t* h16[2] = {reinterpret_cast<half_t*>(ws.h0), reinterpret_cast<half_t*>(ws.h1)};
-    TMR_TRY(launch_lstm_cell0(xp, starts, seq, out, seq > 1 ? h16[0] : nullptr, ws.c, B, st, true));
+    if (!fuse0) TMR_TRY(launch_lstm_cell0(xp, starts, seq, out, seq > 1 ? h16[0] : nullptr, ws.c, B, st, true));
     for (int t = 1; t < seq; ++t) {
       const bool last = (t == seq - 1);
       TMR_TRY(umma_lstm_step(w16 + LstmPacked::whh_off, xp, starts, seq, t, h16[(t - 1) & 1], last ? nullptr : h16[t & 1],

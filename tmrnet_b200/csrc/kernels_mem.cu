@@ -509,6 +509,21 @@ __global__ void interleave_bias_kernel(const float* __restrict__ bih, const floa
   dst[r] = bih[gate * kD + unit] + bhh[gate * kD + unit];
 }
 
+__global__ void row2clip_kernel(const int64_t* __restrict__ starts, int seq, int B, int64_t n_rows, int64_t row0,
+                                int32_t* __restrict__ row2clip) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t r = starts ? starts[b] - row0 : (int64_t)b * seq;
+  if (r >= 0 && r < n_rows) row2clip[r] = b;
+}
+int launch_row2clip(const int64_t* starts, int seq, int B, int64_t n_rows, int64_t row0, int32_t* row2clip, cudaStream_t st) {
+  if (n_rows == 0) return TMR_OK;
+  TMR_CUDA(cudaMemsetAsync(row2clip, 0xff, sizeof(int32_t) * n_rows, st));          // -1 everywhere
+  if (B > 0) row2clip_kernel<<<(B + 255) / 256, 256, 0, st>>>(starts, seq, B, n_rows, row0, row2clip);
+  TMR_LAUNCH_CHECK("row2clip_kernel");
+  return TMR_OK;
+}
+
 __global__ void to_half_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = pack_h4(__ldg(src + i));

@@ -20,6 +20,9 @@ struct LinearArgs {
   const half_t* a16 = nullptr;
   half_t* a_scratch = nullptr;
   bool a2_plus_a = false;       // with a_scratch and a2: the a2 half becomes fp16(a2 + a) (deferred residual)
+  // tensor-core LSTM input projection only: row r starts clip row2clip[r] (-1: none) -> the epilogue also writes
+  // step 0 of that clip's recurrence (c0 fp32, h0 fp16) and lstm_cell0_kernel is not launched
+  const int32_t* row2clip = nullptr; float* c0 = nullptr; half_t* h0_16 = nullptr;
 };
 
 // ---- fp32 CUDA-core path (kernels_simt.cu) ----
@@ -72,6 +75,8 @@ int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, co
 // y = relu(layer_norm(v) * w + b) over rows of 512; half_out: y receives fp16
 int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, void* y,
                           int half_out, cudaStream_t st);
+// row2clip[r] = clip whose first frame is projected row r (r = starts[b] - row0, or b * seq without starts), else -1
+int launch_row2clip(const int64_t* starts, int seq, int B, int64_t n_rows, int64_t row0, int32_t* row2clip, cudaStream_t st);
 // dst[n] = fp16(src[n])
 int launch_to_half(const float* src, half_t* dst, int64_t n, cudaStream_t st);
 // dst[M,K] = fp16([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))

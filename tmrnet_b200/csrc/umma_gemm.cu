@@ -84,6 +84,9 @@ struct GemmParams {
   int64_t M; int N; int K; int k_split;
   // EPI_LINEAR
   const float* bias; const float* residual; int64_t ldr; float* out; int64_t ldo; int relu;
+  // EPI_LINEAR as the LSTM input projection (gate-interleaved columns): rows that start a clip also get step 0 of
+  // that clip's recurrence from zero state, c0 = sig(i) tanh(g), h0 = sig(o) tanh(c0), written as c0[clip] / h0[clip]
+  const int32_t* row2clip; float* c0; half_t* h0_16;
   // EPI_LSTM (N = 4*512 gate-interleaved columns)
   const float* xp; const int64_t* starts; int seq; int t; float* h_out; half_t* h_out16; float* c;
   int x_tma; int64_t x_row0;          // tma_x covers the projected rows; its row 0 is projected row x_row0
@@ -400,6 +403,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 *reinterpret_cast<float4*>(p.out + mr * p.ldo + n) = v;
+                if (p.row2clip) {                       // v = (i, f, g, o) of hidden unit n / 4; f * c_{-1} = 0 drops out
+                  const int clip = __ldg(p.row2clip + mr);
+                  if (clip >= 0) {
+                    const float a = ex2_approx(fminf(-1.4426950408889634f * v.x, 40.f));
+                    const float d = ex2_approx(fminf(-2.8853900817779268f * v.z, 40.f));
+                    const float e = ex2_approx(fminf(-1.4426950408889634f * v.w, 40.f));
+                    const float cn = (1.f - d) * rcp_approx((1.f + a) * (1.f + d));          // sigmoid(i) tanh(g)
+                    const float f2 = ex2_approx(fminf(-2.8853900817779268f * cn, 40.f));
+                    const float hn = (1.f - f2) * rcp_approx((1.f + e) * (1.f + f2));        // sigmoid(o) tanh(c)
+                    const int64_t o = (int64_t)clip * kD + (n >> 2);
+                    p.c0[o] = cn;
+                    reinterpret_cast<uint16_t*>(p.h0_16)[o] = (uint16_t)(pack_h2(hn, 0.f) & 0xffffu);
+                  }
+                }
               }
             }
           }
@@ -532,6 +549,8 @@ int umma_linear(const LinearArgs& g, cudaStream_t st) {
   umma::GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.K;
   p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu;
+  p.row2clip = g.row2clip; p.c0 = g.c0; p.h0_16 = g.h0_16;
+  TMR_CHECK_ARG(!g.row2clip || (g.c0 && g.h0_16 && g.N == 4 * kD), "f16 linear: fused LSTM step 0 needs c0 / h0 and N = 4 x 512");
   return umma::launch_gemm<umma::EPI_LINEAR>(g.a16, g.lda, nullptr, 0, 0, g.w16, g.ldw, p, st);
 }
 
