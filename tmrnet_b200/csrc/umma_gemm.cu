@@ -53,9 +53,9 @@ constexpr int BM = 128, BN = 256, BK = 64;           // BK fp16 = 128 bytes = on
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 // Per-epilogue configuration.  The LSTM-cell epilogue, not the MMAs, bounds the recurrent step, so it gets
 // 16 epilogue warps (4 per SM sub-partition), each with XBUF 32x32 fp32 smem tiles: the landing zones of the
-// warp's own TMA loads of projected rows.  With fp16 operands a 32 KB stage covers K = 64, so the main loop
-// needs fewer stages than the epilogue needs prefetch depth: XBUF = 2 trades two stages for a second tile.
-// The plain epilogue keeps 8 warps (one 4 KB transpose tile each) and 4 / 6 stages.
+// warp's own TMA loads of projected rows.  XBUF = 2 (a second tile for two of the five stages) measured the same
+// 143 us per 41 600 clips as XBUF = 1 and is not instantiated.  The plain epilogue keeps 8 warps (one 4 KB
+// transpose tile each) and 4 / 6 stages.  Batches of >= 256 clips take umma_lstm_ws.cu instead of EPI_LSTM here.
 template <int EPI, int XBUF = 1> struct Cfg {
   static constexpr int STAGES = (EPI == EPI_LSTM) ? 3 : 4;
   static constexpr int STAGES_2SM = (EPI == EPI_LSTM) ? (XBUF == 2 ? 3 : 5) : 6;      // 32 KB stages in 2-SM mode
