@@ -144,3 +144,66 @@ def test_relaxed_boundary_evaluator_hand_cases():
     assert abs(out["mean_accuracy"] - 95.0) < 1e-9 and out["jaccard_per_phase"].shape == (7,)
     with pytest.raises(ValueError):
         evaluate(gt, gt[:-1])
+
+
+# ------------------------------------------------------------------------------------------
+# a10 host control flow: LR schedules, best-model selection, per-phase metrics (TRAIN:806-809, 983-984, 1023-1052)
+# ------------------------------------------------------------------------------------------
+class _FakeTrainer:
+    def __init__(self, lr):
+        self.lr = lr
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_plateau_lr_matches_torch_reduce_on_plateau(seed):
+    from tmrnet_b200.train import PlateauLR
+    rng = np.random.default_rng(seed)
+    # a loss curve that improves, stalls for long stretches, and improves again
+    losses = np.concatenate([np.linspace(3, 1, 8), 1.0 + 1e-5 * rng.random(25), np.linspace(0.99, 0.7, 5),
+                             0.7 + 0.05 * rng.random(30), [0.1], 0.1 + rng.random(15)])
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([{"params": [p]}], lr=5e-4)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "min")
+    tr = _FakeTrainer(5e-4)
+    mine = PlateauLR(tr)
+    for v in losses:
+        ref.step(float(v))
+        mine.step(float(v))
+        assert tr.lr == opt.param_groups[0]["lr"]
+    assert tr.lr < 5e-4                      # the curve did trigger reductions
+
+
+def test_step_lr_matches_torch():
+    from tmrnet_b200.train import StepLR
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.StepLR(opt, step_size=3, gamma=0.1)
+    tr = _FakeTrainer(1e-3)
+    mine = StepLR(tr, 3, 0.1)
+    for _ in range(10):
+        opt.step(); ref.step(); mine.step()
+        assert abs(tr.lr - opt.param_groups[0]["lr"]) <= 1e-12 * 1e-3 + 1e-18
+
+
+def test_best_model_tracker_tie_rule_and_checkpoint_name():
+    from tmrnet_b200.train import BestModelTracker
+    t = BestModelTracker()
+    sd = {"w": torch.zeros(2)}
+    assert t.update(0, 0.50, 0.60, lambda: sd) and t.best_epoch == 0
+    assert not t.update(1, 0.90, 0.55, lambda: sd)                 # lower val acc: ignored whatever the train acc
+    assert t.update(2, 0.70, 0.60, lambda: sd) and t.best_epoch == 2          # exact tie, higher train acc: taken
+    assert not t.update(3, 0.65, 0.60, lambda: sd) and t.best_epoch == 2      # exact tie, lower train acc: kept
+    assert t.update(4, 0.10, 0.61, lambda: sd) and t.best_epoch == 4 and t.correspond_train_acc == 0.10
+    t.best_val_acc, t.correspond_train_acc, t.best_epoch = 0.87654, 0.91239, 7
+    assert t.checkpoint_name(seq=10, train_bs=400) == "lstm_epoch_7_length_10_opt_0_mulopt_1_flip_1_crop_1_batch_400_train_9124_val_8765"
+
+
+def test_per_phase_precision_recall_matches_sklearn():
+    from sklearn import metrics
+    from tmrnet_b200.train import per_phase_precision_recall
+    rng = np.random.default_rng(0)
+    labels = rng.integers(0, 7, size=500)
+    preds = np.where(rng.random(500) < 0.7, labels, rng.integers(0, 6, size=500))     # class 6 is never predicted wrongly-only
+    p, r = per_phase_precision_recall(labels, preds)
+    assert np.allclose(p, metrics.precision_score(labels, preds, average=None, zero_division=0))
+    assert np.allclose(r, metrics.recall_score(labels, preds, average=None, zero_division=0))

@@ -126,3 +126,46 @@ def test_dropout_masks_are_seeded_and_scaled():
     assert not torch.equal(g1, b.grads.flat)
     l0, _, _ = a.forward_backward(X, LF, Y, dropout=False)
     assert float(l0) != float(l1)
+
+
+def test_fit_epoch_loop_learns_and_tracks_best():
+    """The reference's epoch loop (TRAIN:815-1056) around HeadTrainer.step on a tiny synthetic job whose labels are a
+    function of the features: training loss falls, validation loss equals the oracle's sum-reduced CE on the same
+    weights, the plateau scheduler and the best-model tracker are driven per epoch."""
+    from tmrnet_b200.train import PlateauLR, fit
+    dev = torch.device("cuda:0")
+    C, seq, L = 7, 10, 30
+    lengths = [60, 45, 70]
+    index = tb.LFBIndex.from_lengths(lengths, seq)
+    starts = np.array(tb.get_useful_start_idx(seq, lengths))
+    feats = synth.features(sum(lengths), seed=9)
+    bank = synth.bank(len(starts), seed=9)
+    labels = (np.argmax(feats[:, :C], axis=1)).astype(np.int64)          # learnable from the last frame's features
+    sd = synth.head_state_dict(num_class=C, seed=4)
+    m = tb.resnet_lstm(num_class=C, sequence_length=seq)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(dev)
+    tr = HeadTrainer(m, lr=1e-4, p_nl=0.0, p_fc=0.0, seed=1)      # the loss is SUM-reduced over 40 clips (TRAIN:780)
+    sched = PlateauLR(tr, patience=0)
+    fd, bd = torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(starts)
+    tr_s, va_s = np.sort(perm[:120]), np.sort(perm[120:150])
+    seen = []
+    hist, tracker = fit(tr, index, fd, bd, labels, tr_s, va_s, epochs=4, batch_clips=40, L=L, seed=3, scheduler=sched, log=seen.append)
+    assert len(hist) == 4 and len(seen) == 4
+    assert min(h["train_loss"] for h in hist[1:]) < hist[0]["train_loss"]
+    assert all(np.isfinite(h["train_loss"]) for h in hist)
+    assert tracker.best_state is not None and 0 <= tracker.best_epoch < 4
+    assert all(0.0 <= h["val_acc"] <= 1.0 and np.isfinite(h["val_loss"]) for h in hist)
+    assert any(h["best"] for h in hist)
+    # validation loss of the final weights against the oracle head on the same clips
+    sd_now = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    x = np.stack([feats[s:s + seq] for s in va_s])
+    lf = orc.get_long_feature(va_s, orc.build_start_dict(starts.tolist()), bank, L)
+    logits = orc.head(x, lf, sd_now, dtype=torch.float64)[0]
+    y = torch.from_numpy(labels[va_s + seq - 1])
+    ref_loss = float(Fn.cross_entropy(logits, y, reduction="sum")) / len(va_s)
+    m.eval()
+    hist2, _ = fit(tr, index, fd, bd, labels, tr_s[:0], va_s, epochs=1, batch_clips=40, L=L)
+    assert abs(hist2[0]["val_loss"] - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))

@@ -125,3 +125,176 @@ class HeadTrainer:
         self.allreduce_grads()
         self.sgd_update()
         return loss, logits, pred
+
+
+# ---------------------------------------------------------------------------------------------
+# Host control flow around the step (TRAIN:780-812, 925-1056): learning-rate schedules on the
+# validation loss, per-epoch bookkeeping, best-model selection.  Plain Python on purpose - this is
+# the reference's epoch loop with the head's forward/backward/update swapped for HeadTrainer.step().
+# ---------------------------------------------------------------------------------------------
+class PlateauLR:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'min') as the reference constructs it (TRAIN:808-809:
+    every default - factor 0.1, patience 10, relative threshold 1e-4, no cooldown, min_lr 0, eps 1e-8), acting
+    on HeadTrainer.lr.  The reference's two parameter groups (lr/10 for the LSTM, lr for the rest) are both
+    multiplied by `factor`, which is what scaling the trainer's base lr does.  step(metric) after every epoch
+    (TRAIN:1023-1027)."""
+
+    def __init__(self, trainer, factor=0.1, patience=10, threshold=1e-4, cooldown=0, min_lr=0.0, eps=1e-8):
+        if factor >= 1.0:
+            raise ValueError("Factor should be < 1.0.")
+        self.trainer, self.factor, self.patience, self.threshold = trainer, factor, patience, threshold
+        self.cooldown, self.min_lr, self.eps = cooldown, min_lr, eps
+        self.best = float("inf")
+        self.num_bad_epochs = 0
+        self.cooldown_counter = 0
+        self.last_epoch = 0
+
+    def _is_better(self, a):
+        return a < self.best * (1.0 - self.threshold)
+
+    def step(self, metric):
+        current = float(metric)
+        self.last_epoch += 1
+        if self._is_better(current):
+            self.best = current
+            self.num_bad_epochs = 0
+        else:
+            self.num_bad_epochs += 1
+        if self.cooldown_counter > 0:
+            self.cooldown_counter -= 1
+            self.num_bad_epochs = 0
+        if self.num_bad_epochs > self.patience:
+            new_lr = max(self.trainer.lr * self.factor, self.min_lr)
+            if self.trainer.lr - new_lr > self.eps:
+                self.trainer.lr = new_lr
+            self.cooldown_counter = self.cooldown
+            self.num_bad_epochs = 0
+        return self.trainer.lr
+
+
+class StepLR:
+    """lr_scheduler.StepLR(optimizer, step_size, gamma) (TRAIN:806-807), acting on HeadTrainer.lr."""
+
+    def __init__(self, trainer, step_size, gamma=0.1):
+        self.trainer, self.step_size, self.gamma = trainer, int(step_size), float(gamma)
+        self.base_lr = trainer.lr
+        self.last_epoch = 0
+
+    def step(self, metric=None):
+        self.last_epoch += 1
+        self.trainer.lr = self.base_lr * self.gamma ** (self.last_epoch // self.step_size) if self.step_size > 0 else self.base_lr
+        return self.trainer.lr
+
+
+def per_phase_precision_recall(labels, preds, num_class=None):
+    """sklearn.metrics.precision_score / recall_score(average=None) as TRAIN:983-984 uses them: one value per class
+    that occurs in labels or preds (sorted), 0 where the denominator is empty."""
+    import numpy as np
+    labels = np.asarray(labels, dtype=np.int64).ravel()
+    preds = np.asarray(preds, dtype=np.int64).ravel()
+    classes = np.unique(np.concatenate([labels, preds])) if num_class is None else np.arange(num_class)
+    prec, rec = [], []
+    for c in classes:
+        tp = float(np.sum((preds == c) & (labels == c)))
+        pp, ap = float(np.sum(preds == c)), float(np.sum(labels == c))
+        prec.append(tp / pp if pp > 0 else 0.0)
+        rec.append(tp / ap if ap > 0 else 0.0)
+    return np.asarray(prec), np.asarray(rec)
+
+
+class BestModelTracker:
+    """TRAIN:1029-1039: keep the weights of the epoch with the highest validation accuracy; on an exact tie, the one
+    with the higher training accuracy.  checkpoint_name() reproduces the reference's file stem (TRAIN:1041-1052)."""
+
+    def __init__(self):
+        self.best_val_acc = 0.0
+        self.correspond_train_acc = 0.0
+        self.best_epoch = 0
+        self.best_state = None
+
+    def update(self, epoch, train_acc, val_acc, state_dict_fn):
+        took = False
+        if val_acc > self.best_val_acc:
+            self.best_val_acc, self.correspond_train_acc, self.best_epoch = val_acc, train_acc, epoch
+            took = True
+        if val_acc == self.best_val_acc and train_acc > self.correspond_train_acc:
+            self.correspond_train_acc, self.best_epoch = train_acc, epoch
+            took = True
+        if took:
+            self.best_state = {k: v.detach().clone() for k, v in state_dict_fn().items()}
+        return took
+
+    def checkpoint_name(self, seq, train_bs, optimizer_choice=0, multi_optim=1, use_flip=1, crop_type=1):
+        save_val = int("{:4.0f}".format(self.best_val_acc * 10000))
+        save_train = int("{:4.0f}".format(self.correspond_train_acc * 10000))
+        return ("lstm_epoch_" + str(self.best_epoch) + "_length_" + str(seq) + "_opt_" + str(optimizer_choice)
+                + "_mulopt_" + str(multi_optim) + "_flip_" + str(use_flip) + "_crop_" + str(crop_type)
+                + "_batch_" + str(train_bs) + "_train_" + str(save_train) + "_val_" + str(save_val))
+
+
+def fit(trainer, index, feats, bank, labels, train_starts, val_starts, epochs, batch_clips=120, L=30, seed=0,
+        scheduler=None, val_index=None, val_feats=None, val_bank=None, val_labels=None, log=None):
+    """The reference's epoch loop for the head (TRAIN:815-1056) over precomputed features and a cached bank:
+    shuffled clip starts -> get_long_feature -> HeadTrainer.step; validation in eval mode with the same
+    sum-reduced loss; scheduler.step(val loss); best-model tracking.  `labels` are per FRAME; a clip's label is
+    that of its last frame (TRAIN:838, 942).  Returns (history list of per-epoch dicts, BestModelTracker).
+    The validation split defaults to the training tensors (index / feats / bank / labels) when not given."""
+    import numpy as np
+    from . import lfb
+    model = trainer.model
+    seq = model.sequence_length
+    dev = trainer.device
+    rng = np.random.default_rng(seed)
+    val_index = index if val_index is None else val_index
+    val_feats = feats if val_feats is None else val_feats
+    val_bank = bank if val_bank is None else val_bank
+    val_labels = labels if val_labels is None else val_labels
+    labels_t = torch.as_tensor(labels, dtype=torch.int64, device=dev)
+    val_labels_t = torch.as_tensor(val_labels, dtype=torch.int64, device=dev)
+    train_starts = np.asarray(train_starts, dtype=np.int64)
+    val_starts = np.asarray(val_starts, dtype=np.int64)
+    frame_off = torch.arange(seq, device=dev)
+    tracker = BestModelTracker()
+    history = []
+
+    def clip_features(f, starts_dev):
+        return f[(starts_dev[:, None] + frame_off[None, :]).reshape(-1)].reshape(len(starts_dev), seq, F)
+
+    for epoch in range(epochs):
+        model.train()
+        order = rng.permutation(train_starts)
+        tr_loss, tr_correct = 0.0, 0
+        for lo in range(0, len(order), batch_clips):
+            s = order[lo:lo + batch_clips]
+            s_dev = torch.from_numpy(s).to(dev)
+            lf = lfb.get_long_feature(s, index, bank, L)
+            y = labels_t[s_dev + (seq - 1)]
+            loss, _, pred = trainer.step(clip_features(feats, s_dev), lf, y)
+            tr_loss += float(loss)
+            tr_correct += int((pred == y).sum())
+        model.eval()
+        va_loss, va_correct, va_preds, va_labels = 0.0, 0, [], []
+        for lo in range(0, len(val_starts), batch_clips):
+            s = val_starts[lo:lo + batch_clips]
+            s_dev = torch.from_numpy(s).to(dev)
+            lf = lfb.get_long_feature(s, val_index, val_bank, L)
+            y = val_labels_t[s_dev + (seq - 1)]
+            with torch.no_grad():
+                logits, pred, _ = model.predict(clip_features(val_feats, s_dev), lf)
+            logp = torch.log_softmax(logits.double(), dim=1)
+            w = trainer.class_weight.double()[y] if trainer.class_weight is not None else 1.0
+            va_loss += float(-(w * logp[torch.arange(len(y), device=dev), y]).sum())
+            va_correct += int((pred == y).sum())
+            va_preds.append(pred.cpu()); va_labels.append(y.cpu())
+        n_tr, n_va = max(1, len(train_starts)), max(1, len(val_starts))
+        prec, rec = per_phase_precision_recall(torch.cat(va_labels).numpy(), torch.cat(va_preds).numpy()) if va_labels else ([], [])
+        rec_e = dict(epoch=epoch, lr=trainer.lr, train_loss=tr_loss / n_tr, train_acc=tr_correct / n_tr,
+                     val_loss=va_loss / n_va, val_acc=va_correct / n_va,
+                     val_precision_each_phase=prec, val_recall_each_phase=rec)
+        if scheduler is not None:
+            scheduler.step(rec_e["val_loss"])
+        rec_e["best"] = tracker.update(epoch, rec_e["train_acc"], rec_e["val_acc"], model.state_dict)
+        history.append(rec_e)
+        if log is not None:
+            log(rec_e)
+    return history, tracker
