@@ -30,6 +30,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
+    run(args.batch, args.steps, args.warmup)
+
+
+def run(batch=40, steps=20, warmup=3):
+    """Also reachable as `bench.py --train [--train-batch B] [--steps K] [--warmup W]` (same launch line as the
+    inference bench, so the driver's torchrun command works unchanged)."""
+    args = argparse.Namespace(batch=batch, steps=steps, warmup=warmup)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

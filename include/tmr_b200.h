@@ -67,10 +67,15 @@ int tmr_build_frame2row(const int64_t* lens_host, int V, int seq, int32_t* frame
  * out[b,k,:] = bank[row(b,k),:], row(b,k) = frame2row[starts[b]-k-1] (0 if the key is negative);
  * TMR_PAD_ZERO writes zeros where the key precedes the clip's own video (needs frame2vstart).
  * starts: device int64[B] global clip-start frame ids; frame2row/frame2vstart: device int32.
- * rows_out (nullable): device int32[B*L] receiving the gathered row ids (-1 for zero rows). */
+ * rows_out (nullable): device int32[B*L] receiving the gathered row ids (-1 for zero rows).
+ * status (nullable): device int32, OR-ed with 1 when some starts[b] is not a valid clip start of the
+ * table (the reference raises KeyError there, TRAIN:310) and with 2 when a table entry lies outside
+ * [0, n_rows); such clips get an all-zero window and row ids -2.  The kernel never reads out of bounds,
+ * with or without `status`; the caller zeroes *status before and reads it after (a sync). */
 int tmr_gather_windows(const float* bank, int64_t n_rows, const int32_t* frame2row,
                        const int32_t* frame2vstart, int64_t n_frames, const int64_t* starts, int B,
-                       int L, int D, int pad_mode, float* out, int32_t* rows_out, void* stream);
+                       int L, int D, int pad_mode, float* out, int32_t* rows_out, int32_t* status,
+                       void* stream);
 
 /* ---- weight packing (once per weight update; caller owns the packed buffers) -------------------
  * Inputs use the reference state-dict layouts. */
@@ -122,7 +127,10 @@ int tmr_lstm_last_fwd(const void* packed, const float* x, int B, int seq, int F,
                       void* workspace, size_t workspace_bytes, int math_mode, void* stream);
 /* Frame-deduplicated form: feats (n_frames,F) holds every frame once; clip b covers frames
  * starts[b] .. starts[b]+seq-1 (device int64[B]).  The input projection runs once per frame.
- * workspace >= tmr_lstm_workspace_bytes(n_frames, B, D). */
+ * workspace >= tmr_lstm_workspace_bytes(n_frames, B, D).
+ * PRECONDITION (not checked on the device): 0 <= starts[b] and starts[b]+seq <= n_frames for every b
+ * (the recurrence reads projected row starts[b]+t).  Starts need not be distinct or sorted: clips that
+ * share a start each get their own state (tested). */
 int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_frames,
                              const int64_t* starts, int B, int seq, int F, int D, float* out,
                              void* workspace, size_t workspace_bytes, int math_mode, void* stream);
@@ -183,7 +191,12 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
  *                    per (clip, slot) over the slot's own neighbours); with n_irregular_rows = 0 they go
  *                    through the per-clip gather + TimeConv instead;
  *   pb_row_base, pb_rows  bank row range covering slot L-1 of the first regular clip .. slot 0 of the
- *                    last one (pb_rows = 0 when the batch has no regular clip).  Needs L >= 6. */
+ *                    last one (pb_rows = 0 when the batch has no regular clip).  Needs L >= 6.
+ *   feats, feats_f16 feats_f16 = 0: fp32 features (the reference's dtype; converted to fp16 once, on the device);
+ *                    feats_f16 = 1: the caller already holds fp16 features (optional input contract that halves the
+ *                    host->device bytes; bit-identical results, since the MMA operand is the same fp16 value).
+ *   starts must be valid clip starts of the table, in range of feats, ascending (checked by BankInference on
+ *   the host); they need not be distinct. */
 /* The bank-level TimeConv alone: pb[(row - row_base)*7 + v][D] for bank rows row_base .. row_base+pb_rows-1,
  * v = 0 interior slot, 1..3 slot k = 0,1,2, 4..6 slot k = L-1, L-2, L-3 (see tmrnet_b200/csrc/umma_bankconv.cu). */
 size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D);
@@ -193,7 +206,7 @@ size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n
                                              int64_t pb_rows, int L, int D);
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
                               const void* nlblock_packed, const void* classifier_packed,
-                              const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                              const void* feats, int feats_f16, int64_t n_feat_frames, int64_t frame0, const float* bank,
                               int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
                               int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
                               const int64_t* irregular_starts, int n_irregular, const int32_t* irregular_rows,

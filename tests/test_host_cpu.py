@@ -152,17 +152,20 @@ def test_relaxed_boundary_evaluator_hand_cases():
 class _FakeTrainer:
     def __init__(self, lr):
         self.lr = lr
+        self.lstm_lr = lr * 0.1
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_plateau_lr_matches_torch_reduce_on_plateau(seed):
+    """Both reference parameter groups (lr and lr/10, TRAIN:797-805) against torch, through enough reductions
+    that the eps = 1e-8 rule stops the LSTM group one decade before the other group."""
     from tmrnet_b200.train import PlateauLR
     rng = np.random.default_rng(seed)
     # a loss curve that improves, stalls for long stretches, and improves again
     losses = np.concatenate([np.linspace(3, 1, 8), 1.0 + 1e-5 * rng.random(25), np.linspace(0.99, 0.7, 5),
-                             0.7 + 0.05 * rng.random(30), [0.1], 0.1 + rng.random(15)])
-    p = torch.nn.Parameter(torch.zeros(1))
-    opt = torch.optim.SGD([{"params": [p]}], lr=5e-4)
+                             0.7 + 0.05 * rng.random(30), [0.1], 0.1 + rng.random(70)])
+    p, q = torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([{"params": [p]}, {"params": [q], "lr": 5e-5}], lr=5e-4)
     ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "min")
     tr = _FakeTrainer(5e-4)
     mine = PlateauLR(tr)
@@ -170,7 +173,9 @@ def test_plateau_lr_matches_torch_reduce_on_plateau(seed):
         ref.step(float(v))
         mine.step(float(v))
         assert tr.lr == opt.param_groups[0]["lr"]
+        assert tr.lstm_lr == opt.param_groups[1]["lr"]
     assert tr.lr < 5e-4                      # the curve did trigger reductions
+    assert tr.lstm_lr > tr.lr * 0.1 * 0.999 and tr.lr <= 5e-8   # ... down to where the eps rule holds a group back
 
 
 def test_step_lr_matches_torch():

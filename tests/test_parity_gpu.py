@@ -98,6 +98,33 @@ def test_gather_matches_golden_values(golden_dir):
     assert np.array_equal(out.cpu().numpy(), z["long_feature"])
 
 
+def test_gather_invalid_cuda_starts_raise_like_the_reference_dict():
+    """TRAIN:310: dict_start_idx_LFB[start] raises KeyError for a frame that cannot start a clip.  Host starts are
+    checked on the host; CUDA starts by the kernel's status word (no out-of-bounds read either way)."""
+    dev = _dev()
+    lengths, seq, L = [30, 12, 25], 10, 30
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    n_rows = len(idx)
+    bank = torch.from_numpy(synth.bank(n_rows, seed=3)).to(dev)
+    good = torch.tensor([0, 5, 20, 30, 32, 42, 57], device=dev)
+    ref = tb.get_long_feature(good.cpu().numpy(), idx, bank, L)
+    assert torch.equal(tb.get_long_feature(good, idx, bank, L), ref)
+    for bad in (21, 29, 33, 41, 58, 66, 67, 10 ** 9, -1):          # tails of videos, past the end, negative
+        with pytest.raises(KeyError):
+            tb.get_long_feature(torch.tensor([0, bad, 5], device=dev), idx, bank, L)
+        with pytest.raises(KeyError):
+            tb.get_long_feature([0, bad, 5], idx, bank, L)
+    # trusted=True: no read-back; the invalid clip's window is all zeros, its neighbours are untouched
+    out, rows = tb.get_long_feature(torch.tensor([0, 33, 5], device=dev), idx, bank, L, return_rows=True, trusted=True)
+    assert torch.equal(out[1], torch.zeros_like(out[1])) and bool((rows[1] == -2).all())
+    assert torch.equal(out[0], ref[0]) and torch.equal(out[2], ref[1])
+    # a reference-style plain dict (table only reaches its largest key)
+    d = dict(idx)
+    assert torch.equal(tb.get_long_feature(good, d, bank, L), ref)
+    with pytest.raises(KeyError):
+        tb.get_long_feature(torch.tensor([58], device=dev), d, bank, L)
+
+
 def test_gather_zero_pad_mode():
     dev = _dev()
     lengths, seq, L = [25, 14, 40], 10, 12
@@ -279,34 +306,48 @@ def test_lstm_weights_stationary_step(B, contiguous):
     assert torch.equal(got, got_f)                    # same fp16 operands and summation order on both routes
 
 
-def test_lstm_weights_stationary_equals_streamed_engine():
-    """TMR_LSTM_WS=0 routes the same step through the streamed GEMM engine (umma_gemm.cu, EPI_LSTM): same fp16
-    operands, same K order inside one accumulator -> bit-identical h_T.  The switch is read once per process,
-    so each variant runs in its own interpreter."""
+def test_lstm_large_batch_engine_equals_small_batch_engine():
+    """Batches of >= 256 clips take the weights-stationary / persistent recurrence kernels, smaller ones the
+    streamed GEMM engine (umma_gemm.cu, EPI_LSTM): same fp16 operands, same K order inside one accumulator ->
+    bit-identical h_T.  600 clips at once against the same clips in chunks of 200."""
     _need_mode("f16")
-    import hashlib
-    import subprocess
-    import sys
-    code = (
-        "import sys, hashlib, torch, numpy as np\n"
-        f"sys.path.insert(0, {ROOT!r})\n"
-        "import tmrnet_b200 as tb\n"
-        "from tmrnet_b200 import ops, synth\n"
-        "dev = torch.device('cuda:0')\n"
-        "B, seq = 600, 10\n"
-        "feats = torch.from_numpy(synth.features(B + seq + 20, seed=3)).to(dev)\n"
-        "starts = torch.arange(B); starts[301:] += 15\n"
-        "m = tb.resnet_lstm(); m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.head_state_dict(seed=1234).items()}); m = m.to(dev).eval()\n"
-        "h = ops.lstm_last_frames(m.packs()[0], feats, starts.to(dev), seq, 'f16')\n"
-        "print(hashlib.sha256(h.cpu().numpy().tobytes()).hexdigest())\n"
-    )
-    digests = []
-    for ws in ("1", "0"):
-        env = dict(os.environ, TMR_LSTM_WS=ws)
-        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert out.returncode == 0, out.stderr[-2000:]
-        digests.append(out.stdout.strip().splitlines()[-1])
-    assert digests[0] == digests[1]
+    dev = _dev()
+    B, seq = 600, 10
+    feats = torch.from_numpy(synth.features(B + seq + 20, seed=3)).to(dev)
+    starts = torch.arange(B)
+    starts[301:] += 15
+    starts = starts.to(dev)
+    m = _model(7)
+    big = ops.lstm_last_frames(m.packs()[0], feats, starts, seq, "f16")
+    small = torch.cat([ops.lstm_last_frames(m.packs()[0], feats, starts[i:i + 200].contiguous(), seq, "f16")
+                       for i in range(0, B, 200)])
+    assert torch.equal(big, small)
+
+
+def test_lstm_duplicate_and_unsorted_starts():
+    """Clips that share a start frame (and starts in arbitrary order) each get their own state: step 0 rides in the
+    projection's epilogue through a one-clip-per-row table, clips that lose their slot are fixed up
+    (lstm_cell0_fix_kernel).  f16 result of every duplicate == the same clip computed alone, and within
+    tolerance of the fp32 mode / the oracle."""
+    _need_mode("f16")
+    dev = _dev()
+    seq = 10
+    feats_np = synth.features(400, seed=21)
+    feats = torch.from_numpy(feats_np).to(dev)
+    rng = np.random.default_rng(3)
+    for B in (7, 300, 700):
+        st = rng.integers(0, 400 - seq, size=B)
+        st[1] = st[0]; st[B // 2] = st[0]; st[-1] = st[2]            # duplicates, unsorted
+        starts = torch.from_numpy(st).to(dev)
+        m = _model(7)
+        got = ops.lstm_last_frames(m.packs()[0], feats, starts, seq, "f16")
+        uniq, inv = np.unique(st, return_inverse=True)
+        alone = ops.lstm_last_frames(m.packs()[0], feats, torch.from_numpy(uniq).to(dev), seq, "f16")
+        assert torch.equal(got, alone[torch.from_numpy(inv).to(dev)])
+        x = torch.from_numpy(np.stack([feats_np[s:s + seq] for s in st]))
+        assert rel_err(got, orc.lstm_last(x, _sd(7))) < TOL["f16"]
+        got32 = ops.lstm_last_frames(m.packs()[0], feats, starts, seq, "fp32")
+        assert rel_err(got32, orc.lstm_last(x, _sd(7))) < TOL["fp32"]
 
 
 def test_f16_operands_saturate_instead_of_overflowing():
@@ -678,6 +719,169 @@ def test_host_buffer_pass_equals_resident_pass():
     for k in ("logits", "pred", "score"):
         assert torch.equal(out[k], ref[k]), k
     assert torch.equal(pred_h, ref["pred"].cpu()) and torch.equal(score_h, ref["score"].cpu())
+
+
+def test_fp16_host_features_give_bit_identical_results():
+    """Optional input contract: the caller hands fp16 features (half the PCIe bytes).  The tensor-core path rounds
+    fp32 features to fp16 (round-to-nearest) before the MMA anyway, so both contracts give the same bits."""
+    from tmrnet_b200.infer import BankInference
+    _need_mode("f16")
+    dev = _dev()
+    lengths, seq, L, feats, bank = _small_job(seed=6)
+    m = _model(7)
+    idx = tb.LFBIndex.from_lengths(lengths, seq)
+    eng = BankInference(m, idx, seq, L, batch_clips=128, math_mode="f16")
+    b = torch.from_numpy(bank).to(dev)
+    f32 = torch.from_numpy(feats)
+    ref = {k: v.clone() for k, v in eng.run(f32.to(dev), b).items()}
+    got = eng.run(f32.to(dev).half(), b, graph=False)
+    for k in ("logits", "pred", "score"):
+        assert torch.equal(got[k], ref[k]), k
+    out, (pred_h, score_h) = eng.run_host(f32.half().pin_memory(), b)
+    torch.cuda.synchronize()
+    assert torch.equal(out["logits"], ref["logits"]) and torch.equal(pred_h, ref["pred"].cpu())
+    with pytest.raises(TypeError):
+        BankInference(m, idx, seq, L, batch_clips=128, math_mode="fp32").run(f32.to(dev).half(), b)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_video_sharded_bank_level_path_is_bit_identical_to_unsharded(world):
+    """The bench path (bank-level TimeConv, tensor cores) sharded by video with halo rows: concatenated shard
+    outputs == the unsharded pass, bit for bit (what bench.py --gpus N asserts on real ranks)."""
+    _need_mode("f16")
+    from tmrnet_b200.infer import BankInference, VideoShard, shard_videos
+    dev = _dev()
+    seq, L = 10, 30
+    lengths = [157, 12, 140, 9, 133, 210, 45, 95, 11, 64, 118, 300, 77, 52]
+    feats = synth.features(sum(lengths), seed=12)
+    bank = synth.bank(len(synth.clip_starts(lengths, seq)), seed=12)
+    m = _model(7)
+    full = BankInference(m, tb.LFBIndex.from_lengths(lengths, seq), seq, L, math_mode="f16")
+    ref = {k: v.clone() for k, v in full.run(torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)).items()}
+    parts = []
+    for lo, hi in shard_videos(lengths, world):
+        if lo == hi:
+            continue
+        sh = VideoShard(lengths, seq, L, lo, hi)
+        eng = BankInference(m, sh.build_index(), seq, L, math_mode="f16", starts=sh.own_local_starts())
+        f = torch.from_numpy(feats[sh.frame_lo:sh.frame_hi]).to(dev)
+        b = torch.from_numpy(bank[sh.row_lo:sh.row_hi]).to(dev)
+        parts.append({k: v.clone() for k, v in eng.run(f, b).items()})
+    for key in ("logits", "pred", "score"):
+        assert torch.equal(torch.cat([p[key] for p in parts]), ref[key]), key
+
+
+def _report(name, obj):
+    """Numbers the parity tests measure on the B200 (copied into profiles/ by hand after the run)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, name), "w") as f:
+        json.dump(obj, f, indent=1)
+
+
+def test_bench_job_every_clip_against_the_oracle():
+    """BASELINE configs[1] at full size, EVERY clip (83 022) of the bench job (seed 1234, the weights bench.py uses)
+    against the CPU oracle in fp32 (the reference's own precision): logits within 1e-3 of max|ref|, argmax equal
+    wherever the oracle's top-2 margin exceeds the tolerance band, and the number of clips inside the band and of
+    argmax flips reported (gpurun_out/parity_full_job.json).  Also: 8 video shards == the unsharded pass bit for bit."""
+    from tmrnet_b200.infer import BankInference, VideoShard, shard_videos
+    _need_mode("f16")
+    dev = _dev()
+    seq, L, C, seed = 10, 30, 7, 1234
+    lengths = synth.video_lengths(40, seed=seed)
+    index = tb.LFBIndex.from_lengths(lengths, seq)
+    n_clips = len(index)
+    feats = synth.features(sum(lengths), seed=seed)
+    bank = synth.bank(n_clips, seed=seed)
+    m = _model(C, seed)
+    sd = _sd(C, seed)
+    fd, bd = torch.from_numpy(feats).to(dev), torch.from_numpy(bank).to(dev)
+    out = {k: v.clone() for k, v in BankInference(m, index, seq, L, math_mode="f16").run(fd, bd).items()}
+    out32 = BankInference(m, index, seq, L, math_mode="fp32", batch_clips=8192).run(fd, bd)
+    # the oracle over every clip, in chunks (reference window walk: Python dict probes, TRAIN:298-326)
+    starts = synth.clip_starts(lengths, seq)
+    d = orc.build_start_dict(starts.tolist())
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = np.empty((n_clips, C), np.float32)
+    with torch.no_grad():
+        for lo in range(0, n_clips, 4096):
+            s = starts[lo:lo + 4096]
+            x = feats[(s[:, None] + np.arange(seq)[None, :]).reshape(-1)].reshape(len(s), seq, -1)
+            lf = orc.get_long_feature(s, d, bank, L)
+            ref[lo:lo + len(s)] = orc.head(x, lf, sd)[0].numpy()
+    ref_t = torch.from_numpy(ref)
+    scale = float(ref_t.abs().max())
+    err16 = float((out["logits"].cpu() - ref_t).abs().max()) / scale
+    err32 = float((out32["logits"].cpu() - ref_t).abs().max()) / scale
+    top2 = torch.topk(ref_t, 2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    band = 2 * TOL["f16"] * scale
+    inside = margin <= band
+    flips16 = out["pred"].cpu() != ref_t.argmax(1)
+    flips32 = out32["pred"].cpu() != ref_t.argmax(1)
+    rep = {"clips": n_clips, "logits_rel_err_f16": err16, "logits_rel_err_fp32_mode": err32,
+           "max_abs_ref_logit": scale, "margin_band": band, "clips_inside_band": int(inside.sum()),
+           "argmax_flips_f16": int(flips16.sum()), "argmax_flips_f16_outside_band": int((flips16 & ~inside).sum()),
+           "argmax_flips_fp32_mode": int(flips32.sum()), "min_top2_margin": float(margin.min()),
+           "margin_at_f16_flips": [float(v) for v in margin[flips16][:20]]}
+    # 8 video shards (what bench.py --gpus 8 runs on real ranks), emulated one after another
+    parts = []
+    for lo, hi in shard_videos(lengths, 8):
+        sh = VideoShard(lengths, seq, L, lo, hi)
+        eng = BankInference(m, sh.build_index(), seq, L, math_mode="f16", starts=sh.own_local_starts())
+        parts.append({k: v.clone() for k, v in eng.run(fd[sh.frame_lo:sh.frame_hi], bd[sh.row_lo:sh.row_hi]).items()})
+    rep["shards8_logits_bit_identical"] = bool(torch.equal(torch.cat([p["logits"] for p in parts]), out["logits"]))
+    rep["shards8_pred_bit_identical"] = bool(torch.equal(torch.cat([p["pred"] for p in parts]), out["pred"]))
+    _report("parity_full_job.json", rep)
+    assert err32 < TOL["fp32"] * 5, rep          # fp32 CUDA mode vs the fp32 oracle: summation-order noise only
+    assert err16 < TOL["f16"], rep
+    assert rep["argmax_flips_f16_outside_band"] == 0, rep
+    assert rep["argmax_flips_fp32_mode"] == 0 or int((flips32 & ~inside).sum()) == 0, rep
+    assert rep["shards8_pred_bit_identical"] and rep["shards8_logits_bit_identical"], rep
+
+
+def test_f16_operand_range_sweep():
+    """fp16 operands over the dynamic range real inputs may have: backbone features x {1e-3, 1, 10, 100} (post-avgpool
+    ResNet-50 features are O(1-10)), bank rows in (-0.5, 0.5) or pushed to (-1, 1), TimeConv / NLBlock weights x {1, 4}
+    (fine-tuned weights are larger than their initialisers).  Logits against the fp64 oracle, every point within
+    1e-3 of max|ref|; the table goes to gpurun_out/f16_range_sweep.json."""
+    _need_mode("f16")
+    dev = _dev()
+    seq, L, C, B = 10, 30, 7, 192
+    base = synth.head_state_dict(num_class=C, seed=1234)
+    lengths = [700]
+    starts = synth.clip_starts(lengths, seq)
+    pick = starts[np.linspace(0, len(starts) - 1, B).astype(np.int64)]
+    d = orc.build_start_dict(starts.tolist())
+    feats0 = synth.features(sum(lengths), seed=9)
+    rows = []
+    worst = 0.0
+    for wscale in (1.0, 4.0):
+        sd = {k: (v * np.float32(wscale) if k.startswith(("time_conv.", "nl_block.linear")) and k.endswith("weight") else v)
+              for k, v in base.items()}
+        m = tb.resnet_lstm(num_class=C)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        m = m.to(dev).eval()
+        for bscale in (1.0, 1.999):
+            bank = synth.bank(len(starts), seed=9) * np.float32(bscale)
+            lf = orc.get_long_feature(pick, d, bank, L)
+            for fscale in (1e-3, 1.0, 10.0, 100.0):
+                feats = feats0 * np.float32(fscale)
+                x = np.stack([feats[s:s + seq] for s in pick])
+                ref = orc.head(x, lf, sd, dtype=torch.float64)[0]
+                with torch.no_grad():
+                    m.math_mode = "f16"
+                    got = m.predict(torch.from_numpy(x).to(dev), torch.from_numpy(lf).to(dev))[0]
+                    m.math_mode = "fp32"
+                    got32 = m.predict(torch.from_numpy(x).to(dev), torch.from_numpy(lf).to(dev))[0]
+                e16, e32 = rel_err(got, ref), rel_err(got32, ref)
+                flips = int((got.argmax(1).cpu() != ref.argmax(1)).sum())
+                rows.append({"weight_scale": wscale, "bank_scale": bscale, "feature_scale": fscale, "rel_err_f16": e16,
+                             "rel_err_fp32_mode": e32, "argmax_flips_f16": flips, "max_abs_ref_logit": float(ref.abs().max())})
+                worst = max(worst, e16)
+    _report("f16_range_sweep.json", {"B": B, "tolerance": TOL["f16"], "worst_rel_err_f16": worst, "points": rows})
+    assert worst < TOL["f16"], rows
 
 
 def test_bank_builder_is_self_consistent_with_the_head():

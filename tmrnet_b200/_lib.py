@@ -24,7 +24,7 @@ SIGNATURES = {
     "tmr_version": (_i, []),
     "tmr_device_arch": (_i, []),
     "tmr_build_frame2row": (_i, [_p, _i, _i, _p, _p, _p]),
-    "tmr_gather_windows": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "tmr_gather_windows": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "tmr_timeconv_packed_bytes": (_sz, [_i]),
     "tmr_timeconv_pack": (_i, [_p] * 6 + [_i, _p, _p]),
     "tmr_nlblock_packed_bytes": (_sz, [_i]),
@@ -51,7 +51,7 @@ SIGNATURES = {
     "tmr_bankconv_workspace_bytes": (_sz, [_i64, _i]),
     "tmr_bankconv_fwd": (_i, [_p, _p, _i64, _i64, _i64, _i, _p, _p, _sz, _p]),
     "tmr_head_frames_dedup_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i64, _i, _i]),
-    "tmr_head_frames_dedup_fwd": (_i, [_p] * 5 + [_i64, _i64, _p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _p, _i, _i64, _i64]
+    "tmr_head_frames_dedup_fwd": (_i, [_p] * 5 + [_i, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _p, _i, _i64, _i64]
                                   + [_i] * 6 + [_p, _p, _p, _p, _p, _sz, _p]),
     "tmr_head_train_workspace_bytes": (_sz, [_i] * 6),
     "tmr_head_train_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _p, _p, _sz, _p]),
@@ -74,8 +74,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    try:
+        stale = _build.needs_build()          # missing, or older than any csrc/ file or the header
+        have_nvcc = bool(_build.nvcc_path())
+    except RuntimeError:
+        have_nvcc = False
+    if not os.path.exists(LIB_PATH) or (stale and have_nvcc):
         _build.build()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

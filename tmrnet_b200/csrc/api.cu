@@ -108,9 +108,11 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
 }
 
 struct LstmWs { float* xp; float* xr; float* h0; float* h1; float* c; };
+// x_f16: x points to fp16 features (tensor-core mode only): the conversion pass is skipped, the MMA reads them in place
 static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
-                     int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0) {
+                     int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0, bool x_f16 = false) {
   const bool tc = mode == TMR_MATH_F16;
+  TMR_CHECK_ARG(!x_f16 || tc, "lstm: fp16 features need TMR_MATH_F16");
   const float* w = pk;
   const half_t* w16 = mirror16<LstmPacked>(pk);
   // input projection for every row of x once: xp = x Wih'^T + (b_ih + b_hh)', gate-interleaved
@@ -119,6 +121,7 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   g.out = ws.xp; g.ldo = 4 * kD; g.M = n_rows_x; g.N = 4 * kD; g.K = kF;
   g.w16 = w16 + LstmPacked::wih_off;
   g.a_scratch = tc ? reinterpret_cast<half_t*>(ws.xr) : nullptr;
+  if (x_f16) { g.a = nullptr; g.a16 = reinterpret_cast<const half_t*>(x); g.lda = kF; }
   // tensor-core mode, seq > 1: step 0 of the recurrence (zero state) rides in the projection's epilogue.  The
   // row -> clip table lives in the unused half of the fp16-feature slot (n_rows_x x 2048 x 2 of its 4 bytes used).
   const bool fuse0 = tc && seq > 1;
@@ -128,6 +131,8 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
     g.row2clip = row2clip; g.c0 = ws.c; g.h0_16 = reinterpret_cast<half_t*>(ws.h0);
   }
   TMR_TRY(do_linear(g, mode, st));
+  if (fuse0)     // clips sharing a start with another clip lost the table slot: their step 0 runs here
+    TMR_TRY(launch_lstm_cell0_fix(ws.xp, starts, B, n_rows_x, frame0, g.row2clip, ws.c, reinterpret_cast<half_t*>(ws.h0), st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
   // (Running the recurrence in L2-sized sub-batches - all steps of one before the next, so that the projected
   // rows consecutive clips share stay in L2 - was measured slower at every size: the extra pipeline ramps
@@ -230,17 +235,18 @@ int tmr_build_frame2row(const int64_t* lens_host, int V, int seq, int32_t* frame
 
 int tmr_gather_windows(const float* bank, int64_t n_rows, const int32_t* frame2row,
                        const int32_t* frame2vstart, int64_t n_frames, const int64_t* starts, int B,
-                       int L, int D, int pad_mode, float* out, int32_t* rows_out, void* stream) {
+                       int L, int D, int pad_mode, float* out, int32_t* rows_out, int32_t* status,
+                       void* stream) {
   TMR_TRY(check_dims(D));
   TMR_CHECK_ARG(B >= 0 && L >= 1, "gather: bad B=%d L=%d", B, L);
   TMR_CHECK_ARG(pad_mode == TMR_PAD_REPEAT || pad_mode == TMR_PAD_ZERO, "gather: bad pad_mode %d", pad_mode);
   if (B == 0) return TMR_OK;
-  TMR_CHECK_ARG(bank && frame2row && starts && out, "gather: null pointer");
+  TMR_CHECK_ARG(bank && frame2row && starts && (out || rows_out), "gather: null pointer");
   TMR_CHECK_ARG(pad_mode != TMR_PAD_ZERO || frame2vstart, "gather: TMR_PAD_ZERO needs frame2vstart");
   TMR_CHECK_ARG(aligned16(bank) && aligned16(out), "gather: bank/out must be 16-byte aligned");
   TMR_CHECK_ARG(n_rows > 0 && n_frames > 0, "gather: empty bank");
   return launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames, starts, B, L, pad_mode, out,
-                       rows_out, (cudaStream_t)stream);
+                       rows_out, (cudaStream_t)stream, status);
 }
 
 size_t tmr_timeconv_packed_bytes(int D) { return D == kD ? TimeConvPacked::total * sizeof(float) : 0; }
@@ -506,7 +512,7 @@ size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n
 }
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,
                               const void* nlblock_packed, const void* classifier_packed,
-                              const float* feats, int64_t n_feat_frames, int64_t frame0, const float* bank,
+                              const void* feats, int feats_f16, int64_t n_feat_frames, int64_t frame0, const float* bank,
                               int64_t n_rows, const int32_t* frame2row, const int32_t* frame2vstart,
                               int64_t n_frames_total, const int64_t* starts, int B, const int32_t* src_idx,
                               const int64_t* irregular_starts, int n_irregular, const int32_t* irregular_rows,
@@ -559,7 +565,8 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   TMR_CHECK_ARG(ok, "head_frames_dedup: workspace too small (%zu < %zu)", workspace_bytes,
                 tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, n_irregular_rows, pb_rows, L, D));
   float* St = St_out ? St_out : St_ws;
-  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0));
+  TMR_TRY(lstm_impl((const float*)lstm_packed, (const float*)feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0,
+                    feats_f16 != 0));
   if (pb_rows > 0) {
     // fp16 copy of the bank rows the convolutions touch, then one pass of tap products per row
     half_t* bank16 = reinterpret_cast<half_t*>(bank_r);

@@ -35,10 +35,15 @@ __device__ __forceinline__ void stg_na(float4* p, const float4& v) {
 // -------------------------------------------------------------------------------------------
 constexpr int kGatherWarps = 8;
 
+// Memory safety: a start that is not a valid clip start of the table (outside [0, n_frames), or a frame whose
+// table entry is only the "row the reference walk is still remembering": f2r[s] == f2r[s+1]) makes the
+// reference raise KeyError (TRAIN:310).  Here such a clip gets an all-zero window, row indices -2, and bit 0 of
+// *status; a table entry outside [0, n_rows) sets bit 1.  Nothing is ever read out of bounds.
 __global__ void __launch_bounds__(kGatherWarps * 32)
 gather_kernel(const float* __restrict__ bank, int64_t n_rows, const int32_t* __restrict__ f2r,
-              const int32_t* __restrict__ f2v, const int64_t* __restrict__ starts, int64_t total,
-              int L, int pad_mode, float* __restrict__ out, int32_t* __restrict__ rows_out) {
+              const int32_t* __restrict__ f2v, int64_t n_frames, const int64_t* __restrict__ starts, int64_t total,
+              int L, int pad_mode, float* __restrict__ out, int32_t* __restrict__ rows_out,
+              int32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31;
   const int64_t wid0 = (int64_t)blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
   const int64_t stride = (int64_t)gridDim.x * kGatherWarps;
@@ -47,12 +52,20 @@ gather_kernel(const float* __restrict__ bank, int64_t n_rows, const int32_t* __r
     const int k = (int)(w - b * L);
     const int64_t s = starts[b];
     const int64_t key = s - k - 1;
-    int64_t row;
-    if (pad_mode == TMR_PAD_ZERO) {
-      row = (key >= (int64_t)f2v[s]) ? (int64_t)f2r[key] : -1;
+    int64_t row = -2;
+    int bad = 0;
+    if (s < 0 || s >= n_frames) {
+      bad = 1;
     } else {
-      row = (key >= 0) ? (int64_t)f2r[key] : 0;
+      const int32_t own = f2r[s];
+      if (own < 0 || (s + 1 < n_frames && f2r[s + 1] == own)) bad = 1;
     }
+    if (!bad) {
+      if (pad_mode == TMR_PAD_ZERO) row = (key >= (int64_t)f2v[s]) ? (int64_t)f2r[key] : -1;
+      else row = (key >= 0) ? (int64_t)f2r[key] : 0;
+      if (row >= n_rows || row < -1) { bad = 2; row = -2; }
+    }
+    if (bad && status && lane == 0) atomicOr(status, bad);
     if (out) {                                 // out == nullptr: window ROW INDICES only
       float4 v[4];
       if (row >= 0) {
@@ -73,15 +86,15 @@ gather_kernel(const float* __restrict__ bank, int64_t n_rows, const int32_t* __r
 
 int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
                   int64_t n_frames, const int64_t* starts, int B, int L, int pad_mode, float* out,
-                  int32_t* rows_out, cudaStream_t st) {
+                  int32_t* rows_out, cudaStream_t st, int32_t* status) {
   const int64_t total = (int64_t)B * L;
   if (total == 0) return TMR_OK;
   // grid: enough warps to cover the rows, capped at a multiple of the 148 SMs (8 CTAs each)
   int64_t blocks = (total + kGatherWarps - 1) / kGatherWarps;
   const int64_t cap = 148 * 8 * 4;
   if (blocks > cap) blocks = cap;
-  gather_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, st>>>(bank, n_rows, f2r, f2v, starts, total,
-                                                               L, pad_mode, out, rows_out);
+  gather_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, st>>>(bank, n_rows, f2r, f2v, n_frames, starts, total,
+                                                               L, pad_mode, out, rows_out, status);
   TMR_LAUNCH_CHECK("gather_kernel");
   return TMR_OK;
 }
@@ -516,6 +529,42 @@ __global__ void row2clip_kernel(const int64_t* __restrict__ starts, int seq, int
   const int64_t r = starts ? starts[b] - row0 : (int64_t)b * seq;
   if (r >= 0 && r < n_rows) row2clip[r] = b;
 }
+// After the projection whose epilogue ran step 0 for the clips the table names: a clip that LOST its table slot
+// (two clips with the same start: the table holds one clip per projected row) still needs c0 / h0.  One thread per
+// clip compares row2clip[start] with its own id; losers compute the 512 cells from the projected row with the same
+// formula as the fused epilogue (bit-identical c0 / h0).  Distinct starts: one 4-byte load per clip.
+__global__ void lstm_cell0_fix_kernel(const float* __restrict__ xp, const int64_t* __restrict__ starts, int B,
+                                      int64_t n_rows, int64_t row0, const int32_t* __restrict__ row2clip,
+                                      float* __restrict__ c, half_t* __restrict__ h16) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t r = starts[b] - row0;
+  const bool in_range = r >= 0 && r < n_rows;
+  if (in_range && row2clip[r] == b) return;
+  const float4* src = reinterpret_cast<const float4*>(xp + r * (4 * kD));
+  for (int u = 0; u < kD; ++u) {
+    float cn = 0.f, hn = 0.f;
+    if (in_range) {
+      const float4 p = __ldg(src + u);
+      const float a = ex2f_approx(fminf(-1.4426950408889634f * p.x, 40.f));
+      const float d = ex2f_approx(fminf(-2.8853900817779268f * p.z, 40.f));
+      const float e = ex2f_approx(fminf(-1.4426950408889634f * p.w, 40.f));
+      cn = (1.f - d) * rcpf_approx((1.f + a) * (1.f + d));
+      const float f2 = ex2f_approx(fminf(-2.8853900817779268f * cn, 40.f));
+      hn = (1.f - f2) * rcpf_approx((1.f + e) * (1.f + f2));
+    }
+    c[(int64_t)b * kD + u] = cn;
+    h16[(int64_t)b * kD + u] = (half_t)(pack_h2(hn, 0.f) & 0xffffu);
+  }
+}
+int launch_lstm_cell0_fix(const float* xp, const int64_t* starts, int B, int64_t n_rows, int64_t row0,
+                          const int32_t* row2clip, float* c, half_t* h16, cudaStream_t st) {
+  if (B == 0 || !starts) return TMR_OK;           // without starts clip b owns row b * seq: no collisions
+  lstm_cell0_fix_kernel<<<(B + 255) / 256, 256, 0, st>>>(xp, starts, B, n_rows, row0, row2clip, c, h16);
+  TMR_LAUNCH_CHECK("lstm_cell0_fix_kernel");
+  return TMR_OK;
+}
+
 int launch_row2clip(const int64_t* starts, int seq, int B, int64_t n_rows, int64_t row0, int32_t* row2clip, cudaStream_t st) {
   if (n_rows == 0) return TMR_OK;
   TMR_CUDA(cudaMemsetAsync(row2clip, 0xff, sizeof(int32_t) * n_rows, st));          // -1 everywhere

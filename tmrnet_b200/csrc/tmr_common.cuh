@@ -39,6 +39,16 @@ int set_error(int code, const char* fmt, ...);
     if (rc__ != TMR_OK) return rc__; \
   } while (0)
 
+// Experiment switches (pipeline depth, cluster mode, timing ablations) are read from the environment ONLY in
+// builds made with -DTMR_EXPERIMENT (TMR_B200_NVCC_FLAGS=-DTMR_EXPERIMENT python -m tmrnet_b200.build --force);
+// the shipped library ignores the environment, so no variable can change what it computes.
+#ifdef TMR_EXPERIMENT
+#include <stdlib.h>
+inline int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+inline int env_int(const char*, int dflt) { return dflt; }
+#endif
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

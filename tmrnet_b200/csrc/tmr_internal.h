@@ -55,7 +55,7 @@ int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, 
 // ---- memory-bound kernels (kernels_mem.cu) ----
 int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
                   int64_t n_frames, const int64_t* starts, int B, int L, int pad_mode, float* out,
-                  int32_t* rows_out, cudaStream_t st);
+                  int32_t* rows_out, cudaStream_t st, int32_t* status = nullptr);
 // irregular clips of the bank-level path: compact + round the rows their windows touch, assemble their
 // TimeConv from unshifted per-row tap products (umma_bankconv_raw)
 int launch_compact_rows_half(const float* bank, const int32_t* rows, int n, half_t* out, cudaStream_t st);
@@ -77,6 +77,9 @@ int launch_layernorm_relu(const float* v, const float* w, const float* b, int B,
                           int half_out, cudaStream_t st);
 // row2clip[r] = clip whose first frame is projected row r (r = starts[b] - row0, or b * seq without starts), else -1
 int launch_row2clip(const int64_t* starts, int seq, int B, int64_t n_rows, int64_t row0, int32_t* row2clip, cudaStream_t st);
+// clips whose start collides with another clip's (lost the row2clip slot): step 0 from the projected row
+int launch_lstm_cell0_fix(const float* xp, const int64_t* starts, int B, int64_t n_rows, int64_t row0,
+                          const int32_t* row2clip, float* c, half_t* h16, cudaStream_t st);
 // dst[n] = fp16(src[n])
 int launch_to_half(const float* src, half_t* dst, int64_t n, cudaStream_t st);
 // dst[M,K] = fp16([a | a2]) (columns < k_split from a (lda), the rest from a2 (lda2))

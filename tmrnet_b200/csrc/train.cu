@@ -297,7 +297,15 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, const int64_t* 
   for (int c = 1; c < C; ++c) if (l[c] > mx) { mx = l[c]; am = c; }
   float den = 0.f;
   for (int c = 0; c < C; ++c) den += expf(l[c] - mx);
-  const int y = (int)labels[b];
+  const int64_t yl = labels[b];
+  if (yl < 0 || yl >= C) {                 // torch raises here; on the device: no out-of-bounds read, NaN loss / gradient
+    const float nan = __int_as_float(0x7fc00000);
+    for (int c = 0; c < 16; ++c) dlog16[(int64_t)b * 16 + c] = c < C ? nan : 0.f;
+    atomicAdd(loss, nan);
+    if (pred) pred[b] = am;
+    return;
+  }
+  const int y = (int)yl;
   const float w = cw ? cw[y] : 1.f;
   for (int c = 0; c < 16; ++c) dlog16[(int64_t)b * 16 + c] = c < C ? w * (expf(l[c] - mx) / den - (c == y ? 1.f : 0.f)) : 0.f;
   atomicAdd(loss, w * (logf(den) + mx - l[y]));

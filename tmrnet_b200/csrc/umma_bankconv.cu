@@ -370,7 +370,7 @@ int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, 
 static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
   using namespace umma;
   p.num_tiles = ((p.pb_rows + 2 * BC_OUT - 1) / (2 * BC_OUT)) * (kD / BC_NCH);      // a CTA pair emits 2 x 122 rows
-  static const int abl = [] { const char* e = getenv("TMR_BC_ABL"); return e ? atoi(e) : 0; }();
+  static const int abl = env_int("TMR_BC_ABL", 0);
   p.ablate = abl;
   CUtensorMap tx, tw3, tw5, tw7;
   {

@@ -478,11 +478,11 @@ static int launch_gemm(const half_t* a, int64_t lda, const half_t* a2, int64_t l
       const_cast<GemmParams&>(p).x_tma = 1;
     }
   }
-  static const int tlflag = [] { const char* e = getenv("TMR_TIMELINE"); return e ? atoi(e) : 0; }();
+  static const int tlflag = env_int("TMR_TIMELINE", 0);
   const_cast<GemmParams&>(p).timeline = tlflag;
-  static const int lstm_stages = [] { const char* e = getenv("TMR_LSTM_STAGES"); return e ? atoi(e) : 0; }();
+  static const int lstm_stages = env_int("TMR_LSTM_STAGES", 0);
   const_cast<GemmParams&>(p).stages = (EPI == EPI_LSTM) ? lstm_stages : 0;
-  static const int cluster = [] { const char* e = getenv("TMR_GEMM_CLUSTER"); return e ? atoi(e) : 3; }();
+  static const int cluster = env_int("TMR_GEMM_CLUSTER", 3);
   const int64_t m_tiles = (p.M + BM - 1) / BM;
   const int64_t n_tiles = (p.N + BN - 1) / BN;
   if ((cluster == 2 || cluster == 3) && m_tiles >= 2) {
@@ -560,7 +560,7 @@ int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, 
   if (B == 0) return TMR_OK;
   // batches of at least one 256-clip tile: the weights-stationary kernel (umma_lstm_ws.cu); TMR_LSTM_WS=0 keeps
   // the streamed GEMM engine below, which also serves small batches
-  static const int ws = [] { const char* e = getenv("TMR_LSTM_WS"); return e ? atoi(e) : 1; }();
+  static const int ws = env_int("TMR_LSTM_WS", 1);
   if (ws && B >= 256)
     return umma_lstm_step_ws(whh16, xp, starts, seq, t, h_prev, h_out16, h_out, c, B, st, xp_base, xp_rows, xp_row0);
   umma::GemmParams p{};

@@ -288,7 +288,7 @@ int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* start
   if (pps < 1) pps = 1;
   if ((int64_t)pps > p.m_pairs) pps = (int)p.m_pairs;
   p.pairs_per_slice = pps;
-  static const int cfg = [] { const char* e = getenv("TMR_LSTM_WS_CFG"); return e ? atoi(e) : 8; }();
+  static const int cfg = env_int("TMR_LSTM_WS_CFG", 8);
   CUtensorMap ta, tb, tx;
   {
     uint64_t da[2] = {(uint64_t)kD, (uint64_t)B};

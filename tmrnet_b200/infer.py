@@ -73,6 +73,8 @@ class BankInference:
         self.math_mode = math_mode
         if starts is None:       # every clip of the index; a VideoShard passes its owned clips only
             starts = np.fromiter(index.keys(), dtype=np.int64, count=len(index))
+        else:                    # caller-chosen clips: each must be a valid clip start of the index (KeyError otherwise,
+            index.check_starts(np.asarray(starts, dtype=np.int64))      # like the reference's dict probe)
         self.starts_host = np.sort(np.asarray(starts, dtype=np.int64))
         self._ws = None
         self._starts_dev = None
@@ -178,14 +180,14 @@ class BankInference:
         return dict(lib=lib, plan=plan, dedup=dedup, dplan=dplan, dten=dten, ws=self._ws, f2r=f2r, f2v=f2v, mode=mode,
                     packs=self.model.packs(), bank=bank, starts=self._starts_dev)
 
-    def _launch_batch(self, ctx, i, feats_ptr, out, stream):
+    def _launch_batch(self, ctx, i, feats_ptr, out, stream, feats_f16=False):
         """Enqueue batch i; feats_ptr addresses the features of frame plan[i].frame_lo."""
         lo, hi, fl, fh = ctx["plan"][i]
         lib, packs, bank, ws = ctx["lib"], ctx["packs"], ctx["bank"], ctx["ws"]
         Cn = self.model.num_class
         st = out.get("St")
-        common_in = (_ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]),
-                     C.c_void_p(feats_ptr), fh - fl, fl,
+        head_in = (_ptr(packs[0]), _ptr(packs[1]), _ptr(packs[2]), _ptr(packs[3]), C.c_void_p(feats_ptr))
+        common_in = (fh - fl, fl,
                      _ptr(bank), bank.shape[0], _ptr(ctx["f2r"]), _ptr(ctx["f2v"]), ctx["f2r"].numel(),
                      C.c_void_p(ctx["starts"].data_ptr() + lo * 8), hi - lo)
         common_out = (C.c_void_p(out["logits"].data_ptr() + lo * Cn * 4),
@@ -195,12 +197,14 @@ class BankInference:
                       _ptr(ws), ws.numel())
         if ctx["dedup"]:
             d, (src_dev, irr_dev, irr_rows_dev) = ctx["dplan"][i], ctx["dten"][i]
-            check(lib.tmr_head_frames_dedup_fwd(*common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
+            check(lib.tmr_head_frames_dedup_fwd(*head_in, int(feats_f16), *common_in, _ptr(src_dev), _ptr(irr_dev), len(d["irr"]),
                                                 _ptr(irr_rows_dev), len(d["irr_rows"]),
                                                 d["row_base"], d["pb_rows"], self.seq, self.L, F, D, Cn,
                                                 self.pad_mode, *common_out, stream))
         else:
-            check(lib.tmr_head_frames_fwd(*common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
+            if feats_f16:
+                raise TypeError("fp16 features are an input contract of the tensor-core bank-level path only (dedup=True, math 'f16')")
+            check(lib.tmr_head_frames_fwd(*head_in, *common_in, self.seq, self.L, F, D, Cn, self.pad_mode,
                                           *common_out, ctx["mode"], stream))
 
     def run(self, feats, bank, out=None, want_st=False, graph=None):
@@ -210,17 +214,19 @@ class BankInference:
         graph: None (default) - the second pass over the SAME buffers (features, bank, outputs, packed
         weights) is captured into a CUDA graph and later passes replay it (one launch instead of ~55, no
         per-launch tensor-map encoding on the host); True / False force or forbid that."""
-        feats = _dev(feats, "feats")
+        f16 = isinstance(feats, torch.Tensor) and feats.dtype == torch.float16
+        feats = _dev(feats, "feats", torch.float16 if f16 else torch.float32)
         bank = _dev(bank, "bank")
         dev = feats.device
         if out is None:
             out = self._alloc_out(dev, want_st)
         ctx = self._prepare(dev, bank)
+        esz = 2 if f16 else 4
 
         def enqueue():
             stream = _stream()
             for i, (lo, hi, fl, fh) in enumerate(ctx["plan"]):
-                self._launch_batch(ctx, i, feats.data_ptr() + fl * F * 4, out, stream)
+                self._launch_batch(ctx, i, feats.data_ptr() + fl * F * esz, out, stream, f16)
 
         key = (feats.data_ptr(), bank.data_ptr(), tuple(sorted((k, v.data_ptr()) for k, v in out.items())),
                tuple(p.data_ptr() for p in ctx["packs"] if p is not None), ctx["ws"].data_ptr(), ctx["mode"],
@@ -250,9 +256,11 @@ class BankInference:
         (device outputs, (pred_host, score_host))."""
         bank = _dev(bank, "bank")
         dev = bank.device
-        if not (isinstance(feats_host, torch.Tensor) and not feats_host.is_cuda and feats_host.dtype == torch.float32
+        if not (isinstance(feats_host, torch.Tensor) and not feats_host.is_cuda
+                and feats_host.dtype in (torch.float32, torch.float16)
                 and feats_host.dim() == 2 and feats_host.shape[1] == F and feats_host.is_contiguous()):
-            raise TypeError(f"feats_host must be a contiguous CPU float32 tensor (n_frames,{F})")
+            raise TypeError(f"feats_host must be a contiguous CPU float32 (or, optionally, float16) tensor (n_frames,{F})")
+        f16 = feats_host.dtype == torch.float16
         if self.host_batch_clips != self.batch_clips:      # host streaming uses its own (smaller) batches
             if self._host_eng is None:
                 self._host_eng = BankInference(self.model, self.index, self.seq, self.L, self.host_batch_clips,
@@ -264,8 +272,9 @@ class BankInference:
         ctx = self._prepare(dev, bank)
         plan = ctx["plan"]
         max_frames = max((fh - fl for _, _, fl, fh in plan), default=1)
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < max_frames or self._stage[0].device != dev:
-            self._stage = [torch.empty((max_frames, F), dtype=torch.float32, device=dev) for _ in range(3)]
+        if (getattr(self, "_stage", None) is None or self._stage[0].shape[0] < max_frames or self._stage[0].device != dev
+                or self._stage[0].dtype != feats_host.dtype):
+            self._stage = [torch.empty((max_frames, F), dtype=feats_host.dtype, device=dev) for _ in range(3)]
             self._copy_stream = torch.cuda.Stream(device=dev)
         if host_out is None:
             n = len(self.starts_host)
@@ -288,7 +297,7 @@ class BankInference:
                     buf[:fh - fl].copy_(feats_host[fl:fh], non_blocking=True)
                     copied[i].record(self._copy_stream)
                 compute.wait_event(copied[i])
-                self._launch_batch(ctx, i, buf.data_ptr(), out, stream)
+                self._launch_batch(ctx, i, buf.data_ptr(), out, stream, f16)
                 freed[i % 3] = torch.cuda.Event(enable_timing=timed)
                 freed[i % 3].record(compute)
                 if timed:

@@ -9,6 +9,7 @@ torch.Tensor(np.array(..)).to(device) right after, :873-876).
 from __future__ import annotations
 
 import pickle
+import threading
 
 import numpy as np
 import torch
@@ -85,19 +86,22 @@ class LFBIndex(dict):
         return self._dev[device]
 
 
-_dict_cache = {}
+_dict_cache = []                  # [(reference dict, its LFBIndex)]: one entry, swapped atomically
+_dict_cache_lock = threading.Lock()
 
 
 def _as_index(dict_start_idx_LFB):
+    """The reference passes the same plain dict on every call; its device tables are built once.  The
+    reference's DataParallel calls forward from one Python thread per GPU, so the cache is guarded."""
     if isinstance(dict_start_idx_LFB, LFBIndex):
         return dict_start_idx_LFB
-    key = (id(dict_start_idx_LFB), len(dict_start_idx_LFB))
-    hit = _dict_cache.get(key)
-    if hit is None or hit[0] is not dict_start_idx_LFB:
-        _dict_cache.clear()
-        hit = (dict_start_idx_LFB, LFBIndex.from_dict(dict_start_idx_LFB))
-        _dict_cache[key] = hit
-    return hit[1]
+    with _dict_cache_lock:
+        for d, idx in _dict_cache:
+            if d is dict_start_idx_LFB and len(d) == len(idx):
+                return idx
+        idx = LFBIndex.from_dict(dict_start_idx_LFB)
+        _dict_cache[:] = [(dict_start_idx_LFB, idx)]
+        return idx
 
 
 def to_device_bank(lfb, device="cuda"):
@@ -124,7 +128,7 @@ def save_bank(bank, path):
 
 
 def get_long_feature(start_index_list, dict_start_idx_LFB, lfb, LFB_length=LFB_LENGTH_DEFAULT,
-                     pad_mode="repeat", return_rows=False):
+                     pad_mode="repeat", return_rows=False, trusted=False):
     """Past-`LFB_length` window of every clip in `start_index_list` (TRAIN:298-326).
 
     start_index_list: global clip-start frame ids (list / numpy / tensor; e.g. data[2][0::seq]).
@@ -132,11 +136,17 @@ def get_long_feature(start_index_list, dict_start_idx_LFB, lfb, LFB_length=LFB_L
     lfb: the bank, a CUDA fp32 tensor (N,512) (numpy float64 banks are uploaded on every call —
          convert once with to_device_bank()).
     pad_mode 'repeat' = reference semantics; 'zero' = zero rows before the clip's own video
-    (needs an LFBIndex built from_lengths).  Returns a CUDA tensor (B, LFB_length, 512)."""
+    (needs an LFBIndex built from_lengths).  Returns a CUDA tensor (B, LFB_length, 512).
+
+    A frame that cannot start a clip raises KeyError as the reference's dict probe does (TRAIN:310): host
+    starts are checked on the host, CUDA starts by the kernel (its status word is read back: one sync).
+    trusted=True skips the read-back for CUDA starts; invalid starts then yield all-zero windows."""
     index = _as_index(dict_start_idx_LFB)
     bank = lfb if isinstance(lfb, torch.Tensor) and lfb.is_cuda else to_device_bank(lfb)
+    validate = False
     if isinstance(start_index_list, torch.Tensor) and start_index_list.is_cuda:
-        starts = start_index_list.to(device=bank.device, dtype=torch.int64)   # trusted: no host round trip
+        starts = start_index_list.to(device=bank.device, dtype=torch.int64).reshape(-1)
+        validate = not trusted
     else:
         host = np.asarray(start_index_list.cpu() if isinstance(start_index_list, torch.Tensor) else start_index_list,
                           dtype=np.int64).reshape(-1)
@@ -146,4 +156,4 @@ def get_long_feature(start_index_list, dict_start_idx_LFB, lfb, LFB_length=LFB_L
     mode = {"repeat": ops.TMR_PAD_REPEAT, "zero": ops.TMR_PAD_ZERO}[pad_mode]
     if mode == ops.TMR_PAD_ZERO and f2v is None:
         raise ValueError("pad_mode='zero' needs an LFBIndex.from_lengths(...) index (video boundaries)")
-    return ops.gather_windows(bank, f2r, starts, int(LFB_length), f2v, mode, return_rows)
+    return ops.gather_windows(bank, f2r, starts, int(LFB_length), f2v, mode, return_rows, validate=validate)

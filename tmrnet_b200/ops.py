@@ -74,7 +74,10 @@ def build_frame2row(list_each_length, seq: int):
 
 
 def gather_windows(bank, frame2row, starts, L: int, frame2vstart=None, pad_mode=TMR_PAD_REPEAT,
-                   return_rows=False):
+                   return_rows=False, validate=False):
+    """validate=True: the kernel's status word is read back (one sync) and a start that is not a valid clip
+    start of the table raises KeyError like the reference's dict probe (TRAIN:310).  Without it such clips
+    come back as all-zero windows; the kernel never reads out of bounds either way."""
     bank = _dev(bank, "bank")
     frame2row = _dev(frame2row, "frame2row", torch.int32)
     starts = _dev(starts, "starts", torch.int64)
@@ -85,10 +88,22 @@ def gather_windows(bank, frame2row, starts, L: int, frame2vstart=None, pad_mode=
     rows = torch.empty((B, L), dtype=torch.int32, device=bank.device) if return_rows else None
     if frame2vstart is not None:
         frame2vstart = _dev(frame2vstart, "frame2vstart", torch.int32)
+    status = torch.zeros(1, dtype=torch.int32, device=bank.device) if validate else None
     with torch.cuda.device(bank.device):
         check(_lib.load().tmr_gather_windows(_ptr(bank), bank.shape[0], _ptr(frame2row), _ptr(frame2vstart),
                                              frame2row.numel(), _ptr(starts), B, int(L), D, int(pad_mode),
-                                             _ptr(out), _ptr(rows), _stream()))
+                                             _ptr(out), _ptr(rows), _ptr(status), _stream()))
+    if validate:
+        code = int(status.item())
+        if code & 1:
+            n = frame2row.numel()
+            s = starts.clamp(0, max(n - 1, 0))
+            own = frame2row[s]
+            nxt = frame2row[(s + 1).clamp(max=max(n - 1, 0))]
+            bad = (starts < 0) | (starts >= n) | (own < 0) | ((s + 1 < n) & (nxt == own))
+            raise KeyError(int(starts[bad][0]))
+        if code & 2:
+            raise IndexError("frame2row names a bank row outside the bank")
     return (out, rows) if return_rows else out
 
 

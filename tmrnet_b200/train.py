@@ -63,6 +63,7 @@ class HeadTrainer:
         self.grads = FlatBuffer(shapes, dev)
         self.momentum_buf = FlatBuffer(shapes, dev)
         self.lr, self.momentum, self.weight_decay, self.lstm_lr_scale = lr, momentum, weight_decay, lstm_lr_scale
+        self.lstm_lr = lr * lstm_lr_scale       # the reference's second parameter group (TRAIN:797-805); schedulers move both
         self.class_weight = None if class_weight is None else torch.as_tensor(class_weight, dtype=torch.float32, device=dev)
         self.p_nl, self.p_fc, self.seed = float(p_nl), float(p_fc), int(seed)
         self.steps = 0
@@ -86,6 +87,16 @@ class HeadTrainer:
         Cn = self.model.num_class
         if long_feature.shape[0] != B or labels.numel() != B:
             raise ValueError("batch size mismatch between x, long_feature and labels")
+        if self.class_weight is not None and self.class_weight.numel() != Cn:
+            raise ValueError(f"class_weight has {self.class_weight.numel()} entries for {Cn} classes")
+        # parameters may have been moved / reassigned since construction (model.to(), load_state_dict keeps storage)
+        if any(p is not None and p.data_ptr() != int(self._pp[i] or 0) for i, p in enumerate(self.params)):
+            named = dict(self.model.named_parameters())
+            self.params = [named.get(k) for k in PARAM_ORDER]
+            if any(p is not None and (p.device != self.device or p.dtype != torch.float32 or not p.is_contiguous())
+                   for p in self.params):
+                raise RuntimeError("HeadTrainer: parameters moved to another device / dtype after construction")
+            self._pp = (C.c_void_p * 24)(*[p.data_ptr() if p is not None else 0 for p in self.params])
         lib = _lib.load()
         need = lib.tmr_head_train_workspace_bytes(B, seq, L, D, F, Cn)
         if self._ws is None or self._ws.numel() < need:
@@ -114,7 +125,7 @@ class HeadTrainer:
             for i, p in enumerate(self.params):
                 if p is None:
                     continue
-                lr = self.lr * (self.lstm_lr_scale if PARAM_ORDER[i].startswith("lstm.") else 1.0)
+                lr = self.lstm_lr if PARAM_ORDER[i].startswith("lstm.") else self.lr
                 check(lib.tmr_sgd_step(_ptr(p), _ptr(self.grads.views[i]), _ptr(self.momentum_buf.views[i]), p.numel(),
                                        lr, self.momentum, self.weight_decay, first, _stream()))
         self.steps += 1
@@ -164,9 +175,13 @@ class PlateauLR:
             self.cooldown_counter -= 1
             self.num_bad_epochs = 0
         if self.num_bad_epochs > self.patience:
-            new_lr = max(self.trainer.lr * self.factor, self.min_lr)
-            if self.trainer.lr - new_lr > self.eps:
-                self.trainer.lr = new_lr
+            # torch applies the eps rule to every parameter group on its own: the LSTM group (lr/10) stops
+            # decaying one decade before the other group does
+            for attr in ("lr", "lstm_lr"):
+                old = getattr(self.trainer, attr)
+                new_lr = max(old * self.factor, self.min_lr)
+                if old - new_lr > self.eps:
+                    setattr(self.trainer, attr, new_lr)
             self.cooldown_counter = self.cooldown
             self.num_bad_epochs = 0
         return self.trainer.lr
@@ -177,12 +192,14 @@ class StepLR:
 
     def __init__(self, trainer, step_size, gamma=0.1):
         self.trainer, self.step_size, self.gamma = trainer, int(step_size), float(gamma)
-        self.base_lr = trainer.lr
+        self.base_lr, self.base_lstm_lr = trainer.lr, trainer.lstm_lr
         self.last_epoch = 0
 
     def step(self, metric=None):
         self.last_epoch += 1
-        self.trainer.lr = self.base_lr * self.gamma ** (self.last_epoch // self.step_size) if self.step_size > 0 else self.base_lr
+        k = self.gamma ** (self.last_epoch // self.step_size) if self.step_size > 0 else 1.0
+        self.trainer.lr = self.base_lr * k
+        self.trainer.lstm_lr = self.base_lstm_lr * k
         return self.trainer.lr
 
 
