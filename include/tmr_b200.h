@@ -135,6 +135,11 @@ int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_f
                              const int64_t* starts, int B, int seq, int F, int D, float* out,
                              void* workspace, size_t workspace_bytes, int math_mode, void* stream);
 
+/* Stage-1 model surface (code/models.py:38-48: LSTM over the clip, every step's h goes to the 512 -> C fc):
+ * h of ALL steps, time-major out_tm (seq,B,D), fp32 CUDA-core path.  workspace >= tmr_lstm_workspace_bytes(B*seq,B,D). */
+int tmr_lstm_seq_fwd(const void* packed, const float* x, int B, int seq, int F, int D, float* out_tm,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a8 + a9: classifier and eval post-processing (TRAIN:249-252 eval mode, EVAL:122-125,491-493)
  * logits = fc_c(relu(fc_h_c([St || y1]))); score = max softmax probability; pred = first argmax.
  * logits (B,C) fp32, pred int64[B], score fp32[B] (pred/score nullable).
@@ -231,6 +236,19 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
                            const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
                            float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* The same step split at the logits, for torch.autograd: what lets the reference's loop body run unchanged -
+ *   model.train(); outputs = model.forward(inputs, long_feature); loss = criterion(outputs, labels);
+ *   loss.backward(); optimizer.step()                                              (TRAIN:876-887)
+ * with stock torch losses and optimisers (SGD with or without nesterov, Adam; TRAIN:786-805).
+ * tmr_head_train_fwd: training-mode forward, logits (B,C) out, activations saved in `workspace`.
+ * tmr_head_train_bwd: given the SAME workspace (untouched in between), the same params / x / long_feature and
+ * dlogits (B,C), overwrites the 24 grads.  logits_scratch: any (B,C) fp32 buffer. */
+int tmr_head_train_fwd(const float* const* params, const float* x, const float* long_feature, int B, int seq, int L, int F,
+                       int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int tmr_head_train_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                       const float* dlogits, int B, int seq, int L, int F, int D, int C, float* logits_scratch,
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* torch.optim.SGD update on one flat fp32 tensor (momentum, weight decay, dampening 0, no nesterov),
  * TRAIN:797-805,887:  d = g + wd*p ; buf = first_step ? d : momentum*buf + d ; p -= lr*buf. */
 int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,

@@ -212,3 +212,85 @@ def test_per_phase_precision_recall_matches_sklearn():
     p, r = per_phase_precision_recall(labels, preds)
     assert np.allclose(p, metrics.precision_score(labels, preds, average=None, zero_division=0))
     assert np.allclose(r, metrics.recall_score(labels, preds, average=None, zero_division=0))
+
+
+# ------------------------------------------------------------------------------------------
+# 8f-3: checkpoint I/O either side of the path (TRAIN:772-774, 1053; EVAL:443-447; code/models.py)
+# ------------------------------------------------------------------------------------------
+class _RefShapedHead(torch.nn.Module):
+    """A torch module with the attribute layout of the reference's stage-2 `resnet_lstm` (TRAIN:209-230: share, lstm,
+    fc_c, fc_h_c, nl_block, dropout, time_conv) and a stand-in trunk: what the reference's STRICT load
+    (EVAL:443-447) would check our checkpoint against."""
+
+    def __init__(self, C):
+        super().__init__()
+        nn = torch.nn
+        self.share = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4))
+        self.lstm = nn.LSTM(2048, 512, batch_first=True)
+        self.fc_c = nn.Linear(512, C)
+        self.fc_h_c = nn.Linear(1024, 512)
+        self.nl_block = nn.Module()
+        for i in (1, 2, 3, 4):
+            setattr(self.nl_block, f"linear{i}", nn.Linear(512, 512))
+        self.nl_block.layer_norm = nn.LayerNorm([1, 512])
+        self.dropout = nn.Dropout(0.5)
+        self.time_conv = nn.Module()
+        for i, k in ((1, 3), (2, 5), (3, 7)):
+            setattr(self.time_conv, f"timeconv{i}", nn.Conv1d(512, 512, k, padding=k // 2))
+
+
+@pytest.mark.parametrize("C", [6, 7, 8])
+def test_reference_checkpoint_round_trip_is_strict_loadable(tmp_path, C):
+    import tmrnet_b200 as tb
+    ref = _RefShapedHead(C)
+    ref_sd = ref.state_dict()                                   # what torch.save(model.module.state_dict()) holds
+    m = tb.resnet_lstm(num_class=C)
+    m.load_reference_state_dict(ref_sd)                         # strict on the head's keys; share.* kept aside
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    path = str(tmp_path / "latest_model.pth")
+    m.save_reference_checkpoint(path)
+    back = torch.load(path)
+    assert list(back.keys()) == list(ref_sd.keys())             # same keys in the same order
+    fresh = _RefShapedHead(C)
+    fresh.load_state_dict(back, strict=True)                    # EVAL:443-447
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    # a head-only checkpoint (no trunk available) still loads the reference way it is used at TRAIN:774
+    bare = tb.resnet_lstm(num_class=C)
+    bare.load_state_dict(m.state_dict())
+    res = _RefShapedHead(C).load_state_dict(bare.reference_state_dict(), strict=False)
+    assert all(k.startswith("share.") for k in res.missing_keys) and not res.unexpected_keys
+    # wrong class count is an error, as in the reference
+    with pytest.raises(RuntimeError):
+        tb.resnet_lstm(num_class=C + 1).load_reference_state_dict(ref_sd)
+
+
+def test_stage1_checkpoint_feeds_the_head_and_the_stage1_surface():
+    """TRAIN:772-774: the stage-2 model starts from a STAGE-1 checkpoint with strict=False - `share.*` and `lstm.*`
+    match, the stage-1 classifier `fc.*` does not exist in the head.  code/models.py names the trunk `res.*`."""
+    import types
+    import tmrnet_b200 as tb
+    g = torch.Generator().manual_seed(0)
+    stage1 = {"res.0.weight": torch.randn(4, 3, 1, 1, generator=g),
+              "lstm.weight_ih_l0": torch.randn(2048, 2048, generator=g), "lstm.weight_hh_l0": torch.randn(2048, 512, generator=g),
+              "lstm.bias_ih_l0": torch.randn(2048, generator=g), "lstm.bias_hh_l0": torch.randn(2048, generator=g),
+              "fc.weight": torch.randn(7, 512, generator=g), "fc.bias": torch.randn(7, generator=g)}
+    head = tb.resnet_lstm(num_class=7)
+    before = head.fc_c.weight.detach().clone()
+    missing, dropped = head.load_stage1_state_dict(stage1)
+    assert torch.equal(head.lstm.weight_ih_l0, stage1["lstm.weight_ih_l0"]) and torch.equal(head.fc_c.weight, before)
+    assert sorted(dropped) == ["fc.bias", "fc.weight"] and "fc_c.weight" in missing and not any(k.startswith("lstm.") for k in missing)
+    assert list(head.reference_state_dict().keys())[0] == "share.0.weight"      # res.* written back under the scripts' prefix
+    # the stage-1 surface itself: constructor, keys, optimisers of code/models.py
+    args = types.SimpleNamespace(opt=0, lr=5e-4, momentum=0.9, dampening=0, weightdecay=5e-4, nesterov=True, seq=10)
+    s1 = tb.models.resnet_lstm(args, 7)
+    s1.load_reference_state_dict(stage1)
+    assert sorted(s1.state_dict().keys()) == sorted(k for k in stage1 if not k.startswith("res."))
+    assert sorted(s1.reference_state_dict().keys()) == sorted(stage1.keys())
+    opt = s1.get_optimizers()
+    assert isinstance(opt, torch.optim.SGD) and [g["lr"] for g in opt.param_groups] == [5e-4, 5e-4] and opt.defaults["nesterov"]
+    args.opt = 1
+    assert isinstance(s1.get_optimizers(), torch.optim.Adam)
+    with pytest.raises(RuntimeError):
+        s1.train()(torch.zeros(1, 10, 2048))

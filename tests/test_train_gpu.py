@@ -169,3 +169,123 @@ def test_fit_epoch_loop_learns_and_tracks_best():
     m.eval()
     hist2, _ = fit(tr, index, fd, bd, labels, tr_s[:0], va_s, epochs=1, batch_clips=40, L=L)
     assert abs(hist2[0]["val_loss"] - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
+
+
+# ---------------------------------------------------------------------------------------------
+# the boundary: training THROUGH the module with stock torch losses / optimisers (TRAIN:786-805, 876-887)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_timeconv", [True, False])
+def test_module_autograd_gradients_match_reference_graph(monkeypatch, use_timeconv):
+    """model(x, long_feature) records ONE autograd node; loss.backward() fills .grad of every head parameter with the
+    gradient torch autograd gives over the fp64 oracle graph (dropout off: eval mode with autograd on)."""
+    _patch_oracle(monkeypatch)
+    dev, sd, m, x, lf, labels, cw = _setup(use_timeconv=use_timeconv)
+    ref_loss, ref_logits, ref_g = _autograd_reference(sd, x, lf, labels, cw, use_timeconv)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    m.eval()
+    criterion = torch.nn.CrossEntropyLoss(reduction="sum", weight=torch.from_numpy(cw).to(dev))     # TRAIN:780
+    outputs = m.forward(X, LF)
+    assert outputs.requires_grad
+    loss = criterion(outputs, Y)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    for k, prm in m.named_parameters():
+        g, r = prm.grad.cpu().double(), ref_g[k].reshape(prm.shape)
+        scale = float(r.abs().max())
+        if k == "nl_block.linear2.bias":
+            assert float(g.abs().max()) == 0.0
+            continue
+        assert float((g - r).abs().max()) <= 2e-4 * scale + 1e-7, k
+    # a second backward through a fresh forward ACCUMULATES, as autograd does
+    criterion(m.forward(X, LF), Y).backward()
+    k, prm = next(iter(m.named_parameters()))
+    assert torch.allclose(prm.grad.cpu().double(), 2 * ref_g[k].reshape(prm.shape), rtol=1e-3, atol=1e-7)
+    # frozen features: inputs that require grad are refused, not silently ignored
+    with pytest.raises(RuntimeError):
+        m.forward(X.clone().requires_grad_(), LF)
+
+
+def test_reference_loop_body_with_torch_sgd_equals_head_trainer():
+    """Three iterations of the reference's loop body (TRAIN:876-887) on the module with torch.optim.SGD built like
+    TRAIN:797-805 (LSTM group at lr/10, momentum 0.9, weight decay 5e-4) == three HeadTrainer.step() calls."""
+    dev, sd, m, x, lf, labels, cw = _setup(B=10, C=7)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    twin = tb.resnet_lstm(num_class=7, sequence_length=10)
+    twin.load_state_dict(m.state_dict())
+    twin = twin.to(dev)
+    for mod in (m, twin):
+        mod.dropout.p = 0.0
+        mod.nl_block.dropout.p = 0.0
+    lr = 1e-3
+    optimizer = torch.optim.SGD([
+        {"params": m.lstm.parameters()},
+        {"params": m.time_conv.parameters(), "lr": lr},
+        {"params": m.nl_block.parameters(), "lr": lr},
+        {"params": m.fc_h_c.parameters(), "lr": lr},
+        {"params": m.fc_c.parameters(), "lr": lr},
+    ], lr=lr / 10, momentum=0.9, dampening=0, weight_decay=5e-4, nesterov=False)
+    criterion_phase = torch.nn.CrossEntropyLoss(reduction="sum", weight=torch.from_numpy(cw).to(dev))
+    tr = HeadTrainer(twin, lr=lr, momentum=0.9, weight_decay=5e-4, lstm_lr_scale=0.1, class_weight=cw, p_nl=0.0, p_fc=0.0)
+    m.train()
+    for step in range(3):
+        optimizer.zero_grad()
+        outputs_phase = m.forward(X, LF)
+        _, preds_phase = torch.max(outputs_phase.data, 1)
+        loss_phase = criterion_phase(outputs_phase, Y)
+        loss_phase.backward()
+        optimizer.step()
+        loss2, _, pred2 = tr.step(X, LF, Y)
+        assert abs(float(loss_phase) - float(loss2)) <= 1e-5 * abs(float(loss2))
+        assert torch.equal(preds_phase, pred2)
+        for (k, a), (_, b) in zip(m.named_parameters(), twin.named_parameters()):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-8), (step, k)
+    # the inference path sees the updated weights (packed-weight caches follow the parameters' version counters)
+    m.eval()
+    with torch.no_grad():
+        a, b = m(X, LF), twin.eval()(X, LF)
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("opt", ["adam", "nesterov"])
+def test_adam_and_nesterov_branches_train(opt):
+    """optimizer_choice == 1 (Adam, TRAIN:800-805) and use_nesterov (TRAIN:786-799) work through stock torch
+    optimisers on the module's parameters; the loss on a fixed batch falls."""
+    dev, sd, m, x, lf, labels, cw = _setup(B=16, C=7)
+    X, LF, Y = (torch.from_numpy(a).to(dev) for a in (x, lf, labels))
+    if opt == "adam":
+        optimizer = torch.optim.Adam([{"params": m.lstm.parameters()}, {"params": [p for k, p in m.named_parameters()
+                                                                                 if not k.startswith("lstm.")], "lr": 1e-4}], lr=1e-5)
+    else:
+        optimizer = torch.optim.SGD(m.parameters(), lr=1e-4, momentum=0.9, dampening=0, weight_decay=5e-4, nesterov=True)
+    criterion = torch.nn.CrossEntropyLoss(reduction="sum")
+    m.train()
+    m.dropout.p = 0.0
+    m.nl_block.dropout.p = 0.0
+    losses = []
+    for _ in range(6):
+        optimizer.zero_grad()
+        loss = criterion(m(X, LF), Y)
+        loss.backward()
+        optimizer.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_module_training_mode_dropout():
+    dev, sd, m, x, lf, labels, cw = _setup(B=8, C=7)
+    X, LF = torch.from_numpy(x).to(dev), torch.from_numpy(lf).to(dev)
+    m.train()
+    torch.manual_seed(11)
+    m._train_calls = 0
+    a = m(X, LF).detach().clone()
+    b = m(X, LF).detach().clone()
+    assert not torch.equal(a, b)                       # fresh masks per call
+    torch.manual_seed(11)
+    m._train_calls = 0
+    assert torch.equal(m(X, LF).detach(), a)           # reproducible under torch.manual_seed
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(X, LF), m(X, LF)
+    assert torch.equal(e1, e2)
+    g = m(X, LF)                                       # eval + autograd: dropout off, differentiable, fp32 forward
+    assert g.requires_grad and float((g.detach() - e1).abs().max()) < 2e-3 * float(e1.abs().max())

@@ -41,6 +41,7 @@ SIGNATURES = {
     "tmr_lstm_workspace_bytes": (_sz, [_i64, _i, _i]),
     "tmr_lstm_last_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _i, _p]),
     "tmr_lstm_last_frames_fwd": (_i, [_p, _p, _i64, _p, _i, _i, _i, _i, _p, _p, _sz, _i, _p]),
+    "tmr_lstm_seq_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "tmr_classifier_workspace_bytes": (_sz, [_i, _i]),
     "tmr_fc_argmax_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _i, _p]),
     "tmr_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -55,6 +56,8 @@ SIGNATURES = {
                                   + [_i] * 6 + [_p, _p, _p, _p, _p, _sz, _p]),
     "tmr_head_train_workspace_bytes": (_sz, [_i] * 6),
     "tmr_head_train_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _p, _p, _sz, _p]),
+    "tmr_head_train_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _sz, _p]),
+    "tmr_head_train_bwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 6 + [_p, _p, _sz, _p]),
     "tmr_sgd_step": (_i, [_p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, _i, _p]),
     "tmr_linear_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _i, _p]),
 }

@@ -10,6 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtmr_b200.so")
+LIB_EXP = os.path.join(HERE, "libtmr_b200_exp.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -43,11 +44,18 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: libtmr_b200.so cannot be built (there is no CPU fallback)")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiment: bool = False) -> str:
+    """experiment=True builds libtmr_b200_exp.so with -DTMR_EXPERIMENT (environment switches and kernel
+    timelines for the scripts/ measurements) next to the product library, which it never replaces."""
+    if experiment:
+        return _build(LIB_EXP, os.path.join(HERE, "build_exp"), verbose, ["-DTMR_EXPERIMENT"])
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), verbose, [])
+
+
+def _build(LIB: str, tmpdir: str, verbose: bool, extra) -> str:
     objs = []
-    tmpdir = os.path.join(HERE, "build")
     os.makedirs(tmpdir, exist_ok=True)
     nvcc = nvcc_path()
     procs = []
@@ -56,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                "--expt-extended-lambda", "-I", INCLUDE, "-c", src, "-o", obj]
-        cmd[1:1] = os.environ.get("TMR_B200_NVCC_FLAGS", "").split()      # e.g. -DTMR_EPI_PROFILE (experiments)
+        cmd[1:1] = os.environ.get("TMR_B200_NVCC_FLAGS", "").split() + list(extra)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -80,4 +88,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiment="--experiment" in sys.argv))

@@ -142,6 +142,20 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   if (tc) {
     half_t* h16[2] = {reinterpret_cast<half_t*>(ws.h0), reinterpret_cast<half_t*>(ws.h1)};
     if (!fuse0) TMR_TRY(launch_lstm_cell0(xp, starts, seq, out, seq > 1 ? h16[0] : nullptr, ws.c, B, st, true));
+    // Batches of at least one 256-clip tile: ALL recurrent steps in one persistent launch (umma_lstm_persist.cu; c in
+    // registers, h exchanged through L2).  Its per-tile arrival counters sit behind the row -> clip table in the
+    // unused part of the fp16-feature slot.
+    if (fuse0 && B >= 256 && env_int("TMR_LSTM_PERSIST", 1)) {
+      const size_t spare = (size_t)n_rows_x * kF * 2;                       // bytes of ws.xr the fp16 features do not use
+      const size_t table = align_up((size_t)n_rows_x * sizeof(int32_t), 256);
+      const size_t nflags = 2 * (((size_t)B + 255) / 256);
+      if (table + nflags * sizeof(int32_t) <= spare) {
+        int32_t* flags = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws.xr) + (size_t)n_rows_x * kF * 2 + table);
+        const int rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
+                                         ws.xp, n_rows_x, frame0);
+        if (rc != TMR_ERR_UNSUPPORTED) return rc;
+      }
+    }
     for (int t = 1; t < seq; ++t) {
       const bool last = (t == seq - 1);
       TMR_TRY(umma_lstm_step(w16 + LstmPacked::whh_off, xp, starts, seq, t, h16[(t - 1) & 1], last ? nullptr : h16[t & 1],
@@ -367,6 +381,31 @@ int tmr_lstm_last_frames_fwd(const void* packed, const float* feats, int64_t n_f
   TMR_CHECK_ARG(B == 0 || starts, "lstm_frames: starts is null");
   return lstm_entry(packed, feats, n_frames, starts, B, seq, F, D, out, workspace, workspace_bytes,
                     math_mode, stream);
+}
+
+/* Stage-1 surface (code/models.py:38-48): h of EVERY step, time-major out_tm[t][b][:] (fp32 CUDA-core path). */
+int tmr_lstm_seq_fwd(const void* packed, const float* x, int B, int seq, int F, int D, float* out_tm,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  TMR_TRY(check_dims(D, F));
+  TMR_CHECK_ARG(B >= 0 && seq >= 1, "lstm_seq: bad B=%d seq=%d", B, seq);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(packed && x && out_tm && workspace, "lstm_seq: null pointer");
+  TMR_CHECK_ARG(aligned16(x) && aligned16(out_tm) && aligned16(workspace) && aligned16(packed), "lstm_seq: pointers must be 16-byte aligned");
+  Carver cv(workspace, workspace_bytes);
+  LstmWs ws;
+  TMR_CHECK_ARG(carve_lstm(cv, (int64_t)B * seq, B, ws), "lstm_seq: workspace too small (%zu < %zu)", workspace_bytes,
+                tmr_lstm_workspace_bytes((int64_t)B * seq, B, D));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)packed;
+  LinearArgs g;
+  g.a = x; g.lda = kF; g.w = pk + LstmPacked::wih_off; g.ldw = kF; g.bias = pk + LstmPacked::bias_off;
+  g.out = ws.xp; g.ldo = 4 * kD; g.M = (int64_t)B * seq; g.N = 4 * kD; g.K = kF;
+  TMR_TRY(simt_linear(g, st));
+  const size_t step = (size_t)B * kD;
+  TMR_TRY(launch_lstm_cell0(ws.xp, nullptr, seq, out_tm, nullptr, ws.c, B, st, false));
+  for (int t = 1; t < seq; ++t)
+    TMR_TRY(simt_lstm_step(pk + LstmPacked::whh_off, ws.xp, nullptr, seq, t, out_tm + (t - 1) * step, out_tm + t * step, ws.c, B, st));
+  return TMR_OK;
 }
 
 size_t tmr_classifier_workspace_bytes(int B, int D) { return 3 * fbytes((size_t)(B > 0 ? B : 1) * D); }

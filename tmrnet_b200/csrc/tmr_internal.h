@@ -47,6 +47,11 @@ int umma_lstm_step(const half_t* whh16, const float* xp, const int64_t* starts, 
 int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* starts, int seq, int t,
                       const half_t* h_prev, half_t* h_out16, float* h_out, float* c, int B, cudaStream_t st,
                       const float* xp_base, int64_t xp_rows, int64_t xp_row0);
+// all recurrent steps 1 .. seq-1 in one persistent launch (umma_lstm_persist.cu); TMR_ERR_UNSUPPORTED when the
+// device cannot keep a group of 8 CTA pairs resident
+int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* starts, int seq, half_t* h16a, half_t* h16b,
+                      float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st, const float* xp_base,
+                      int64_t xp_rows, int64_t xp_row0);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,

@@ -360,18 +360,34 @@ size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C
   return n + (1 << 16);
 }
 
-/* Forward (training mode) + backward of the head for one batch.  params/grads: 24 device pointers in
- * the order documented at the top of train.cu (timeconv entries may be NULL for the NL-only wiring).
- * x (B,seq,F) features, long_feature (B,L,D), labels int64[B], class_weight float[C] or NULL.
- * Dropout p_nl (NLBlock, 0.2 in the reference) and p_fc (0.5) with a counter-based mask from `seed`.
- * Outputs: grads (overwritten), logits (B,C), loss (1 float, sum-reduced), pred int64[B] (nullable). */
-int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
-                           const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
-                           float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+/* Forward (training mode) + loss + backward of the head for one batch, as phases over ONE workspace layout
+ * (the carving below is identical whatever the phase, so activations saved by a forward-only call are found
+ * again by a later backward-only call on the same workspace):
+ *   PH_FWD   features, window -> logits (saves gates / c / h of all steps, TimeConv branch winners, softmax p,
+ *            LayerNorm xhat / rstd, dropout masks)
+ *   PH_LOSS  CrossEntropyLoss(reduction='sum'[, weight]) and its dlogits
+ *   PH_BWD   dlogits -> grads of the 24 parameters (overwritten, not accumulated)
+ * dlogits_ext (B,C): the caller's gradient w.r.t. the logits (autograd) instead of the built-in loss. */
+enum { PH_FWD = 1, PH_LOSS = 2, PH_BWD = 4 };
+
+__global__ void pad_dlogits_kernel(const float* __restrict__ d, int B, int C, float* __restrict__ d16) {
+  const int64_t n = (int64_t)B * 16;
+  GRID_STRIDE(i, n) { const int64_t b = i / 16; const int c = (int)(i % 16); d16[i] = c < C ? d[b * C + c] : 0.f; }
+}
+
+static int train_impl(int phase, const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                      const int64_t* labels, const float* class_weight, const float* dlogits_ext, int B, int seq, int L,
+                      int F, int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   TMR_CHECK_ARG(D == kD && F == kF, "train: D/F unsupported");
   TMR_CHECK_ARG(B >= 1 && seq >= 1 && L >= 1 && C >= 1 && C <= 16, "train: bad sizes (C <= 16)");
-  TMR_CHECK_ARG(params && grads && x && long_feature && labels && logits && loss && workspace, "train: null pointer");
+  TMR_CHECK_ARG(params && x && long_feature && logits && workspace, "train: null pointer");
+  TMR_CHECK_ARG(!(phase & PH_LOSS) || (labels && loss), "train: loss phase needs labels and loss");
+  TMR_CHECK_ARG(!(phase & PH_BWD) || grads, "train: backward phase needs grads");
+  TMR_CHECK_ARG(!(phase & PH_BWD) || (phase & PH_LOSS) || dlogits_ext, "train: backward phase needs the loss phase or dlogits");
+  const bool do_fwd = phase & PH_FWD, do_loss = phase & PH_LOSS, do_bwd = phase & PH_BWD;
   cudaStream_t st = (cudaStream_t)stream;
   const bool has_tc = params[4] != nullptr;
   const int S = seq;
@@ -380,83 +396,101 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
   Ws w{(char*)workspace, workspace_bytes};
 #define TAKE(name, n) float* name = w.f(n); TMR_CHECK_ARG(name, "train: workspace too small at " #name)
   const float *Wih = params[0], *Whh = params[1];
+  // ---- the whole workspace layout, phase-independent ----
   TAKE(x_tm, (size_t)T * kF); TAKE(bsum, 4 * kD); TAKE(xp, (size_t)T * 4 * kD); TAKE(hh, (size_t)B * 4 * kD);
   TAKE(gates, (size_t)T * 4 * kD); TAKE(cst, (size_t)T * kD); TAKE(hst, (size_t)T * kD);
-  // ---------------- forward: LSTM ----------------
-  permute_bsf_kernel<<<nblk(T * kF), 256, 0, st>>>(x, B, S, kF, x_tm);
-  add_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(params[2], params[3], bsum, 4 * kD);
-  TMR_TRY(gemm_nt(x_tm, kF, Wih, kF, bsum, xp, 4 * kD, T, 4 * kD, kF, st));
-  for (int t = 0; t < S; ++t) {
-    if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st));
-    lstm_cell_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(xp + (size_t)t * B * 4 * kD, t > 0 ? hh : nullptr,
-                                                               t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
-                                                               gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
-                                                               hst + (size_t)t * B * kD, B);
-  }
-  const float* St = hst + (size_t)(S - 1) * B * kD;
-  // ---------------- forward: TimeConv ----------------
-  const float* Lt = long_feature;
-  float *c3 = nullptr, *c5 = nullptr, *c7 = nullptr, *Ltb = nullptr, *shiftb = nullptr;
+  float *c3 = nullptr, *c5 = nullptr, *c7 = nullptr, *Ltb = nullptr, *shiftb = nullptr, *wtap = nullptr;
   uint8_t* branch = nullptr;
-  float* convs[3] = {nullptr, nullptr, nullptr};
   if (has_tc) {
     c3 = w.f((size_t)R * kD); c5 = w.f((size_t)R * kD); c7 = w.f((size_t)R * kD); Ltb = w.f((size_t)R * kD);
-    shiftb = w.f((size_t)R * kD); branch = (uint8_t*)w.f((size_t)R * kD / 4 + 64);
-    TMR_CHECK_ARG(c3 && c5 && c7 && Ltb && shiftb && branch, "train: workspace too small (timeconv)");
-    convs[0] = c3; convs[1] = c5; convs[2] = c7;
-    TAKE(wtap, (size_t)kD * kD);
-    for (int ci = 0; ci < 3; ++ci) {         // conv_K = bias + sum_j shift_j(x) . W_K[:,:,j]^T  (tap matrices gathered from (D,D,K))
-      const int K = 3 + 2 * ci, h = K / 2;
-      const float* Wk = params[4 + 2 * ci];
-      for (int j = 0; j < K; ++j) {
-        // wtap[o][c] = Wk[o][c][j]  (strided gather = transpose_pad of a (D*D) x K matrix column j)
-        transpose_pad_kernel<<<dim3(1, (unsigned)((kD * kD + 31) / 32)), dim3(32, 8), 0, st>>>(Wk + j, (int64_t)kD * kD, 1, K, wtap, (int64_t)kD * kD);
-        shift_rows_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, L, j - h, R * kD, shiftb);
-        LinearArgs g; g.a = shiftb; g.lda = kD; g.w = wtap; g.ldw = kD; g.bias = j == 0 ? params[5 + 2 * ci] : nullptr;
-        g.residual = j == 0 ? nullptr : convs[ci]; g.ldr = kD; g.out = convs[ci]; g.ldo = kD; g.M = R; g.N = kD; g.K = kD;
-        TMR_TRY(simt_linear(g, st));
-      }
-    }
-    timeconv_max_train_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, c3, c5, c7, L, R * kD, Ltb, branch);
-    Lt = Ltb;
+    shiftb = w.f((size_t)R * kD); branch = (uint8_t*)w.f((size_t)R * kD / 4 + 64); wtap = w.f((size_t)kD * kD);
+    TMR_CHECK_ARG(c3 && c5 && c7 && Ltb && shiftb && branch && wtap, "train: workspace too small (timeconv)");
   }
-  // ---------------- forward: NLBlock ----------------
   TAKE(W1T, (size_t)kD * kD); TAKE(W2T, (size_t)kD * kD); TAKE(W3T, (size_t)kD * kD); TAKE(W4T, (size_t)kD * kD);
   TAKE(WhT, (size_t)2 * kD * kD); TAKE(WhhT, (size_t)kD * 4 * kD); TAKE(WcT, (size_t)kD * 16);
+  TAKE(q, (size_t)B * kD); TAKE(u, (size_t)B * kD); TAKE(pbuf, (size_t)B * L); TAKE(abar, (size_t)B * kD);
+  TAKE(v, (size_t)B * kD); TAKE(xhat, (size_t)B * kD); TAKE(rstd, B); TAKE(nrm, (size_t)B * kD); TAKE(r, (size_t)B * kD);
+  TAKE(o, (size_t)B * kD); TAKE(od, (size_t)B * kD); TAKE(m1, (size_t)B * kD); TAKE(cat, (size_t)B * 2 * kD);
+  TAKE(z0, (size_t)B * kD); TAKE(z1, (size_t)B * kD); TAKE(m2, (size_t)B * kD); TAKE(z, (size_t)B * kD);
+  TAKE(dlog16, (size_t)B * 16);
+  TAKE(tA, (size_t)2 * kD * Bp); TAKE(tB, (size_t)2 * kD * Bp); TAKE(tC, (size_t)16 * Bp);
+  TAKE(dz, (size_t)B * kD); TAKE(dz0, (size_t)B * kD); TAKE(dcat, (size_t)B * 2 * kD); TAKE(dSt, (size_t)B * kD);
+  TAKE(dod, (size_t)B * kD); TAKE(dr, (size_t)B * kD); TAKE(dv, (size_t)B * kD); TAKE(dabar, (size_t)B * kD);
+  TAKE(du, (size_t)B * kD); TAKE(dq, (size_t)B * kD); TAKE(dsb, (size_t)B * L); TAKE(tmpBD, (size_t)B * kD);
+  float *dLt = nullptr, *d3 = nullptr, *d5 = nullptr, *d7 = nullptr, *dcT = nullptr, *shT = nullptr, *tap = nullptr;
+  if (has_tc) {
+    dLt = w.f((size_t)R * kD); d3 = w.f((size_t)R * kD); d5 = w.f((size_t)R * kD); d7 = w.f((size_t)R * kD);
+    dcT = w.f((size_t)kD * Rp); shT = w.f((size_t)kD * Rp); tap = w.f((size_t)kD * kD);
+    TMR_CHECK_ARG(dLt && d3 && d5 && d7 && dcT && shT && tap, "train: workspace too small (timeconv backward)");
+  }
+  TAKE(dpre, (size_t)T * 4 * kD); TAKE(dc, (size_t)B * kD); TAKE(dh, (size_t)B * kD);
+  TAKE(dpT, (size_t)4 * kD * Tp); TAKE(opT, (size_t)kF * Tp);
+  const float* St = hst + (size_t)(S - 1) * B * kD;
+  const float* Lt = has_tc ? Ltb : long_feature;
+  float* convs[3] = {c3, c5, c7};
+
+  if (do_fwd) {
+    // ---------------- forward: LSTM ----------------
+    permute_bsf_kernel<<<nblk(T * kF), 256, 0, st>>>(x, B, S, kF, x_tm);
+    add_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(params[2], params[3], bsum, 4 * kD);
+    TMR_TRY(gemm_nt(x_tm, kF, Wih, kF, bsum, xp, 4 * kD, T, 4 * kD, kF, st));
+    for (int t = 0; t < S; ++t) {
+      if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st));
+      lstm_cell_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(xp + (size_t)t * B * 4 * kD, t > 0 ? hh : nullptr,
+                                                                 t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
+                                                                 gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
+                                                                 hst + (size_t)t * B * kD, B);
+    }
+    // ---------------- forward: TimeConv ----------------
+    if (has_tc) {
+      for (int ci = 0; ci < 3; ++ci) {         // conv_K = bias + sum_j shift_j(x) . W_K[:,:,j]^T  (tap matrices gathered from (D,D,K))
+        const int K = 3 + 2 * ci, h = K / 2;
+        const float* Wk = params[4 + 2 * ci];
+        for (int j = 0; j < K; ++j) {
+          // wtap[o][c] = Wk[o][c][j]  (strided gather = transpose_pad of a (D*D) x K matrix column j)
+          transpose_pad_kernel<<<dim3(1, (unsigned)((kD * kD + 31) / 32)), dim3(32, 8), 0, st>>>(Wk + j, (int64_t)kD * kD, 1, K, wtap, (int64_t)kD * kD);
+          shift_rows_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, L, j - h, R * kD, shiftb);
+          LinearArgs g; g.a = shiftb; g.lda = kD; g.w = wtap; g.ldw = kD; g.bias = j == 0 ? params[5 + 2 * ci] : nullptr;
+          g.residual = j == 0 ? nullptr : convs[ci]; g.ldr = kD; g.out = convs[ci]; g.ldo = kD; g.M = R; g.N = kD; g.K = kD;
+          TMR_TRY(simt_linear(g, st));
+        }
+      }
+      timeconv_max_train_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, c3, c5, c7, L, R * kD, Ltb, branch);
+    }
+    // ---------------- forward: NLBlock ----------------
+    TMR_TRY(transpose_pad(params[12], kD, kD, kD, W2T, kD, st));
+    TMR_TRY(gemm_nt(St, kD, params[10], kD, params[11], q, kD, B, kD, kD, st));            // q = St W1^T + b1
+    TMR_TRY(gemm_nt(q, kD, W2T, kD, nullptr, u, kD, B, kD, kD, st));                       // u = W2^T q
+    attention_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, B, L, scale, pbuf, abar);
+    TMR_TRY(gemm_nt(abar, kD, params[14], kD, params[15], v, kD, B, kD, kD, st));          // v = W3 abar + b3
+    layernorm_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, params[18], params[19], B, xhat, rstd, nrm, r);
+    TMR_TRY(gemm_nt(r, kD, params[16], kD, params[17], o, kD, B, kD, kD, st));             // o = W4 r + b4
+    dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(o, p_nl, seed * 2 + 1, (int64_t)B * kD, od, m1);
+    make_cat_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(St, od, B, cat);
+    // ---------------- forward: classifier ----------------
+    TMR_TRY(gemm_nt(cat, 2 * kD, params[20], 2 * kD, params[21], z0, kD, B, kD, 2 * kD, st));
+    dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z0, p_fc, seed * 2 + 2, (int64_t)B * kD, z1, m2);
+    relu_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z1, z, (int64_t)B * kD);
+    TMR_TRY(gemm_nt(z, kD, params[22], kD, params[23], logits, C, B, C, kD, st));
+    TMR_LAUNCH_CHECK("train forward");
+  }
+  if (do_loss) {
+    TMR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    ce_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(logits, labels, class_weight, B, C, dlog16, loss, pred);
+    TMR_LAUNCH_CHECK("train loss");
+  }
+  if (!do_bwd) return TMR_OK;
+  if (!do_loss) pad_dlogits_kernel<<<nblk((int64_t)B * 16), 256, 0, st>>>(dlogits_ext, B, C, dlog16);
+
+  // weight transposes the backward GEMMs read (recomputed here: the weights cannot have changed since the forward,
+  // autograd's version counters check that)
   TMR_TRY(transpose_pad(params[10], kD, kD, kD, W1T, kD, st));
-  TMR_TRY(transpose_pad(params[12], kD, kD, kD, W2T, kD, st));
   TMR_TRY(transpose_pad(params[14], kD, kD, kD, W3T, kD, st));
   TMR_TRY(transpose_pad(params[16], kD, kD, kD, W4T, kD, st));
   TMR_TRY(transpose_pad(params[20], kD, 2 * kD, 2 * kD, WhT, kD, st));       // (D,2D) -> (2D, D)
   TMR_TRY(transpose_pad(Whh, 4 * kD, kD, kD, WhhT, 4 * kD, st));             // (4D,D) -> (D, 4D)
   TMR_TRY(transpose_pad(params[22], C, kD, kD, WcT, 16, st));                // (C,D)  -> (D, 16) zero padded
-  TAKE(q, (size_t)B * kD); TAKE(u, (size_t)B * kD); TAKE(pbuf, (size_t)B * L); TAKE(abar, (size_t)B * kD);
-  TAKE(v, (size_t)B * kD); TAKE(xhat, (size_t)B * kD); TAKE(rstd, B); TAKE(nrm, (size_t)B * kD); TAKE(r, (size_t)B * kD);
-  TAKE(o, (size_t)B * kD); TAKE(od, (size_t)B * kD); TAKE(m1, (size_t)B * kD); TAKE(cat, (size_t)B * 2 * kD);
-  TAKE(z0, (size_t)B * kD); TAKE(z1, (size_t)B * kD); TAKE(m2, (size_t)B * kD); TAKE(z, (size_t)B * kD);
-  TMR_TRY(gemm_nt(St, kD, params[10], kD, params[11], q, kD, B, kD, kD, st));            // q = St W1^T + b1
-  TMR_TRY(gemm_nt(q, kD, W2T, kD, nullptr, u, kD, B, kD, kD, st));                       // u = W2^T q
-  attention_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, B, L, scale, pbuf, abar);
-  TMR_TRY(gemm_nt(abar, kD, params[14], kD, params[15], v, kD, B, kD, kD, st));          // v = W3 abar + b3
-  layernorm_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, params[18], params[19], B, xhat, rstd, nrm, r);
-  TMR_TRY(gemm_nt(r, kD, params[16], kD, params[17], o, kD, B, kD, kD, st));             // o = W4 r + b4
-  dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(o, p_nl, seed * 2 + 1, (int64_t)B * kD, od, m1);
-  make_cat_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(St, od, B, cat);
-  // ---------------- forward: classifier + loss ----------------
-  TMR_TRY(gemm_nt(cat, 2 * kD, params[20], 2 * kD, params[21], z0, kD, B, kD, 2 * kD, st));
-  dropout_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z0, p_fc, seed * 2 + 2, (int64_t)B * kD, z1, m2);
-  relu_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(z1, z, (int64_t)B * kD);
-  TMR_TRY(gemm_nt(z, kD, params[22], kD, params[23], logits, C, B, C, kD, st));
-  TAKE(dlog16, (size_t)B * 16);
-  TMR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  ce_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(logits, labels, class_weight, B, C, dlog16, loss, pred);
-  TMR_LAUNCH_CHECK("train forward");
-
   // ---------------- backward: classifier ----------------
-  TAKE(tA, (size_t)2 * kD * Bp); TAKE(tB, (size_t)2 * kD * Bp); TAKE(tC, (size_t)16 * Bp);
-  TAKE(dz, (size_t)B * kD); TAKE(dz0, (size_t)B * kD); TAKE(dcat, (size_t)B * 2 * kD); TAKE(dSt, (size_t)B * kD);
-  TAKE(dod, (size_t)B * kD); TAKE(dr, (size_t)B * kD); TAKE(dv, (size_t)B * kD); TAKE(dabar, (size_t)B * kD);
-  TAKE(du, (size_t)B * kD); TAKE(dq, (size_t)B * kD); TAKE(dsb, (size_t)B * L); TAKE(tmpBD, (size_t)B * kD);
   // dWc = dlogits^T z ; dbc ; dz = dlogits Wc
   TMR_TRY(transpose_pad(dlog16, B, 16, 16, tC, Bp, st));                                  // (16, Bp)
   TMR_TRY(transpose_pad(z, B, kD, kD, tA, Bp, st));                                       // (D, Bp)
@@ -488,8 +522,6 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
   TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[14], kD, kD, kD, (int)Bp, st));           // dW3 = dv^T abar
   TMR_TRY(colsum(dv, nullptr, B, kD, kD, grads[15], 0, st));
   TMR_TRY(gemm_nt(dv, kD, W3T, kD, nullptr, dabar, kD, B, kD, kD, st));                    // dabar = dv W3
-  float* dLt = nullptr;
-  if (has_tc) { dLt = w.f((size_t)R * kD); TMR_CHECK_ARG(dLt, "train: workspace too small (dLt)"); }
   attention_train_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, pbuf, dabar, B, L, scale, dsb, du, dLt);
   // u = W2^T q : dq = du W2^T (out[b,i] = sum_j du[b,j] W2[i][j]) ; dW2 = q^T du ; db2 = 0
   TMR_TRY(gemm_nt(du, kD, params[12], kD, nullptr, dq, kD, B, kD, kD, st));
@@ -506,8 +538,6 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
   axpy_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(tmpBD, dSt, (int64_t)B * kD);
   // ---------------- backward: TimeConv (weights only; the bank has no gradient) ----------------
   if (has_tc) {
-    TAKE(d3, (size_t)R * kD); TAKE(d5, (size_t)R * kD); TAKE(d7, (size_t)R * kD);
-    TAKE(dcT, (size_t)kD * Rp); TAKE(shT, (size_t)kD * Rp); TAKE(tap, (size_t)kD * kD);
     conv_route_kernel<<<nblk(R * kD), 256, 0, st>>>(dLt, branch, R * kD, d3, d5, d7);
     float* dcs[3] = {d3, d5, d7};
     for (int ci = 0; ci < 3; ++ci) {
@@ -523,7 +553,6 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
     }
   }
   // ---------------- backward: LSTM (BPTT) ----------------
-  TAKE(dpre, (size_t)T * 4 * kD); TAKE(dc, (size_t)B * kD); TAKE(dh, (size_t)B * kD);
   zero_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dc, (int64_t)B * kD);
   copy_vec_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dSt, dh, (int64_t)B * kD);
   for (int t = S - 1; t >= 0; --t) {
@@ -532,7 +561,6 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
                                                                dpre + (size_t)t * B * 4 * kD, B);
     if (t > 0) TMR_TRY(gemm_nt(dpre + (size_t)t * B * 4 * kD, 4 * kD, WhhT, 4 * kD, nullptr, dh, kD, B, kD, 4 * kD, st));   // dh_{t-1} = dpre_t Whh
   }
-  TAKE(dpT, (size_t)4 * kD * Tp); TAKE(opT, (size_t)kF * Tp);
   TMR_TRY(transpose_pad(dpre, T, 4 * kD, 4 * kD, dpT, Tp, st));                              // (4D, Tp)
   TMR_TRY(transpose_pad(x_tm, T, kF, kF, opT, Tp, st));                                      // (F, Tp)
   TMR_TRY(gemm_nt(dpT, Tp, opT, Tp, nullptr, grads[0], kF, 4 * kD, kF, (int)Tp, st));        // dWih = dpre^T X
@@ -549,6 +577,39 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
   TMR_LAUNCH_CHECK("train backward");
 #undef TAKE
   return TMR_OK;
+}
+
+extern "C" {
+
+/* One call: forward (training mode) + CrossEntropyLoss(sum[, weight]) + backward.  params/grads: 24 device pointers in
+ * the order documented at the top of train.cu (timeconv entries may be NULL for the NL-only wiring).
+ * x (B,seq,F) features, long_feature (B,L,D), labels int64[B], class_weight float[C] or NULL.
+ * Dropout p_nl (NLBlock, 0.2 in the reference) and p_fc (0.5) with a counter-based mask from `seed`.
+ * Outputs: grads (overwritten), logits (B,C), loss (1 float, sum-reduced), pred int64[B] (nullable). */
+int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                           const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
+                           float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return train_impl(PH_FWD | PH_LOSS | PH_BWD, params, grads, x, long_feature, labels, class_weight, nullptr, B, seq, L, F, D, C,
+                    p_nl, p_fc, seed, logits, loss, pred, workspace, workspace_bytes, stream);
+}
+
+/* The same step split at the logits, for torch.autograd (tmrnet_b200.modules: model.train(); out = model(x, lf);
+ * loss = criterion(out, y); loss.backward(); optimizer.step() - the reference's loop body, TRAIN:876-887):
+ * tmr_head_train_fwd saves its activations in `workspace`; tmr_head_train_bwd, given the SAME workspace (untouched
+ * in between), the same params / x / long_feature and dlogits (B,C), overwrites grads. */
+int tmr_head_train_fwd(const float* const* params, const float* x, const float* long_feature, int B, int seq, int L, int F,
+                       int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return train_impl(PH_FWD, params, nullptr, x, long_feature, nullptr, nullptr, nullptr, B, seq, L, F, D, C, p_nl, p_fc, seed,
+                    logits, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+int tmr_head_train_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
+                       const float* dlogits, int B, int seq, int L, int F, int D, int C, float* logits_scratch,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  TMR_CHECK_ARG(dlogits, "train_bwd: dlogits is null");
+  return train_impl(PH_BWD, params, grads, x, long_feature, nullptr, nullptr, dlogits, B, seq, L, F, D, C, 0.f, 0.f, 0,
+                    logits_scratch, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 /* torch.optim.SGD step on one flat tensor (momentum mu, weight decay wd, dampening 0): see sgd_kernel. */

@@ -154,6 +154,7 @@ class resnet_lstm(nn.Module):
         self._lstm_cache = _PackedCache()
         self._cls_cache = _PackedCache()
         self.math_mode = None
+        self._backbone_state = {}
 
     # -- packed weights -------------------------------------------------------------------
     def _lstm_params(self):
@@ -176,19 +177,60 @@ class resnet_lstm(nn.Module):
         if self.time_conv is not None:
             self.time_conv._cache.invalidate()
 
-    def load_reference_state_dict(self, sd):
-        """Load a reference checkpoint (torch.save(model.module.state_dict()),
-        train_non-local_mutiConv_resnet.py:1053): backbone `share.*` keys are dropped."""
+    def load_reference_state_dict(self, sd, strict=True):
+        """Load a reference stage-2 checkpoint (torch.save(model.module.state_dict()), TRAIN:1053,1056): the head's
+        keys must match exactly (strict, like EVAL:443-447); the backbone's `share.*` tensors are not used by the head
+        and are kept aside untouched so save_reference_checkpoint() can write them back."""
+        self._backbone_state = {k: v for k, v in sd.items() if k.startswith(("share.", "res."))}
         own = {k: v for k, v in sd.items() if not k.startswith(("share.", "res."))}
-        return self.load_state_dict(own, strict=True)
+        return self.load_state_dict(own, strict=strict)
+
+    def load_stage1_state_dict(self, sd):
+        """What the reference does before stage-2 training (TRAIN:772-774): load a STAGE-1 checkpoint with
+        strict=False - only `share.*` (kept aside here) and `lstm.*` match; the stage-1 classifier `fc.*` has no
+        counterpart in the head (`fc_c` is 512 -> C on the 512-d fc_h_c output, a different layer) and is dropped.
+        Returns (missing head keys, dropped keys) like load_state_dict(strict=False)."""
+        self._backbone_state = {k: v for k, v in sd.items() if k.startswith(("share.", "res."))}
+        own = dict(self.state_dict())
+        take = {k: v for k, v in sd.items() if k in own and tuple(v.shape) == tuple(own[k].shape)}
+        dropped = [k for k in sd if k not in take and not k.startswith(("share.", "res."))]
+        res = self.load_state_dict(take, strict=False)
+        return list(res.missing_keys), dropped
+
+    def reference_state_dict(self, backbone_state=None):
+        """State dict in the reference's layout and key order (share.* first, then lstm, fc_c, fc_h_c, nl_block,
+        time_conv - the attribute order of TRAIN:209-230): `share.*` from `backbone_state` or from the checkpoint
+        this model was loaded from.  With them the reference's strict load (EVAL:443-447) accepts the file; without
+        a backbone only strict=False loads (TRAIN:774) do."""
+        from collections import OrderedDict
+        out = OrderedDict()
+        bb = getattr(self, "_backbone_state", {}) if backbone_state is None else backbone_state
+        for k, v in bb.items():
+            out[k if k.startswith("share.") else "share." + k.split(".", 1)[1]] = v
+        for k, v in self.state_dict().items():
+            out[k] = v.detach().cpu()
+        return out
+
+    def save_reference_checkpoint(self, path, backbone_state=None):
+        """torch.save(model.module.state_dict(), path) as TRAIN:1053,1056 writes it."""
+        torch.save(self.reference_state_dict(backbone_state), path)
 
     # -- forward --------------------------------------------------------------------------
     def forward(self, x, long_feature=None):
+        """eval() under torch.no_grad(): the inference kernels (tensor cores by default).  train(), or eval() with
+        autograd recording: the fp32 training forward as one autograd node (tmrnet_b200.train.HeadTrainFunction;
+        dropout 0.2 / 0.5 as NLB:18,38 and TRAIN:228,250 in train(), off in eval()), so the reference's loop body
+        `outputs = model.forward(inputs, long_feature); loss = criterion(outputs, labels); loss.backward();
+        optimizer.step()` (TRAIN:876-887) runs on this module with stock torch losses and optimisers."""
         if long_feature is None:
             raise TypeError("resnet_lstm.forward: long_feature is required")
-        _no_autograd(x, long_feature, *self.parameters())
-        if self.training:
-            raise RuntimeError("resnet_lstm: dropout in training mode is not part of the inference kernels; call .eval()")
+        needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self.training or needs_graph:
+            from .train import head_train_forward
+            if not needs_graph:            # train() under no_grad: dropout active, nothing recorded
+                with torch.no_grad():
+                    return head_train_forward(self, x, long_feature, dropout=self.training)
+            return head_train_forward(self, x, long_feature, dropout=self.training)
         x = x.reshape(-1, self.sequence_length, 2048)
         logits, _, _ = ops.head_fwd(*self.packs(), x, long_feature, self.num_class, self.math_mode)
         return logits

@@ -198,6 +198,20 @@ def lstm_last(packed, x, math_mode=None):
     return out
 
 
+def lstm_seq(packed, x):
+    """h of every step, (B, seq, 512) (stage-1 surface, code/models.py:43-45); fp32 CUDA-core path."""
+    x = _dev(x, "x")
+    if x.dim() != 3 or x.shape[2] != F:
+        raise ValueError(f"LSTM input must be (B,seq,{F}), got {tuple(x.shape)}")
+    B, seq, _ = x.shape
+    lib = _lib.load()
+    out_tm = torch.empty((seq, B, D), dtype=torch.float32, device=x.device)
+    ws = _ws(lib.tmr_lstm_workspace_bytes(B * seq, B, D), x.device)
+    with torch.cuda.device(x.device):
+        check(lib.tmr_lstm_seq_fwd(_ptr(packed), _ptr(x), B, seq, F, D, _ptr(out_tm), _ptr(ws), ws.numel(), _stream()))
+    return out_tm.permute(1, 0, 2).contiguous()
+
+
 def lstm_last_frames(packed, feats, starts, seq: int, math_mode=None):
     feats = _dev(feats, "feats")
     starts = _dev(starts, "starts", torch.int64)

@@ -29,6 +29,86 @@ PARAM_ORDER = [
 ]
 
 
+def _param_list(model):
+    named = dict(model.named_parameters())
+    params = [named.get(k) for k in PARAM_ORDER]
+    if any(p is None for i, p in enumerate(params) if not PARAM_ORDER[i].startswith("time_conv.")):
+        raise ValueError("model is missing head parameters")
+    return params
+
+
+class HeadTrainFunction(torch.autograd.Function):
+    """Training-mode forward of the whole head as ONE autograd node: forward = tmr_head_train_fwd (activations stay
+    in a workspace the node owns), backward = tmr_head_train_bwd on the incoming dlogits.  This is what makes the
+    reference's own loop body work on the module (TRAIN:876-887) with stock torch losses / optimisers / schedulers:
+
+        model.train(); outputs = model.forward(x, long_feature); loss = criterion(outputs, labels)
+        optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+    x (backbone features) and long_feature (bank windows) receive no gradient: the head trains on frozen
+    features."""
+
+    @staticmethod
+    def forward(ctx, x, long_feature, meta, *params):
+        seq, num_class, p_nl, p_fc, seed = meta
+        dev = x.device
+        B, L = x.shape[0], long_feature.shape[1]
+        lib = _lib.load()
+        ws = _ws(lib.tmr_head_train_workspace_bytes(B, seq, L, D, F, num_class), dev)
+        logits = torch.empty((B, num_class), dtype=torch.float32, device=dev)
+        pp = (C.c_void_p * 24)(*[p.data_ptr() if p is not None else 0 for p in params])
+        with torch.cuda.device(dev):
+            check(lib.tmr_head_train_fwd(pp, _ptr(x), _ptr(long_feature), B, seq, L, F, D, num_class, float(p_nl), float(p_fc),
+                                         int(seed), _ptr(logits), _ptr(ws), ws.numel(), _stream()))
+        ctx.save_for_backward(x, long_feature, *[p for p in params if p is not None])
+        ctx.present = [p is not None for p in params]
+        ctx.shapes = [tuple(p.shape) if p is not None else None for p in params]
+        ctx.ws, ctx.dims = ws, (B, seq, L, num_class)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        saved = ctx.saved_tensors            # raises if a parameter was modified in place since the forward
+        x, long_feature = saved[0], saved[1]
+        it = iter(saved[2:])
+        params = [next(it) if present else None for present in ctx.present]
+        B, seq, L, num_class = ctx.dims
+        dev = x.device
+        grads = FlatBuffer(ctx.shapes, dev)
+        dlogits = dlogits.to(torch.float32).contiguous()
+        lib = _lib.load()
+        pp = (C.c_void_p * 24)(*[p.data_ptr() if p is not None else 0 for p in params])
+        gp = (C.c_void_p * 24)(*[g.data_ptr() if g is not None else 0 for g in grads.views])
+        scratch = torch.empty((B, num_class), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.tmr_head_train_bwd(pp, gp, _ptr(x), _ptr(long_feature), _ptr(dlogits), B, seq, L, F, D, num_class,
+                                         _ptr(scratch), _ptr(ctx.ws), ctx.ws.numel(), _stream()))
+        ctx.ws = None
+        return (None, None, None) + tuple(grads.views)
+
+
+def head_train_forward(model, x, long_feature, dropout=True):
+    """resnet_lstm.forward in training mode (or in eval mode with autograd on: dropout off)."""
+    if x.requires_grad or long_feature.requires_grad:
+        raise RuntimeError("tmrnet_b200: the head trains on frozen backbone features and bank rows; x / long_feature "
+                           "cannot require grad (fine-tuning the backbone is outside this path)")
+    x = _dev(x, "x").reshape(-1, model.sequence_length, F)
+    long_feature = _dev(long_feature, "long_feature")
+    if long_feature.dim() != 3 or long_feature.shape[0] != x.shape[0] or long_feature.shape[2] != D:
+        raise ValueError(f"head: x {tuple(x.shape)} / long_feature {tuple(long_feature.shape)} mismatch")
+    params = _param_list(model)
+    for prm in params:
+        if prm is not None and (prm.dtype != torch.float32 or not prm.is_contiguous() or prm.device != x.device):
+            raise TypeError("head parameters must be contiguous fp32 tensors on the input's device")
+    # dropout masks: counter-based generator keyed by torch's seed and a per-model call counter
+    model._train_calls = getattr(model, "_train_calls", 0) + 1
+    seed = (torch.initial_seed() * 1000003 + model._train_calls) & 0x7FFFFFFFFFFFFFFF
+    p_nl = model.nl_block.dropout.p if dropout else 0.0
+    p_fc = model.dropout.p if dropout else 0.0
+    meta = (model.sequence_length, model.num_class, p_nl, p_fc, seed)
+    return HeadTrainFunction.apply(x, long_feature, meta, *params)
+
+
 class FlatBuffer:
     """One contiguous fp32 buffer with per-tensor views (the all-reduce bucket)."""
 
@@ -48,10 +128,7 @@ class HeadTrainer:
     def __init__(self, model, lr=5e-4, momentum=0.9, weight_decay=5e-4, lstm_lr_scale=0.1, class_weight=None,
                  p_nl=0.2, p_fc=0.5, seed=0, process_group=None):
         self.model = model
-        named = dict(model.named_parameters())
-        self.params = [named.get(k) for k in PARAM_ORDER]
-        if any(p is None for i, p in enumerate(self.params) if not PARAM_ORDER[i].startswith("time_conv.")):
-            raise ValueError("model is missing head parameters")
+        self.params = _param_list(model)
         self.has_tc = self.params[4] is not None
         dev = self.params[0].device
         if dev.type != "cuda":
