@@ -161,6 +161,17 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
       :: "memory");
 }
 
+// Scheduling pin: every use of r[] written before this point is complete before any later asm volatile statement
+// (e.g. the __syncwarp / TMA issue that recycles the shared-memory tile those values were loaded from).
+__device__ __forceinline__ void pin_regs32(uint32_t (&r)[32]) {
+  asm volatile(""
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // K-major operand tile staged by TMA with SWIZZLE_128B: rows of 128 bytes (64 fp16 along K), 8-row
 // swizzle atoms of 1024 bytes stacked along M/N (SBO = 1024).  LBO is unused for swizzled K-major.

@@ -311,7 +311,11 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
                 const float4 v = *reinterpret_cast<const float4*>(sb + lane * 32 + ((j ^ (lane & 7)) << 2));
                 gsum[4 * j] += v.x; gsum[4 * j + 1] += v.y; gsum[4 * j + 2] += v.z; gsum[4 * j + 3] += v.w;
               }
-              fence_proxy_async_smem();                   // the tile's generic reads before its next TMA write
+              // WAR on the tile (my reads, then the next TMA write): no proxy fence (it lowers to MEMBAR.ALL.CTA, which
+              // also waits for this thread's h stores to be acknowledged - measured ~10 % of the epilogue).  The reads
+              // have PERFORMED once their values are consumed; the asm below pins the sums (hence the loads' results)
+              // before the __syncwarp that precedes the next issue_x, as in any TMA pipeline's consumer release.
+              pin_regs32(r);
             } else if (rvalid) {
               const float* xr = p.xp + (int64_t)xrow * (4 * kD) + ncol0 + cc;
 #pragma unroll
