@@ -324,6 +324,29 @@ def test_lstm_large_batch_engine_equals_small_batch_engine():
     assert torch.equal(big, small)
 
 
+@pytest.mark.parametrize("B", [256, 1500, 5000, 19000])
+def test_lstm_persistent_recurrence_repeats_bit_identically(B):
+    """The persistent recurrence kernel (CTA pairs exchanging h through L2 under per-tile counters) must give the
+    same bits on every run and the bits of the streamed small-batch engine: any race in the h exchange, the
+    projected-row tile reuse or the accumulator hand-over would show up as a run-to-run difference."""
+    _need_mode("f16")
+    dev = _dev()
+    seq = 10
+    feats = torch.from_numpy(synth.features(B + seq + 40, seed=B)).to(dev)
+    starts = torch.arange(B)
+    starts[B // 3:] += 7                      # one break in the frame sequence: a tile with the scalar projected-row path
+    starts = starts.to(dev)
+    m = _model(7)
+    first = ops.lstm_last_frames(m.packs()[0], feats, starts, seq, "f16")
+    for _ in range(6):
+        assert torch.equal(ops.lstm_last_frames(m.packs()[0], feats, starts, seq, "f16"), first)
+    small = torch.cat([ops.lstm_last_frames(m.packs()[0], feats, starts[i:i + 250].contiguous(), seq, "f16")
+                       for i in range(0, min(B, 2000), 250)])
+    assert torch.equal(first[:small.shape[0]], small)
+    x = torch.stack([feats[s:s + seq].cpu() for s in starts[:64].tolist()])
+    assert rel_err(first[:64], orc.lstm_last(x, _sd(7))) < TOL["f16"]
+
+
 def test_lstm_duplicate_and_unsorted_starts():
     """Clips that share a start frame (and starts in arbitrary order) each get their own state: step 0 rides in the
     projection's epilogue through a one-clip-per-row table, clips that lose their slot are fixed up

@@ -161,6 +161,12 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
       :: "memory");
 }
 
+// 128-bit shared-memory load that the compiler may not move across other volatile asm (mbarrier waits, TMEM waits)
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
 // Scheduling pin: every use of r[] written before this point is complete before any later asm volatile statement
 // (e.g. the __syncwarp / TMA issue that recycles the shared-memory tile those values were loaded from).
 __device__ __forceinline__ void pin_regs32(uint32_t (&r)[32]) {

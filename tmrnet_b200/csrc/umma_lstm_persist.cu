@@ -43,7 +43,9 @@ struct LstmPersistParams {
   int64_t M;                       // clips
   const float* xp; const int64_t* starts; int seq;
   const float* c0;                 // c after step 0 [M][512]
-  half_t* h16[2];                  // h exchange buffers [M][512] fp16; h16[0] holds h after step 0 on entry
+  half_t* h16a; half_t* h16b;      // h exchange buffers [M][512] fp16; h16a holds h after step 0 on entry
+                                   // (two fields, not an array: a dynamically indexed parameter array would move
+                                   // the whole parameter block to local memory)
   float* h_out;                    // h after the last step (fp32, the clip's St)
   int x_tma; int64_t x_row0;       // tma_x covers the projected rows; its row 0 is projected row x_row0
   int groups;                      // G: groups of 8 pairs
@@ -164,14 +166,15 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
       mbar_wait(b_full, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
-      uint32_t use[2] = {0u, 0u};
+      uint32_t use0 = 0u, use1 = 0u;                        // uses of each accumulator (scalars: no local-memory array)
       int item = 0;
       for (int64_t li = 0; li < n_local; li += 2) {
         const int ns = (li + 1 < n_local) ? 2 : 1;
         for (int t = 1; t < p.seq; ++t) {
           for (int s = 0; s < ns; ++s, ++item) {
-            mbar_wait(&acc_empty[s], (use[s] & 1u) ^ 1u);     // both CTAs' epilogues have drained this accumulator
-            ++use[s];
+            const uint32_t u = s ? use1 : use0;
+            mbar_wait(&acc_empty[s], (u & 1u) ^ 1u);          // both CTAs' epilogues have drained this accumulator
+            if (s) ++use1; else ++use0;
             tc_fence_after();
             PTL(item, 2);
             const uint32_t d_tmem = tmem_base + s * P_BN;
@@ -199,13 +202,13 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
     // counter: the fence waits until the CTA's stores are visible device-wide (hundreds of ns), which would
     // otherwise stall every epilogue warp once per item.  Causality is cumulative across the two hops.
     if (lane == 0) {
-      uint32_t use[2] = {0u, 0u};
+      uint32_t use0 = 0u, use1 = 0u;
       for (int64_t li = 0; li < n_local; li += 2) {
         const int ns = (li + 1 < n_local) ? 2 : 1;
         for (int t = 1; t + 1 < p.seq; ++t) {               // the last step's h is the output: nothing to publish
           for (int s = 0; s < ns; ++s) {
-            mbar_wait(&h_done[s], use[s] & 1u);
-            ++use[s];
+            mbar_wait(&h_done[s], (s ? use1 : use0) & 1u);
+            if (s) ++use1; else ++use0;
             __threadfence();
             fence_proxy_async_global();
             atomicAdd(p.flags + ((group + (li + s) * G) * 2 + crank), 1);
@@ -290,17 +293,17 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
           ++use[s];
           tc_fence_after();
           if (warp == 2 && lane == 0) PTL(item, 5);
-          half_t* hdst = last_step ? nullptr : p.h16[t & 1];
+          half_t* hdst = last_step ? nullptr : ((t & 1) ? p.h16b : p.h16a);
           uint4 hpack = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int ch = 0; ch < P_NCH; ++ch) {
             const int cc = 32 * ch;
             const bool lastc = ch + 1 == P_NCH;
-            uint32_t r[32];
-            tmem_ld32(t_row + cc, r);
             const bool nx_ok = lastc ? ncontig : contig;
             const int nx_x0 = lastc ? nx0 : x0;
             const int nx_col = lastc ? ncol0 : ncol0 + cc + 32;
+            uint32_t r[32];
+            tmem_ld32(t_row + cc, r);
             tmem_ld_wait_dep(r);
             float* gsum = reinterpret_cast<float*>(r);
             if (x_pend) {
@@ -420,9 +423,17 @@ int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* start
   using namespace umma;
   if (B == 0 || seq < 2) return TMR_OK;
   const int gmax = persist_groups();
-  if (gmax < 1) return set_error(TMR_ERR_UNSUPPORTED, "persistent LSTM recurrence: fewer than 8 co-resident CTA pairs");
+  if (gmax < 1) {
+    static bool warned = false;
+    if (!warned) {                 // loud, once: the per-step kernels are correct but ~40 % slower
+      warned = true;
+      fprintf(stderr, "libtmr_b200: persistent LSTM recurrence unavailable on this device (fewer than 8 co-resident CTA "
+                      "pairs); using the per-step kernels\n");
+    }
+    return set_error(TMR_ERR_UNSUPPORTED, "persistent LSTM recurrence: fewer than 8 co-resident CTA pairs");
+  }
   LstmPersistParams p{};
-  p.M = B; p.xp = xp; p.starts = starts; p.seq = seq; p.c0 = c0; p.h16[0] = h16a; p.h16[1] = h16b; p.h_out = h_out;
+  p.M = B; p.xp = xp; p.starts = starts; p.seq = seq; p.c0 = c0; p.h16a = h16a; p.h16b = h16b; p.h_out = h_out;
   p.x_row0 = xp_row0; p.flags = flags;
   p.m_pairs = ((int64_t)B + 2 * P_BM - 1) / (2 * P_BM);
   // two tiles in flight per pair: no more groups than pairs of tiles
