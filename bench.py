@@ -431,11 +431,13 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 return a.elapsed_time(b) / reps
 
-            # the recurrence alone: the same call with seq = 10 and seq = 2 differs by exactly 8 recurrent steps
-            # (both run the projection with step 0 fused into its epilogue)
+            # the recurrence alone: the same call with seq = 10 and seq = 2 runs the same projection (step 0 fused into
+            # its epilogue) and the same persistent recurrence kernel over 9 / 1 steps; fixed costs cancel in the
+            # difference (8 steps), scaled to the 9 steps of one launch
             t_l10 = timeit(lambda: ops.lstm_last_frames(packs[0], fr, st, SEQ), 10)
             t_l2 = timeit(lambda: ops.lstm_last_frames(packs[0], fr, st, 2), 10)
             t_step = (t_l10 - t_l2) / (SEQ - 2)
+            t_rec = t_step * (SEQ - 1)
             t_bc = timeit(lambda: ops.bankconv(packs[1], bank_dev, 0, B + L), 10)
             # HBM-bound kernels on windows that do NOT dedupe in L2: random clip starts over the whole bank
             rnd = torch.from_numpy(np.random.default_rng(0).permutation(eng.starts_host)[:B].copy()).to(dev)
@@ -447,15 +449,15 @@ def run_ours(args):
             del win
             kern = {
                 "lstm_step": {"ms": t_step, "tflops": FLOP_LSTM_STEP * B / t_step / 1e9, "clips": B,
-                              "ms_recurrence": t_l10 - t_l2 + t_step, "ms_lstm_total": t_l10},
+                              "ms_recurrence": t_rec, "ms_lstm_total": t_l10},
                 "bankconv": {"ms": t_bc, "tflops": FLOP_BANKCONV_ROW * (B + L) / t_bc / 1e9, "rows": B + L},
                 "timeconv_per_clip": {"ms": t_tc, "tflops": FLOP_TIMECONV * B / t_tc / 1e9, "clips": B},
                 "gather": {"ms": t_g, "gbs": BYTES_GATHER * B / t_g / 1e6, "clips": B},
                 "attention": {"ms": t_at, "gbs": BYTES_RELATION * B / t_at / 1e6, "clips": B},
             }
-            if not args.no_eager:
+            if not args.no_eager and world == 1:
                 eager = torch_eager_rate(dev, feats_dev, bank_dev, index)
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:             # the CPU arm beside it: rank 0 at N = 1 only
             r = cpu_head_rate(256, iters=args.cpu_iters, warmup=1)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
@@ -476,21 +478,26 @@ def run_ours(args):
                     "frac": kern[k]["tflops"] / pk["tensor"], "algorithmic_flop_per_unit": unit_flop,
                     "units_per_launch": units, "ms_per_launch": kern[k]["ms"]}
 
+        # Dominant kernel: the persistent LSTM recurrence (all 9 recurrent steps of every clip in ONE launch).  SURVEY.md
+        # 8(d) puts the LSTM on the tensor roofline (AI ~1 300 flop/B): algorithmic work = 9 steps x 2.097 MFLOP per clip
+        # (step 0 has h = 0 and rides in the projection); its measured DRAM traffic (ncu, committed) is reported beside it.
         traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else None
-        bytes_step = traffic["algorithmic_bytes_per_clip_step"] if traffic else 4 * 512 * 4 + 2 * 512 * 4 + 2 * 512 * 2
-        step_gbs = bytes_step * ls["clips"] / ls["ms"] / 1e6
-        roof = {"kernel": (traffic or {}).get("kernel", "LSTM recurrent step (h.Whh^T + LSTM cell epilogue), largest share of the pass"),
-                "bound": "hbm", "achieved": step_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": step_gbs / pk["hbm"],
-                "traffic": (traffic["dram_bytes_per_clip_step"] * ls["clips"]) if traffic else None,
+        rec_flop = FLOP_LSTM_STEP * (SEQ - 1)
+        rec_tflops = rec_flop * ls["clips"] / ls["ms_recurrence"] / 1e9
+        dram_per_clip = (traffic["dram_bytes_per_clip_step"] * traffic["steps_per_launch"]) if traffic else None
+        roof = {"kernel": (traffic or {}).get("kernel", "umma_lstm_persist_kernel (persistent LSTM recurrence)"),
+                "bound": "tensor", "achieved": rec_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": rec_tflops / pk["tensor"],
+                "traffic": (dram_per_clip * ls["clips"]) if traffic else None,
                 "traffic_source": (traffic or {}).get("source"),
-                "peak_source": pk["source"],
-                "algorithmic_bytes_per_clip": bytes_step, "clips_per_launch": ls["clips"], "ms_per_launch": ls["ms"],
-                "ms_recurrence_9_steps": ls["ms_recurrence"], "ms_lstm_total": ls["ms_lstm_total"],
-                "how": "CUDA events: (10-step LSTM - 2-step LSTM) / 8 on one batch of the full job; both legs run the same "
-                       "projection with step 0 fused, so the difference is exactly 8 recurrent steps",
-                "tensor": {"achieved": ls["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ls["tflops"] / pk["tensor"],
-                           "algorithmic_flop_per_clip": FLOP_LSTM_STEP,
-                           "note": "peak = measured bf16 burst (fp16 operands issue at the same rate)"},
+                "peak_source": pk["source"] + " (bf16 burst; fp16 operands issue at the same rate)",
+                "algorithmic_flop_per_clip": rec_flop, "clips_per_launch": ls["clips"], "ms_per_launch": ls["ms_recurrence"],
+                "ms_lstm_total": ls["ms_lstm_total"], "share_of_step": ls["ms_recurrence"] * (total_clips / world) / ls["clips"] / (ms / args.steps),
+                "how": "CUDA events on one batch of the full job: (10-step LSTM - 2-step LSTM) x 9/8 - both legs run the same "
+                       "projection with step 0 fused and the same persistent kernel over 9 / 1 steps, so fixed costs cancel",
+                "hbm": {"dram_bytes_per_clip": dram_per_clip,
+                        "note": "measured DRAM traffic of the whole recurrence per clip (c never leaves the SM, h is exchanged "
+                                "through L2, projected rows of consecutive steps hit L2); the per-step kernels of round 1 moved "
+                                "~125 KB per clip"},
                 "tensor_kernels": {"bankconv": tens("bankconv", FLOP_BANKCONV_ROW, kern["bankconv"]["rows"]),
                                    "timeconv_per_clip": tens("timeconv_per_clip", FLOP_TIMECONV, kern["timeconv_per_clip"]["clips"])},
                 "hbm_kernels": {"gather": hbm("gather", BYTES_GATHER), "attention": hbm("attention", BYTES_RELATION)}}

@@ -306,25 +306,33 @@ class BankInference:
             host_out[1].copy_(out["score"], non_blocking=True)
         return out, host_out
 
-    def launches_per_run(self) -> int:
-        """Kernel launches of one run() (bench.py's gpu_launches).  Per batch, fp32 mode:
-        projection + cell0 + (seq-1) steps | gather | timeconv | q, u, attention, v, layernorm, out |
-        fc_h_c, fc_c; tensor-core mode adds the fp16 conversion passes (features, window, St, [St|y1]) and folds
-        q, u into one GEMM; the dedup path replaces gather+round+timeconv over all clips by round(bank rows)
-        + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw bankconv +
-        assemble (or gather+round+timeconv without the row list)."""
+    def launches_per_run(self, feats_f16: bool = False) -> int:
+        """Kernel launches of one run() (bench.py's gpu_launches), counted from the launch sequences in csrc/api.cu.
+        LSTM, fp32 mode: projection + cell0 + (seq-1) steps.  Tensor-core mode: feature conversion (none for fp16
+        features) + row->clip table + projection (step 0 fused) + step-0 fix-up + the recurrence - ONE persistent launch
+        for batches of >= 256 clips, seq-1 step launches below.  Tail, fp32: gather | timeconv | q, u, attention, v,
+        layernorm, out | fc_h_c, fc_c; tensor-core mode folds q, u into one GEMM and adds the fp16 conversions of the
+        window, St and [St|y1]; the bank-level path replaces gather + conversion + timeconv over all clips by
+        conversion(bank rows) + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw
+        bankconv + assemble (or gather + conversion + timeconv without the row list)."""
         mode = _mode(self.math_mode if self.math_mode is not None else self.model.math_mode)
         tc = 1 if self.model.time_conv is not None else 0
-        lstm = 1 + 1 + (self.seq - 1)
         tail = 6 + 2
         if mode != ops.TMR_MATH_F16:
-            return (lstm + 1 + tc + tail) * len(self.plan())
+            return (1 + 1 + (self.seq - 1) + 1 + tc + tail) * len(self.plan())
         tail -= 1                                      # u = W21 St + bu: one GEMM for q and u
+
+        def lstm(b):
+            if self.seq == 1:
+                return (0 if feats_f16 else 1) + 1 + 1
+            rec = 1 if b >= 256 else self.seq - 1
+            return (0 if feats_f16 else 1) + 1 + 1 + 1 + rec
+
         if not self._use_dedup():
-            return (lstm + 1 + 1 + 2 * tc + tail + 2) * len(self.plan())
+            return sum(lstm(hi - lo) + 1 + 1 + 2 * tc + tail + 2 for lo, hi, _, _ in self.plan())
         n = 0
-        for d in self.dedup_plan():
-            n += ((lstm + 1) + (2 if d["pb_rows"] > 0 else 0) + (0 if not len(d["irr"]) else 4 if len(d["irr_rows"]) else 3)
+        for (lo, hi, _, _), d in zip(self.plan(), self.dedup_plan()):
+            n += (lstm(hi - lo) + (2 if d["pb_rows"] > 0 else 0) + (0 if not len(d["irr"]) else 4 if len(d["irr_rows"]) else 3)
                   + tail + 2)
         return n
 
