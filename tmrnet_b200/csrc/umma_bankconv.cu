@@ -7,20 +7,27 @@
 // so the per-tap products P_{K,t}[rho] = W_K[:,:,t+h] . bank[rho - t] depend only on the row.  Away
 // from the window edges (3 <= k <= L-4) all taps are present and the TimeConv output is a pure
 // function of rho; at the three slots next to either edge the taps that fall outside the window
-// are dropped (zero "same" padding, NLB:55-65).  This kernel accumulates the 15 tap products of a
-// 128-row x 16-channel tile in TMEM (7 shift groups: 16/32/48/48/48/32/16 columns = 240, two buffers) with
-// tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulate), and its epilogue assembles, per row, the SEVEN variants a window can ask
-// of that row:
+// are dropped (zero "same" padding, NLB:55-65).  This kernel accumulates the 15 unshifted tap products
+// Q_{K,t}[r] = W_K[:,:,t+h] . bank[r] of a 2 x 128-row x 16-channel tile in TMEM (240 columns, two buffers) with
+// tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulate), and its epilogue applies the time shifts and assembles, per
+// row, the SEVEN variants a window can ask of that row:
 //     v0: interior      v1..v3: slot k = 0,1,2 (left-clipped)      v4..v6: slot k = L-1,L-2,L-3
 // each = max(bank[rho], pool, conv3, conv5, conv7) with pool = bank[rho+1] (slot k-1) or 0 for v1
 // (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512]; attention_pb_kernel consumes it.
 // 236 MFLOP/clip become 7.9 MFLOP/row; only summation order changes.
 //
-// The SM's ingest from L2 (about 55 B/cycle) is dear, so the seven time
-// shifts are NOT taken as seven shifted activation loads: the MMAs multiply the tile's rows unshifted
-// and the epilogue applies the shift by exchanging accumulator rows through shared memory (3-row halo,
-// 122 of 128 rows emitted per tile).  (Taking the shifts as row-offset descriptor views of one smem
-// tile — matrix base offset — was tried first and produced wrong products on B200.)
+// Layout of the work (round 2; the first version exchanged accumulator rows through shared memory between two
+// CTA-wide barriers per 8 channels and re-fetched the row tile for each of the 32 channel tiles: tensor pipe 49 %):
+//  * the time shifts are WARP-LOCAL.  A TMEM lane quarter (32 lanes = the rows one epilogue warp may read) holds 32
+//    CONSECUTIVE bank rows, of which the inner 26 are emitted; the next quarter starts 26 rows further, i.e. the four
+//    32-row TMA boxes of a CTA's A tile overlap by 6 rows.  P_{K,t}[rho] = Q_{K,t}[rho - t] is then one
+//    __shfl_up/down of the accumulator value read from TMEM - no shared memory, no barrier, and each epilogue
+//    warp runs on its own.  Cost: 26 of 32 MMA rows are useful (the exchange version used 122 of 128).
+//  * the fp16 rows of a CTA (128 x 512 = 128 KB) stay RESIDENT in shared memory for all 32 channel tiles of their
+//    row block; only the stacked tap weights (15 KB per CTA and 64-channel k-step) stream.  L2 -> SM traffic per
+//    launch halves, and the six-stage weight ring is all the staging the kernel needs.
+//  * a CTA pair owns a CONTIGUOUS range of (row block, channel tile) items, equal for all pairs, so the grid is
+//    balanced to one tile and a pair reloads its rows only when its range crosses into the next row block.
 #include <stdlib.h>
 #include "tmr_internal.h"
 #include "umma_common.cuh"
@@ -28,12 +35,17 @@
 namespace tmr {
 namespace umma {
 
-constexpr int BC_BM = 128;                 // bank rows whose tap products one tile computes
-constexpr int BC_OUT = BC_BM - 6;          // rows it emits: the 3-row halo on either side feeds the shifts
+constexpr int BC_BM = 128;                 // MMA rows per CTA (TMEM lanes)
+constexpr int BC_GROUP = 32;               // rows per TMEM lane quarter = rows one epilogue warp sees
+constexpr int BC_HALO = 3;                 // rows on either side of a group that only feed the shifts
+constexpr int BC_GOUT = BC_GROUP - 2 * BC_HALO;   // 26 rows a group emits
+constexpr int BC_OUT = 4 * BC_GOUT;        // 104 rows a CTA emits per row block (128 in raw mode: no shifts, no halo)
 constexpr int BC_NCH = 16;                 // output channels per tile: 15 taps x 16 = 240 TMEM columns, double-buffered
 constexpr int BC_BK = 64;                  // fp16 input channels per k-step = one 128-byte swizzle row
-constexpr int BC_STAGES = 3;
-constexpr int BC_A_BYTES = BC_BM * BC_BK * 2;                  // 16 KB: the tile's rows for one channel chunk
+constexpr int BC_KB = kD / BC_BK;          // 8 k-steps
+constexpr int BC_A_BYTES = BC_BM * BC_BK * 2;                  // 16 KB: the CTA's rows for one k-step
+constexpr int BC_A_TOTAL = BC_KB * BC_A_BYTES;                 // 128 KB: resident for the whole row block
+constexpr int BC_STAGES = 6;               // weight ring
 // 2-SM MMA (cta_group::2): a CTA PAIR multiplies 2 x 128 rows by the 240 stacked weight rows of the tile's 16
 // channels; each CTA stages its own 128 bank rows and HALF of the weight rows - those of 8 channels:
 constexpr int BC_HCH = BC_NCH / 2;                             // channels whose weight rows one CTA stages
@@ -41,74 +53,80 @@ constexpr int BC_W7_BYTES = 7 * BC_HCH * BC_BK * 2;            //  7 KB: rows or
 constexpr int BC_W5_BYTES = 5 * BC_HCH * BC_BK * 2;            //  5 KB
 constexpr int BC_W3_BYTES = 3 * BC_HCH * BC_BK * 2;            //  3 KB
 constexpr int BC_W_BYTES = BC_W7_BYTES + BC_W5_BYTES + BC_W3_BYTES;   // 15 KB = 120 rows per CTA: ONE MMA of N = 240 per k-step
-constexpr int BC_STAGE_BYTES = BC_A_BYTES + BC_W_BYTES;        // 31 KB
-constexpr int BC_EX_BYTES = 15 * BC_BM * 8 * 4;        // epilogue exchange: 15 taps x 128 rows x 8 channels
-constexpr int BC_SMEM_BYTES = BC_STAGES * BC_STAGE_BYTES + 2 * BC_EX_BYTES + 1024 + 512;   // exchange buffer x 2
-constexpr int BC_EPI_WARPS = 8;            // two per TMEM lane quarter
+constexpr int BC_SMEM_BYTES = BC_A_TOTAL + BC_STAGES * BC_W_BYTES + 1024 + 512;
+constexpr int BC_EPI_WARPS = 8;            // two per TMEM lane quarter: one per 8-channel half of the tile
 constexpr int BC_THREADS = 64 + 32 * BC_EPI_WARPS;
 constexpr int BC_TMEM_COLS = 512;          // 2 accumulator buffers of 256 columns (240 used)
 constexpr int BC_N = 15 * BC_NCH;          // 240
+constexpr int BC_NTILES = kD / BC_NCH;     // 32 channel tiles per row block
+static_assert(BC_SMEM_BYTES <= 227 * 1024, "bankconv: shared memory budget");
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
-  uint32_t u[8];
+// 8 consecutive floats through two 128-bit read-only loads (the caller's pointers are only promised 16-byte alignment)
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&u)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
-// TMEM column of tap t of conv K for channel ch of the tile.  Columns 0..119 are the weight rows CTA 0 staged
-// (channels 0..7: conv7 | conv5 | conv3, each [channel][tap]), columns 120..239 those of CTA 1 (channels 8..15),
-// so a channel's taps are consecutive columns and an 8-channel chunk is three runs of 56 / 40 / 24 columns.
-__host__ __device__ constexpr int col7(int ch) { return (ch / BC_HCH) * (15 * BC_HCH) + (ch % BC_HCH) * 7; }
-__host__ __device__ constexpr int col5(int ch) { return (ch / BC_HCH) * (15 * BC_HCH) + 7 * BC_HCH + (ch % BC_HCH) * 5; }
-__host__ __device__ constexpr int col3(int ch) { return (ch / BC_HCH) * (15 * BC_HCH) + 12 * BC_HCH + (ch % BC_HCH) * 3; }
+// TMEM columns of a tile: 0..119 are the weight rows CTA 0 staged (channels 0..7: conv7 | conv5 | conv3, each
+// [channel][tap]), 120..239 those of CTA 1 (channels 8..15): the taps of an 8-channel half are three runs of
+// 56 / 40 / 24 consecutive columns at offsets 0 / 56 / 96 of the half.
+constexpr int BC_HALF_COLS = 15 * BC_HCH;  // 120
+constexpr int BC_COL7 = 0, BC_COL5 = 7 * BC_HCH, BC_COL3 = 12 * BC_HCH;
 
 struct BankConvParams {
   const float* bank; float* pb; const float* bias3; const float* bias5; const float* bias7;
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
-  int64_t num_tiles;
+  int64_t num_tiles;                                                  // row blocks x 32 channel tiles
   float* q_out; int raw;   // raw: emit the UNSHIFTED tap products Q[row][15][512] instead of the 7 variants
-  int ablate;      // timing experiment (WRONG results), env TMR_BC_ABL: 2 = no global stores
 };
 
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
-// epilogue (two per TMEM lane quarter: one moves the conv7 taps to the exchange buffer, the other conv5 + conv3;
-// then each assembles the variants of 16 of the quarter's 32 rows).  The MMAs compute UNSHIFTED products Q_{K,t}[r] = W_K[:,:,t+h] . bank[r] for the tile's 128
-// rows: one activation tile per channel chunk feeds all 15 taps, whose weight rows (rank-3 TMA boxes
-// over [in-channel][tap][out-channel]) are stacked into ONE 240-row B operand — a single N = 240
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
+// (warp w reads TMEM lane quarter w & 3 and owns the 8-channel half (w - 2) >> 2 of the tile).  The MMAs compute
+// UNSHIFTED products Q_{K,t}[r] = W_K[:,:,t+h] . bank[r]: one resident row tile feeds all 15 taps, whose weight rows
+// (rank-3 TMA boxes over [in-channel][tap][out-channel]) are stacked into ONE 240-row B operand - a single N = 240
 // tcgen05.mma per k-step instead of seven narrow ones (a narrow MMA costs ~100 cycles whatever its N).
-// The time shift P_{K,t}[rho] = Q_{K,t}[rho - t] is applied in the epilogue by exchanging rows through
-// shared memory (hence the 3-row halo).  Accumulators are double-buffered in TMEM so the epilogue of
-// tile i overlaps the main loop of tile i+1.
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BC_THREADS, 1)
 umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w3,
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
                      const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // pointer arithmetic on the __shared__ array (no integer round trip) keeps the shared address space, so the
-  // epilogue staging compiles to STS/LDS instead of generic ST.E/LD.E
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* ex = reinterpret_cast<float*>(smem + BC_STAGES * BC_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ex) + 2 * BC_EX_BYTES);
-  uint64_t* full_bar = bars;                        // [BC_STAGES]
-  uint64_t* empty_bar = bars + BC_STAGES;           // [BC_STAGES]
-  uint64_t* acc_full = bars + 2 * BC_STAGES;        // [2]
-  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint8_t* sA = smem;                                   // [BC_KB][128 rows][64 fp16], resident per row block
+  uint8_t* sW = sA + BC_A_TOTAL;                        // [BC_STAGES][120 weight rows][64 fp16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + BC_STAGES * BC_W_BYTES);
+  uint64_t* a_full = bars;                              // [BC_KB]      TMA -> MMA, once per row block
+  uint64_t* a_empty = a_full + BC_KB;                   // [BC_KB]      MMA -> TMA: the block's last tile has read this k-step
+  uint64_t* w_full = a_empty + BC_KB;                   // [BC_STAGES]
+  uint64_t* w_empty = w_full + BC_STAGES;               // [BC_STAGES]
+  uint64_t* acc_full = w_empty + BC_STAGES;             // [2]
+  uint64_t* acc_empty = acc_full + 2;                   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int N_TILES = kD / BC_NCH;                                 // 32 channel tiles, fastest index
   const uint32_t crank = cluster_ctarank();
-  const int64_t tile0 = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;  // a tile = 2 x 122 rows x 16 channels per CTA pair
   constexpr uint16_t kMask = 3;
+  // my pair's contiguous range of (row block, channel tile) items
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int64_t t_begin = p.num_tiles * pair / n_pairs, t_end = p.num_tiles * (pair + 1) / n_pairs;
+  // rows: raw mode multiplies 128 distinct rows per CTA; otherwise four 32-row groups that overlap by 2 x 3 halo rows
+  const int out_per_cta = p.raw ? BC_BM : BC_OUT;
+  const int group_stride = p.raw ? BC_GROUP : BC_GOUT;
+  const int halo = p.raw ? 0 : BC_HALO;
+  auto group_row0 = [&](int64_t rb, int j) -> int64_t {        // bank row in lane 0 of lane quarter j of this CTA
+    return p.row_base + (rb * 2 + crank) * out_per_cta + (int64_t)j * group_stride - halo;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
-    for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int k = 0; k < BC_KB; ++k) { mbar_init(&a_full[k], 1); mbar_init(&a_empty[k], 1); }
+    for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * BC_EPI_WARPS); }
     fence_barrier_init();
   }
@@ -120,211 +138,223 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own rows per row block, own weight rows per tile) ==========
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = tile0; tile < p.num_tiles; tile += tile_stride) {
-        const int n0 = (int)(tile % N_TILES) * BC_NCH + (int)crank * BC_HCH;     // the 8 channels whose weights I stage
-        const int64_t q0 = p.row_base + ((tile / N_TILES) * 2 + crank) * BC_OUT - 3;   // first row this CTA multiplies
-        for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
-          const int c0 = chunk * BC_BK;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * BC_STAGE_BYTES;
-          uint8_t* sw = sa + BC_A_BYTES;
-          // both CTAs' bytes land on the LEADER's barrier, which only the leader arms
-          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * BC_STAGE_BYTES);
-          tma_load_2d_2sm(sa, &tma_x, &full_bar[stage], c0, (int)(q0 - p.r_lo));                 // OOB rows -> 0
-          tma_load_3d_2sm(sw, &tma_w7, &full_bar[stage], c0, 0, n0);                             // [8 ch][7 taps] rows
-          tma_load_3d_2sm(sw + BC_W7_BYTES, &tma_w5, &full_bar[stage], c0, 0, n0);               // [8 ch][5 taps]
-          tma_load_3d_2sm(sw + BC_W7_BYTES + BC_W5_BYTES, &tma_w3, &full_bar[stage], c0, 0, n0); // [8 ch][3 taps]
+      int64_t rb_prev = -1; int nb = -1;                          // nb: row blocks loaded so far - 1
+      for (int64_t tile = t_begin; tile < t_end; ++tile) {
+        const int64_t rb = tile / BC_NTILES;
+        const int n0 = (int)(tile % BC_NTILES) * BC_NCH + (int)crank * BC_HCH;     // the 8 channels whose weights I stage
+        const bool new_rb = rb != rb_prev;
+        if (new_rb) { ++nb; rb_prev = rb; }
+        for (int kb = 0; kb < BC_KB; ++kb) {
+          const int c0 = kb * BC_BK;
+          if (new_rb) {
+            // both CTAs' bytes land on the LEADER's barrier, which only the leader arms
+            if (nb > 0) mbar_wait(&a_empty[kb], (uint32_t)(nb - 1) & 1u);   // previous block's MMAs have read this k-step
+            if (crank == 0) mbar_expect_tx(&a_full[kb], 2 * BC_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)                                     // OOB rows (before / after the bank slice) -> 0
+              tma_load_2d_2sm(sA + kb * BC_A_BYTES + j * (BC_GROUP * BC_BK * 2), &tma_x, &a_full[kb], c0,
+                              (int)(group_row0(rb, j) - p.r_lo));
+          }
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          uint8_t* sw = sW + stage * BC_W_BYTES;
+          if (crank == 0) mbar_expect_tx(&w_full[stage], 2 * BC_W_BYTES);
+          tma_load_3d_2sm(sw, &tma_w7, &w_full[stage], c0, 0, n0);                             // [8 ch][7 taps] rows
+          tma_load_3d_2sm(sw + BC_W7_BYTES, &tma_w5, &w_full[stage], c0, 0, n0);               // [8 ch][5 taps]
+          tma_load_3d_2sm(sw + BC_W7_BYTES + BC_W5_BYTES, &tma_w3, &w_full[stage], c0, 0, n0); // [8 ch][3 taps]
           if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {                                               // the leader CTA issues for the pair
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && crank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(2 * BC_BM, BC_N);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int64_t tile = tile0; tile < p.num_tiles; tile += tile_stride, ++it) {
+      int64_t rb_prev = -1; int nb = -1;
+      for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int64_t rb = tile / BC_NTILES;
+        const bool new_rb = rb != rb_prev;
+        if (new_rb) { ++nb; rb_prev = rb; }
+        const bool last_of_rb = (tile + 1 == t_end) || ((tile + 1) / BC_NTILES != rb);
         const int acc = it & 1;
         mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);                         // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int chunk = 0; chunk < kD / BC_BK; ++chunk) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = 0; kb < BC_KB; ++kb) {
+          if (new_rb) mbar_wait(&a_full[kb], (uint32_t)nb & 1u);
+          mbar_wait(&w_full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * BC_STAGE_BYTES);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + BC_A_BYTES);             // my 120 of the 240 stacked weight rows
+          const uint64_t da = make_smem_desc_sw128(smem_u32(sA + kb * BC_A_BYTES));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(sW + stage * BC_W_BYTES));   // my 120 of the 240 stacked weight rows
 #pragma unroll
           for (int k = 0; k < BC_BK / 16; ++k)
-            mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (chunk | k) != 0);
-          mma_commit_2sm_mcast(&empty_bar[stage], kMask);
+            mma_f16_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          mma_commit_2sm_mcast(&w_empty[stage], kMask);
+          if (last_of_rb) mma_commit_2sm_mcast(&a_empty[kb], kMask);            // the rows of this k-step may be replaced
           if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit_2sm_mcast(&acc_full[acc], kMask);
       }
     }
   } else {
-    const int q = warp & 3;
-    const int part = (warp - 2) >> 2;                               // which of the quarter's two warps
-    const int r = q * 32 + lane;                                    // phase 1: row inside the tile = TMEM lane
-    // exchange layout: ex[buffer][tap][row][8 channels]; taps 0..6 = conv7 t=-3..3, 7..11 = conv5 t=-2..2,
-    // 12..14 = conv3 t=-1..1.  The two 16-byte halves of a row swap places in rows with bit 2 set, so 128-bit
-    // accesses by eight consecutive rows (phase 1) or by eight (row, half) pairs (phase 2) never share a bank group.
-    auto exh = [&](int buf, int tap, int row, int h) -> float4* {
-      return reinterpret_cast<float4*>(ex + (size_t)buf * (BC_EX_BYTES / 4) + ((size_t)tap * BC_BM + row) * 8 + ((h ^ ((row >> 2) & 1)) << 2));
-    };
-    // phase 2: a lane owns FOUR channels (half = lane & 1 of the 8-channel chunk) of row 32q + 16 part + lane/2,
-    // so every global load / store instruction covers whole 32-byte sectors (16 rows x 32 B) instead of 32
-    // half-filled ones (row per thread).
-    const int half = lane & 1;
-    const int r2 = q * 32 + 16 * part + (lane >> 1);
-    struct TileInfo { int n0; int acc; int64_t prow; bool valid; float4 x0v[2], x1v[2]; };
-    // tile bookkeeping + the exact bank values of the lane's row and of the next one (identity / pool branches),
-    // requested before the accumulator is awaited so their latency hides behind the main loop
-    auto load_tile = [&](int64_t tile, int it, TileInfo& T) {
-      T.acc = it & 1;
-      T.n0 = (int)(tile % N_TILES) * BC_NCH;
-      const int64_t q0 = p.row_base + ((tile / N_TILES) * 2 + crank) * BC_OUT - 3;
-      const int64_t rho = q0 + r2;                                  // bank row
-      T.prow = rho - p.row_base;
-      T.valid = r2 >= 3 && r2 < 3 + BC_OUT && T.prow >= 0 && T.prow < p.pb_rows && rho < p.n_rows;
-      const bool has_next = T.valid && (rho + 1 < p.n_rows);
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                                     // TMEM lane quarter = row group
+    const int part = (warp - 2) >> 2;                           // 8-channel half of the tile
+    const bool lane_emits = lane >= halo && lane < BC_GROUP - halo;
+    int it = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
+      const int64_t rb = tile / BC_NTILES;
+      const int n0 = (int)(tile % BC_NTILES) * BC_NCH + part * BC_HCH;         // my 8 channels
+      const int acc = it & 1;
+      const int64_t rho = group_row0(rb, q) + lane;             // my bank row
+      const int64_t prow = rho - p.row_base;
+      const bool valid = lane_emits && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
+      // exact bank values of my row and of the next one (identity / pool branches), requested before the
+      // accumulator is awaited so their latency hides behind the main loop
+      float x0[8], x1[8];
 #pragma unroll
-      for (int c8 = 0; c8 < 2; ++c8) {
-        const float* src = p.bank + rho * kD + T.n0 + 8 * c8 + 4 * half;
-        T.x0v[c8] = (T.valid && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        T.x1v[c8] = (has_next && !p.raw) ? __ldg(reinterpret_cast<const float4*>(src + kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 8; ++k) { x0[k] = 0.f; x1[k] = 0.f; }
+      if (valid && !p.raw) {
+        ldg8(p.bank + rho * kD + n0, x0);
+        if (rho + 1 < p.n_rows) ldg8(p.bank + (rho + 1) * kD + n0, x1);
       }
-      mbar_wait(&acc_full[T.acc], (it >> 1) & 1);
+      mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-    };
-    // phase 1 of an 8-channel chunk: accumulator -> exchange buffer.  A channel's taps are consecutive TMEM
-    // columns, so the chunk's 8 channels x K taps are ONE run of 56 / 40 / 24 columns: a few wide tcgen05.ld,
-    // and the row goes out as two 128-bit stores per tap (8 channels).  The quarter's two warps split the taps.
-    auto phase1 = [&](const TileInfo& T, int cc, int buf) {
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(T.acc * 256);
-      uint32_t v[32], w[32];
-      if (part == 0) {
-        tmem_ld32(t_row + col7(cc), v);
-        tmem_ld32(t_row + col7(cc) + 32, w);             // 56 used; the rest belongs to conv5
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + part * BC_HALF_COLS);
+
+      if (p.raw) {
+        // Q_{K,t}[rho] = W_K[:,:,t+h] . x[rho] as computed: any window can be assembled from these
+        float* dst = p.q_out + prow * (15 * kD) + n0;
+        uint32_t v[32], w[32];
+        tmem_ld32(t_row + BC_COL7, v);
+        tmem_ld32(t_row + BC_COL7 + 32, w);             // 56 used
         tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int t = 0; t < 7; ++t)
+          for (int t = 0; t < 7; ++t) {
+            uint32_t e[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t e[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 7 + t; e[c] = idx < 32 ? v[idx] : w[idx - 32]; }
-            *reinterpret_cast<uint4*>(exh(buf, t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
+            for (int c = 0; c < 8; ++c) { const int idx = c * 7 + t; e[c] = idx < 32 ? v[idx] : w[idx - 32]; }
+            stg256u(dst + t * kD, e);
           }
-      } else {
-        float f8[8];
-        tmem_ld32(t_row + col5(cc), v);
-        tmem_ld8(t_row + col5(cc) + 32, f8);
-        tmem_ld32(t_row + col3(cc), w);                  // 24 used (columns up to 247 of the 256-column buffer)
+        }
+        uint32_t f8[8];
+        tmem_ld32(t_row + BC_COL5, v);
+        tmem_ld8(t_row + BC_COL5 + 32, f8);
+        tmem_ld32(t_row + BC_COL3, w);                  // 24 used (columns up to 247 of the 256-column buffer)
         tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 5; ++t)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t e[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { const int idx = (4 * h + c) * 5 + t; e[c] = idx < 32 ? v[idx] : __float_as_uint(f8[idx - 32]); }
-            *reinterpret_cast<uint4*>(exh(buf, 7 + t, r, h)) = make_uint4(e[0], e[1], e[2], e[3]);
-          }
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            *reinterpret_cast<uint4*>(exh(buf, 12 + t, r, h)) =
-                make_uint4(w[(4 * h) * 3 + t], w[(4 * h + 1) * 3 + t], w[(4 * h + 2) * 3 + t], w[(4 * h + 3) * 3 + t]);
-      }
-      if (cc + 8 >= BC_NCH) {                            // last TMEM read of this tile: hand the buffer back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&acc_empty[T.acc], 0);
-      }
-    };
-    // phase 2: exchange buffer -> the lane's row: time shifts, the 7 edge variants, stores
-    auto phase2 = [&](const TileInfo& T, int cc, int buf) {
-      if (!T.valid) return;
-      if (p.raw) {            // Q_{K,t}[rho] = W_K[:,:,t+h] . x[rho] as computed: any window can be assembled from these
-        float* dst = p.q_out + T.prow * (15 * kD) + T.n0 + cc + 4 * half;
+        if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+        if (valid) {
 #pragma unroll
-        for (int tap = 0; tap < 15; ++tap) *reinterpret_cast<float4*>(dst + tap * kD) = *exh(buf, tap, r2, half);
-        return;
-      }
-      const float4 bb3 = __ldg(reinterpret_cast<const float4*>(p.bias3 + T.n0 + cc + 4 * half));
-      const float4 bb5 = __ldg(reinterpret_cast<const float4*>(p.bias5 + T.n0 + cc + 4 * half));
-      const float4 bb7 = __ldg(reinterpret_cast<const float4*>(p.bias7 + T.n0 + cc + 4 * half));
-      // P_{K,t}[rho] = Q_{K,t}[rho - t]: row r2 - t of the exchange buffer
-      float P7[7][4], P5[5][4], P3[3][4];
+          for (int t = 0; t < 5; ++t) {
+            uint32_t e[8];
 #pragma unroll
-      for (int t = -3; t <= 3; ++t) {
-        const float4 a = *exh(buf, t + 3, r2 - t, half);
-        P7[t + 3][0] = a.x; P7[t + 3][1] = a.y; P7[t + 3][2] = a.z; P7[t + 3][3] = a.w;
-        if (t >= -2 && t <= 2) {
-          const float4 c = *exh(buf, 7 + t + 2, r2 - t, half);
-          P5[t + 2][0] = c.x; P5[t + 2][1] = c.y; P5[t + 2][2] = c.z; P5[t + 2][3] = c.w;
+            for (int c = 0; c < 8; ++c) { const int idx = c * 5 + t; e[c] = idx < 32 ? v[idx] : f8[idx - 32]; }
+            stg256u(dst + (7 + t) * kD, e);
+          }
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            uint32_t e[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) e[c] = w[c * 3 + t];
+            stg256u(dst + (12 + t) * kD, e);
+          }
         }
-        if (t >= -1 && t <= 1) {
-          const float4 c = *exh(buf, 12 + t + 1, r2 - t, half);
-          P3[t + 1][0] = c.x; P3[t + 1][1] = c.y; P3[t + 1][2] = c.z; P3[t + 1][3] = c.w;
+        continue;
+      }
+
+      // P_{K,t}[rho] = Q_{K,t}[rho - t]: the value lane - t read from TMEM (every lane takes part in the shuffles)
+      auto shifted = [&](uint32_t u, int t) -> float {
+        const float f = __uint_as_float(u);
+        if (t > 0) return __shfl_up_sync(0xffffffffu, f, (unsigned)t);
+        if (t < 0) return __shfl_down_sync(0xffffffffu, f, (unsigned)(-t));
+        return f;
+      };
+      float out[7][8];
+      {   // conv7: 7 variants = left sums Lf_a = sum_{t=-a..-1} P_t plus right sums R_b = bias + sum_{t=0..b} P_t
+        uint32_t v[32], w[32];
+        tmem_ld32(t_row + BC_COL7, v);
+        tmem_ld32(t_row + BC_COL7 + 32, w);             // 56 used
+        float b7[8];
+        ldg8(p.bias7 + n0, b7);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float P[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) { const int idx = c * 7 + j; P[j] = shifted(idx < 32 ? v[idx] : w[idx - 32], j - 3); }
+          const float r0 = b7[c] + P[3], r1 = r0 + P[4], r2 = r1 + P[5], r3 = r2 + P[6];
+          const float l1 = P[2], l2 = l1 + P[1], l3 = l2 + P[0];
+          out[0][c] = l3 + r3;      // interior
+          out[1][c] = r3;           // k = 0
+          out[2][c] = l1 + r3;      // k = 1
+          out[3][c] = l2 + r3;      // k = 2
+          out[4][c] = l3 + r0;      // k = L-1
+          out[5][c] = l3 + r1;      // k = L-2
+          out[6][c] = l3 + r2;      // k = L-3
         }
       }
-      const float b3[4] = {bb3.x, bb3.y, bb3.z, bb3.w}, b5[4] = {bb5.x, bb5.y, bb5.z, bb5.w}, b7[4] = {bb7.x, bb7.y, bb7.z, bb7.w};
-      const float4 xa = T.x0v[cc / 8], xb = T.x1v[cc / 8];
-      const float x0[4] = {xa.x, xa.y, xa.z, xa.w}, x1[4] = {xb.x, xb.y, xb.z, xb.w};
-      float out[7][4];
+      {   // conv5
+        uint32_t v[32], f8[8];
+        tmem_ld32(t_row + BC_COL5, v);
+        tmem_ld8(t_row + BC_COL5 + 32, f8);
+        float b5[8];
+        ldg8(p.bias5 + n0, b5);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // R_b = bias + sum_{t=0..b} P_t ; Lf_a = sum_{t=-a..-1} P_t ; conv(a,b) = Lf_a + R_b
-        const float r7_0 = b7[j] + P7[3][j], r7_1 = r7_0 + P7[4][j], r7_2 = r7_1 + P7[5][j], r7_3 = r7_2 + P7[6][j];
-        const float l7_1 = P7[2][j], l7_2 = l7_1 + P7[1][j], l7_3 = l7_2 + P7[0][j];
-        const float r5_0 = b5[j] + P5[2][j], r5_1 = r5_0 + P5[3][j], r5_2 = r5_1 + P5[4][j];
-        const float l5_1 = P5[1][j], l5_2 = l5_1 + P5[0][j];
-        const float r3_0 = b3[j] + P3[1][j], r3_1 = r3_0 + P3[2][j];
-        const float l3_1 = P3[0][j];
-        const float idp = fmaxf(x0[j], x1[j]);          // identity + pool branches, slots k >= 1
-        const float full3 = l3_1 + r3_1, full5 = l5_2 + r5_2;
-        out[0][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_3, full5), full3), idp);
-        out[1][j] = fmaxf(fmaxf(fmaxf(r7_3, r5_2), r3_1), fmaxf(x0[j], 0.f));          // k = 0: pool sees the zero pad
-        out[2][j] = fmaxf(fmaxf(fmaxf(l7_1 + r7_3, l5_1 + r5_2), full3), idp);         // k = 1
-        out[3][j] = fmaxf(fmaxf(fmaxf(l7_2 + r7_3, full5), full3), idp);               // k = 2
-        out[4][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_0, l5_2 + r5_0), l3_1 + r3_0), idp);   // k = L-1
-        out[5][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_1, l5_2 + r5_1), full3), idp);         // k = L-2
-        out[6][j] = fmaxf(fmaxf(fmaxf(l7_3 + r7_2, full5), full3), idp);               // k = L-3
-      }
-      if (!(p.ablate & 2) || out[0][0] == 123.456f) {
-        float* dst = p.pb + T.prow * (7 * kD) + T.n0 + cc + 4 * half;
+        for (int c = 0; c < 8; ++c) {
+          float P[5];
 #pragma unroll
-        for (int v = 0; v < 7; ++v)
-          *reinterpret_cast<float4*>(dst + v * kD) = make_float4(out[v][0], out[v][1], out[v][2], out[v][3]);
+          for (int j = 0; j < 5; ++j) { const int idx = c * 5 + j; P[j] = shifted(idx < 32 ? v[idx] : f8[idx - 32], j - 2); }
+          const float r0 = b5[c] + P[2], r1 = r0 + P[3], r2 = r1 + P[4];
+          const float l1 = P[1], l2 = l1 + P[0];
+          const float full = l2 + r2;
+          out[0][c] = fmaxf(out[0][c], full);
+          out[1][c] = fmaxf(out[1][c], r2);
+          out[2][c] = fmaxf(out[2][c], l1 + r2);
+          out[3][c] = fmaxf(out[3][c], full);
+          out[4][c] = fmaxf(out[4][c], l2 + r0);
+          out[5][c] = fmaxf(out[5][c], l2 + r1);
+          out[6][c] = fmaxf(out[6][c], full);
+        }
       }
-    };
-    // Software pipeline over the 8-channel chunks of this CTA's tiles with a DOUBLE-BUFFERED exchange buffer:
-    // between two barriers every warp runs phase 1 of chunk j+1 (TMEM latency) and phase 2 of chunk j (shared
-    // memory, math, stores), so the warps of an SM sub-partition overlap the one with the other and a tile
-    // costs two barriers instead of four.  Buffer (j+1)&1 was last read in phase 2 of chunk j-1, which every
-    // warp finished before the barrier in between.
-    int64_t tile = tile0;
-    if (tile < p.num_tiles) {
-      TileInfo cur, nxt;
-      int it = 0;
-      load_tile(tile, it, cur);
-      phase1(cur, 0, 0);
-      for (;;) {
-        epi_barrier();
-        phase1(cur, 8, 1);
-        phase2(cur, 0, 0);
-        epi_barrier();
-        const int64_t ntile = tile + tile_stride;
-        if (ntile < p.num_tiles) { load_tile(ntile, it + 1, nxt); phase1(nxt, 0, 0); }
-        phase2(cur, 8, 1);
-        if (ntile >= p.num_tiles) break;
-        cur = nxt; tile = ntile; ++it;
+      {   // conv3, then the identity and pool branches (pool = max with the next row; slot 0 sees the zero pad)
+        uint32_t v[32];
+        tmem_ld32(t_row + BC_COL3, v);                  // 24 used (columns up to 247 of the 256-column buffer)
+        float b3[8];
+        ldg8(p.bias3 + n0, b3);
+        tmem_ld_wait();
+        tc_fence_before();                              // last TMEM read of this tile: hand the buffer back
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float P[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) P[j] = shifted(v[c * 3 + j], j - 1);
+          const float r0 = b3[c] + P[1], r1 = r0 + P[2];
+          const float l1 = P[0];
+          const float full = l1 + r1;
+          const float idp = fmaxf(x0[c], x1[c]);
+          out[0][c] = fmaxf(fmaxf(out[0][c], full), idp);
+          out[1][c] = fmaxf(fmaxf(out[1][c], r1), fmaxf(x0[c], 0.f));
+          out[2][c] = fmaxf(fmaxf(out[2][c], full), idp);
+          out[3][c] = fmaxf(fmaxf(out[3][c], full), idp);
+          out[4][c] = fmaxf(fmaxf(out[4][c], l1 + r0), idp);
+          out[5][c] = fmaxf(fmaxf(out[5][c], full), idp);
+          out[6][c] = fmaxf(fmaxf(out[6][c], full), idp);
+        }
+      }
+      if (valid) {
+        float* dst = p.pb + prow * (7 * kD) + n0;       // 32 bytes per variant: whole sectors
+#pragma unroll
+        for (int v = 0; v < 7; ++v) stg256(dst + v * kD, out[v]);
       }
     }
   }
@@ -369,14 +399,13 @@ int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, 
 
 static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
   using namespace umma;
-  p.num_tiles = ((p.pb_rows + 2 * BC_OUT - 1) / (2 * BC_OUT)) * (kD / BC_NCH);      // a CTA pair emits 2 x 122 rows
-  static const int abl = env_int("TMR_BC_ABL", 0);
-  p.ablate = abl;
+  const int64_t rows_per_pair = 2 * (p.raw ? BC_BM : BC_OUT);                       // a CTA pair emits 2 x 104 rows (2 x 128 raw)
+  p.num_tiles = ((p.pb_rows + rows_per_pair - 1) / rows_per_pair) * BC_NTILES;
   CUtensorMap tx, tw3, tw5, tw7;
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
     uint64_t str[1] = {(uint64_t)kD * 2};
-    uint32_t box[2] = {BC_BK, BC_BM};
+    uint32_t box[2] = {BC_BK, BC_GROUP};                                            // one lane quarter's 32 rows
     TMR_TRY(make_tmap(&tx, bank16, 2, dims, str, box, 2));
     const half_t* pr = mirror16<TimeConvPacked>(packed);
     const half_t* w[3] = {pr + TimeConvPacked::w3_off, pr + TimeConvPacked::w5_off, pr + TimeConvPacked::w7_off};
@@ -389,7 +418,11 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
       TMR_TRY(make_tmap(tw[i], w[i], 3, dw, sw, bw, 2));
     }
   }
-  TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
+  static bool attr_set = false;
+  if (!attr_set) {
+    TMR_CUDA(cudaFuncSetAttribute(umma_bankconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM_BYTES));
+    attr_set = true;
+  }
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
