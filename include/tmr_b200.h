@@ -203,10 +203,11 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
  *   starts must be valid clip starts of the table, in range of feats, ascending (checked by BankInference on
  *   the host); they need not be distinct. */
 /* The bank-level TimeConv alone: pb[(row - row_base)*7 + v][D] for bank rows row_base .. row_base+pb_rows-1,
- * v = 0 interior slot, 1..3 slot k = 0,1,2, 4..6 slot k = L-1, L-2, L-3 (see tmrnet_b200/csrc/umma_bankconv.cu). */
+ * v = 0 interior slot, 1..3 slot k = 0,1,2, 4..6 slot k = L-1, L-2, L-3 (see tmrnet_b200/csrc/umma_bankconv.cu).
+ * pb receives FP16 values (pb_rows*7*D halves, 16-byte aligned): round-to-nearest of the fp32 TimeConv output. */
 size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D);
 int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
-                     int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream);
+                     int64_t pb_rows, int D, void* pb, void* workspace, size_t workspace_bytes, void* stream);
 size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int n_irregular_rows,
                                              int64_t pb_rows, int L, int D);
 int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_packed,

@@ -2,6 +2,8 @@
 """Time umma_bankconv_kernel alone on the bench bank (env TMR_BC_ABL selects timing ablations)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tmrnet_b200 import _lib, build
+if os.environ.get("TMR_BC_ABL"): _lib.LIB_PATH = build.LIB_EXP
 import tmrnet_b200 as tb
 from tmrnet_b200 import ops, synth
 dev = torch.device("cuda:0")

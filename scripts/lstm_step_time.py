@@ -1,11 +1,22 @@
 #!/usr/bin/env python
-"""Recurrent-step time of the LSTM on a bench-sized batch: (seq-step LSTM - 1-step LSTM) / (seq - 1), CUDA events.
-Usage: lstm_step_time.py [B]   (env TMR_LSTM_WS=0: streamed GEMM engine; TMR_LSTM_WS_CFG=16: 16 epilogue warps)"""
+"""Recurrent-step time of the LSTM on a bench-sized batch: (seq-step LSTM - 2-step LSTM) / (seq - 2), CUDA events.
+Usage: lstm_step_time.py [B] [--lib path/to/variant.so] [--check]
+(--lib: a variant library built for an A/B measurement; --check: h_T of 600 clips against the CPU oracle)"""
 import os, sys
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+argv = [a for a in sys.argv[1:]]
+lib_path = None
+if "--lib" in argv:
+    i = argv.index("--lib"); lib_path = argv[i + 1]; del argv[i:i + 2]
+check = "--check" in argv
+argv = [a for a in argv if a != "--check"]
+sys.argv = [sys.argv[0]] + argv
+from tmrnet_b200 import _lib
+if lib_path:
+    _lib.LIB_PATH = os.path.abspath(lib_path)
 import tmrnet_b200 as tb
 from tmrnet_b200 import ops, synth
 
@@ -31,8 +42,19 @@ def timeit(fn, reps=20):
 
 
 t10 = timeit(lambda: ops.lstm_last_frames(pk, feats, starts, seq, "f16"))
-t1 = timeit(lambda: ops.lstm_last_frames(pk, feats, starts, 1, "f16"))
-step = (t10 - t1) / (seq - 1)
-print(f"B={B} ws={os.environ.get('TMR_LSTM_WS', '1')} cfg={os.environ.get('TMR_LSTM_WS_CFG', '8')}: "
-      f"10-step {t10*1e3:.1f} us, 1-step {t1*1e3:.1f} us, recurrent step {step*1e3:.1f} us "
+t1 = timeit(lambda: ops.lstm_last_frames(pk, feats, starts, 2, "f16"))
+step = (t10 - t1) / (seq - 2)
+print(f"B={B} lib={os.path.basename(lib_path) if lib_path else 'product'}: "
+      f"10-step {t10*1e3:.1f} us, 2-step {t1*1e3:.1f} us, recurrent step {step*1e3:.1f} us (x9 = {9*step*1e3:.0f} us) "
       f"= {B * 14336 / step / 1e6:.0f} GB/s (14 KB/clip), {B * 2.097152e6 / (step * 1e-3) / 1e12:.0f} TFLOP/s")
+
+if check:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tmr_oracle as orc
+    n = 600
+    got = ops.lstm_last_frames(pk, feats[:n + seq - 1], starts[:n], seq, "f16").cpu()
+    fh = feats[:n + seq - 1].cpu().numpy()
+    ref = orc.lstm_last(torch.from_numpy(np.stack([fh[s:s + seq] for s in range(n)])), sd)
+    err = float((got - ref).abs().max() / ref.abs().max())
+    full = ops.lstm_last_frames(pk, feats, starts, seq, "f16")[:n].cpu()
+    print(f"  h_T of {n} clips vs oracle: rel err {err:.2e}; same clips inside the {B}-clip launch: max |diff| {float((full - got).abs().max()):.1e}")

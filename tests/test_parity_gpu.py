@@ -618,6 +618,7 @@ def test_bankconv_variants_match_per_clip_timeconv(L):
     m = _model(7)
     pk = m.time_conv.packed()
     pb = ops.bankconv(pk, torch.from_numpy(bank).to(dev), 0, n_rows).cpu()
+    assert pb.dtype == torch.float16                    # PB is stored in fp16 (round-to-nearest of the fp32 result)
     pb_part = ops.bankconv(pk, torch.from_numpy(bank).to(dev), 130, 200).cpu()       # arbitrary row range
     assert torch.equal(pb_part[3:-3], pb[133:327])
     r0 = np.arange(L + 2, n_rows - 5)
@@ -625,9 +626,10 @@ def test_bankconv_variants_match_per_clip_timeconv(L):
     win = torch.from_numpy(bank[rows])
     k = np.arange(L)
     v = np.where(k <= 2, k + 1, np.where(L - 1 - k <= 2, 4 + (L - 1 - k), 0))
-    ded = pb[torch.from_numpy(rows), torch.from_numpy(np.broadcast_to(v, rows.shape).copy())]
+    ded = pb[torch.from_numpy(rows), torch.from_numpy(np.broadcast_to(v, rows.shape).copy())].float()
     gen = ops.timeconv_max(pk, win.to(dev), "f16").cpu()
-    assert rel_err(ded, gen) < 2e-5
+    assert rel_err(ded, gen.half().float()) < 6e-4      # one fp16 ulp where the fp32 sums straddle a rounding boundary
+    assert rel_err(ded, gen) < 6e-4
     assert rel_err(ded, orc.timeconv(win, _sd(7), dtype=torch.float64)) < TOL["f16"]
 
 

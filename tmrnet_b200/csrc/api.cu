@@ -62,7 +62,7 @@ static inline size_t fbytes(size_t n_floats) { return align_up(n_floats * sizeof
 // producer (which then writes fp16 instead of fp32) or by a conversion pass into `scratch`; weights come
 // from the fp16 mirror of the pack.  fp32 mode touches neither.  Workspace buffers keep their fp32 sizes.
 struct NLWs { float* w0; float* w1; float* s; };
-struct PbSrc { const float* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output
+struct PbSrc { const half_t* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output (PB in fp16)
 // defer_residual (tensor-core head paths): `out` gets W4 r + b4 only; the consumer (classifier_impl with
 // y1_plus_St) adds St while it converts [St || y1] for its GEMM
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
@@ -519,7 +519,7 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
 
 size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D) { return fbytes((size_t)((pb_rows > 0 ? pb_rows : 1) + 8) * D); }
 int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_rows, int64_t row_base,
-                     int64_t pb_rows, int D, float* pb, void* workspace, size_t workspace_bytes, void* stream) {
+                     int64_t pb_rows, int D, void* pb, void* workspace, size_t workspace_bytes, void* stream) {
   TMR_TRY(check_dims(D));
   TMR_TRY(check_mode(TMR_MATH_F16));
   TMR_CHECK_ARG(pb_rows >= 0 && row_base >= 0 && row_base + pb_rows <= n_rows, "bankconv: row range outside the bank");
@@ -534,7 +534,8 @@ int tmr_bankconv_fwd(const void* timeconv_packed, const float* bank, int64_t n_r
   cudaStream_t st = (cudaStream_t)stream;
   half_t* bank16 = reinterpret_cast<half_t*>(bank_r);
   TMR_TRY(launch_to_half(bank + r_lo * kD, bank16, (r_hi - r_lo) * kD, st));
-  return umma_bankconv((const float*)timeconv_packed, bank, bank16, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows, pb, st);
+  return umma_bankconv((const float*)timeconv_packed, bank, bank16, n_rows, r_lo, r_hi - r_lo, row_base, pb_rows,
+                       reinterpret_cast<half_t*>(pb), st);
 }
 
 size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n_irregular, int n_irregular_rows,
@@ -545,7 +546,7 @@ size_t tmr_head_frames_dedup_workspace_bytes(int64_t n_feat_frames, int B, int n
   const size_t nr = (size_t)(n_irregular_rows > 0 ? n_irregular_rows : 0);
   const size_t irr = (n_irregular > 0 && nr > 0) ? fbytes(nr * 15 * D) + fbytes(nr * D) + fbytes(ni * L)
                                                  : 2 * fbytes(ni * L * D);
-  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + fbytes((pr + 8) * D) + fbytes(pr * 7 * D) +
+  return tmr_lstm_workspace_bytes(n_feat_frames, (int)b, D) + fbytes((pr + 8) * D) + fbytes((pr * 7 * D + 1) / 2) +
          fbytes(ni * L * D) + irr + 2 * fbytes(b * D) + tmr_nlblock_workspace_bytes((int)b, D) +
          tmr_classifier_workspace_bytes((int)b, D);
 }
@@ -583,7 +584,7 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   const int64_t r_lo = pb_row_base - 3 > 0 ? pb_row_base - 3 : 0;                       // fp16 bank slice
   const int64_t r_hi = pb_row_base + pb_rows + 4 < n_rows ? pb_row_base + pb_rows + 4 : n_rows;
   float* bank_r = cv.take((size_t)(pb_rows + 8) * kD);
-  float* pb = cv.take((size_t)(pb_rows > 0 ? pb_rows : 1) * 7 * kD);
+  half_t* pb = reinterpret_cast<half_t*>(cv.take(((size_t)(pb_rows > 0 ? pb_rows : 1) * 7 * kD + 1) / 2));   // fp16
   const size_t ni = (size_t)(n_irregular > 0 ? n_irregular : 1);
   float* lt_i = cv.take(ni * L * kD);
   float *win_i = nullptr, *xr_i = nullptr, *q_i = nullptr, *xc_i = nullptr;

@@ -352,23 +352,103 @@ attention_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int 
   attention_body(u, b, L, scale, a, half_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
 }
 
-// Attention over the bank-level TimeConv output PB[row][7][512] (umma_bankconv.cu).  src[b] >= 0:
-// the clip's window is the contiguous run of bank rows whose slot 0 is PB row src[b]; slot k reads
-// PB row src[b]-k in the variant its distance to the window edges selects.  src[b] < 0: an
-// irregular clip (window crosses a video start) whose TimeConv output lt_irr[-1-src[b]] was computed
-// per clip by the general kernel.
+// 16 consecutive fp16 (one 32-byte sector) -> 8 packed fp32 pairs
+__device__ __forceinline__ void ldg_h16(const half_t* p, uint64_t (&x2)[8]) {
+  uint32_t v[8];
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(v[i]));
+    x2[i] = pk2(lo, hi);
+  }
+}
+
+// Attention over the bank-level TimeConv output PB[row][7][512] (fp16, umma_bankconv.cu) for a regular clip: the
+// window is the contiguous run of bank rows whose slot 0 is PB row s; slot k reads PB row s-k in the variant its
+// distance to the window edges selects.  A lane owns 16 CONSECUTIVE channels (one 32-byte sector of an fp16 row, one
+// 256-bit load per slot; loads allocate in L1, where the four warps of a CTA - four consecutive clips - share the
+// interior rows of their windows).
+__device__ __forceinline__ void attention_body_pb16(const float* __restrict__ u, const half_t* __restrict__ pb, int b, int s,
+                                                    int L, float scale, void* __restrict__ a, int half_out) {
+  const int lane = threadIdx.x & 31;
+  uint64_t u2[8], acc2[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(u + (int64_t)b * kD + lane * 16) + i);
+    u2[2 * i] = pk2(q.x, q.y); u2[2 * i + 1] = pk2(q.z, q.w);
+    acc2[2 * i] = acc2[2 * i + 1] = pk2(0.f, 0.f);
+  }
+  float run_max = -INFINITY, run_sum = 0.f;
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    uint64_t x2[KB][8];
+    float d[KB];
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      const int k = min(k0 + kk, L - 1);                 // slots past L re-read the last one and are masked below
+      const int v = (k <= 2) ? k + 1 : ((L - 1 - k <= 2) ? 4 + (L - 1 - k) : 0);
+      ldg_h16(pb + ((int64_t)(s - k) * 7 + v) * kD + lane * 16, x2[kk]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      uint64_t p2 = fmul2(x2[kk][0], u2[0]);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) p2 = ffma2(x2[kk][i], u2[i], p2);
+      float pe, po;
+      upk2(p2, pe, po);
+      d[kk] = pe + po;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) d[kk] = warp_sum(d[kk]);
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      d[kk] = (k0 + kk < L) ? d[kk] * scale : -INFINITY;
+      cmax = fmaxf(cmax, d[kk]);
+    }
+    const float new_max = fmaxf(run_max, cmax);
+    const float corr = expf(run_max - new_max);          // 0 on the first chunk (run_max = -inf)
+    run_sum *= corr;
+    const uint64_t corr2 = pk2(corr, corr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc2[i] = fmul2(acc2[i], corr2);
+#pragma unroll
+    for (int kk = 0; kk < KB; ++kk) {
+      const float p = expf(d[kk] - new_max);             // exp(-inf) = 0 for masked slots
+      run_sum += p;
+      const uint64_t pp = pk2(p, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc2[i] = ffma2(pp, x2[kk][i], acc2[i]);
+    }
+    run_max = new_max;
+  }
+  const float inv = 1.f / run_sum;
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { upk2(acc2[i], o[2 * i], o[2 * i + 1]); o[2 * i] *= inv; o[2 * i + 1] *= inv; }
+  if (half_out) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<half_t*>(a) + (int64_t)b * kD + lane * 16);
+    dst[0] = make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
+    dst[1] = make_uint4(pack_h2(o[8], o[9]), pack_h2(o[10], o[11]), pack_h2(o[12], o[13]), pack_h2(o[14], o[15]));
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a) + (int64_t)b * kD + lane * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  }
+}
+
+// src[b] >= 0: a regular clip, window read from PB (above).  src[b] < 0: an irregular clip (window crosses a video
+// start) whose TimeConv output lt_irr[-1-src[b]] (fp32) was assembled per clip.
 __global__ void __launch_bounds__(kAttnWarps * 32)
-attention_pb_kernel(const float* __restrict__ u, const float* __restrict__ pb, const float* __restrict__ lt_irr,
+attention_pb_kernel(const float* __restrict__ u, const half_t* __restrict__ pb, const float* __restrict__ lt_irr,
                     const int32_t* __restrict__ src, int B, int L, float scale, void* __restrict__ a,
                     int half_out) {
   const int b = blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
   if (b >= B) return;
   const int s = src[b];
   if (s >= 0) {
-    attention_body(u, b, L, scale, a, half_out, [&](int k) {
-      const int v = (k <= 2) ? k + 1 : ((L - 1 - k <= 2) ? 4 + (L - 1 - k) : 0);
-      return reinterpret_cast<const float4*>(pb + ((int64_t)(s - k) * 7 + v) * kD);
-    });
+    attention_body_pb16(u, pb, b, s, L, scale, a, half_out);
   } else {
     const float4* base = reinterpret_cast<const float4*>(lt_irr + (int64_t)(-1 - s) * L * kD);
     attention_body(u, b, L, scale, a, half_out, [&](int k) { return base + (int64_t)k * (kD / 4); });
@@ -383,7 +463,7 @@ int launch_attention(const float* u, const float* Lt, int B, int L, void* a, int
   return TMR_OK;
 }
 
-int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
+int launch_attention_pb(const float* u, const half_t* pb, const float* lt_irr, const int32_t* src, int B, int L,
                         void* a, int half_out, cudaStream_t st) {
   if (B == 0) return TMR_OK;
   const float scale = (float)0.044194173824159216;

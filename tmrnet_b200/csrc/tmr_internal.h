@@ -53,9 +53,9 @@ int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* start
                       float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st, const float* xp_base,
                       int64_t xp_rows, int64_t xp_row0);
 bool umma_available();
-// bank-level TimeConv: pb[(row-row_base)*7 + variant][512] for bank rows row_base .. +pb_rows-1
+// bank-level TimeConv: pb[(row-row_base)*7 + variant][512] (fp16) for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,
-                  int64_t r_cnt, int64_t row_base, int64_t pb_rows, float* pb, cudaStream_t st);
+                  int64_t r_cnt, int64_t row_base, int64_t pb_rows, half_t* pb, cudaStream_t st);
 
 // ---- memory-bound kernels (kernels_mem.cu) ----
 int launch_gather(const float* bank, int64_t n_rows, const int32_t* f2r, const int32_t* f2v,
@@ -74,8 +74,8 @@ int launch_lstm_cell0(const float* xp, const int64_t* starts, int seq, float* h,
                       cudaStream_t st, bool fast_math = false);
 // a[b,:] = sum_k softmax_k(scale * u[b].Lt[b,k]) Lt[b,k,:]; half_out: `a` receives fp16 (half_t[B,512])
 int launch_attention(const float* u, const float* Lt, int B, int L, void* a, int half_out, cudaStream_t st);
-// same attention over the bank-level TimeConv output (see umma_bankconv.cu)
-int launch_attention_pb(const float* u, const float* pb, const float* lt_irr, const int32_t* src, int B, int L,
+// same attention over the bank-level TimeConv output (fp16 PB, see umma_bankconv.cu; irregular clips' rows are fp32)
+int launch_attention_pb(const float* u, const half_t* pb, const float* lt_irr, const int32_t* src, int B, int L,
                         void* a, int half_out, cudaStream_t st);
 // y = relu(layer_norm(v) * w + b) over rows of 512; half_out: y receives fp16
 int launch_layernorm_relu(const float* v, const float* w, const float* b, int B, void* y,

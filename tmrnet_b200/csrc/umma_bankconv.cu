@@ -13,7 +13,10 @@
 // row, the SEVEN variants a window can ask of that row:
 //     v0: interior      v1..v3: slot k = 0,1,2 (left-clipped)      v4..v6: slot k = L-1,L-2,L-3
 // each = max(bank[rho], pool, conv3, conv5, conv7) with pool = bank[rho+1] (slot k-1) or 0 for v1
-// (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512]; attention_pb_kernel consumes it.
+// (F.pad + MaxPool1d(2,1), NLB:67-68).  Output PB[row][7][512] in fp16 (round-to-nearest of the fp32 result: the
+// attention that consumes it - attention_pb_kernel - hands its own output to the next GEMM in fp16 anyway; measured on
+// the oracle: +4.6e-5 relative on the logits, against 6.7e-4 for the whole fp16-operand path).  PB is 6/7 edge variants
+// that exactly one clip reads, so its bytes are most of the DRAM traffic of this kernel AND of the attention.
 // 236 MFLOP/clip become 7.9 MFLOP/row; only summation order changes.
 //
 // Layout of the work (round 2; the first version exchanged accumulator rows through shared memory between two
@@ -26,6 +29,12 @@
 //  * the fp16 rows of a CTA (128 x 512 = 128 KB) stay RESIDENT in shared memory for all 32 channel tiles of their
 //    row block; only the stacked tap weights (15 KB per CTA and 64-channel k-step) stream.  L2 -> SM traffic per
 //    launch halves, and the six-stage weight ring is all the staging the kernel needs.
+//  * the 7 variants leave through shared memory and ONE TMA store per warp and tile (a [26 rows][7 variants]
+//    [8 channels] fp16 box of PB through a 2.9 KB staging tile; what is left of shared memory beside the resident rows
+//    goes to the weight ring - with three weight stages the MMAs starved, tensor pipe 48 %): a row-per-thread epilogue writing 32-byte pieces with st.global costs one L1 wavefront per lane and
+//    instruction, and with the exact-value loads of the identity / pool branches that kept the LSU data pipe 75 % busy
+//    - the limiter of the first warp-local version (ncu: tensor pipe 61 %).  The pool branch's next-row values come
+//    from the neighbouring lane by shuffle instead of a second load.
 //  * a CTA pair owns a CONTIGUOUS range of (row block, channel tile) items, equal for all pairs, so the grid is
 //    balanced to one tile and a pair reloads its rows only when its range crosses into the next row block.
 #include <stdlib.h>
@@ -45,7 +54,7 @@ constexpr int BC_BK = 64;                  // fp16 input channels per k-step = o
 constexpr int BC_KB = kD / BC_BK;          // 8 k-steps
 constexpr int BC_A_BYTES = BC_BM * BC_BK * 2;                  // 16 KB: the CTA's rows for one k-step
 constexpr int BC_A_TOTAL = BC_KB * BC_A_BYTES;                 // 128 KB: resident for the whole row block
-constexpr int BC_STAGES = 6;               // weight ring
+constexpr int BC_STAGES = 4;               // weight ring
 // 2-SM MMA (cta_group::2): a CTA PAIR multiplies 2 x 128 rows by the 240 stacked weight rows of the tile's 16
 // channels; each CTA stages its own 128 bank rows and HALF of the weight rows - those of 8 channels:
 constexpr int BC_HCH = BC_NCH / 2;                             // channels whose weight rows one CTA stages
@@ -53,8 +62,13 @@ constexpr int BC_W7_BYTES = 7 * BC_HCH * BC_BK * 2;            //  7 KB: rows or
 constexpr int BC_W5_BYTES = 5 * BC_HCH * BC_BK * 2;            //  5 KB
 constexpr int BC_W3_BYTES = 3 * BC_HCH * BC_BK * 2;            //  3 KB
 constexpr int BC_W_BYTES = BC_W7_BYTES + BC_W5_BYTES + BC_W3_BYTES;   // 15 KB = 120 rows per CTA: ONE MMA of N = 240 per k-step
-constexpr int BC_SMEM_BYTES = BC_A_TOTAL + BC_STAGES * BC_W_BYTES + 1024 + 512;
 constexpr int BC_EPI_WARPS = 8;            // two per TMEM lane quarter: one per 8-channel half of the tile
+// output staging of one epilogue warp: [26 rows][7 variants][8 channels] fp16, dense (the box of its TMA store).  The
+// row pitch of 112 bytes puts the 16-byte stores of eight consecutive rows (a quarter warp) into eight different bank
+// groups.
+constexpr int BC_OUT_PITCH = 7 * BC_HCH * 2;                   // 112 bytes per row
+constexpr int BC_OUT_BYTES = ((BC_GOUT * BC_OUT_PITCH + 127) / 128) * 128;     // 2944 bytes per warp
+constexpr int BC_SMEM_BYTES = BC_A_TOTAL + BC_STAGES * BC_W_BYTES + BC_EPI_WARPS * BC_OUT_BYTES + 1024 + 512;
 constexpr int BC_THREADS = 64 + 32 * BC_EPI_WARPS;
 constexpr int BC_TMEM_COLS = 512;          // 2 accumulator buffers of 256 columns (240 used)
 constexpr int BC_N = 15 * BC_NCH;          // 240
@@ -65,6 +79,16 @@ static_assert(BC_SMEM_BYTES <= 227 * 1024, "bankconv: shared memory budget");
 __device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// TMA store of a rank-3 box from shared memory (bulk async-group completion); elements outside the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&u)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -79,11 +103,21 @@ constexpr int BC_HALF_COLS = 15 * BC_HCH;  // 120
 constexpr int BC_COL7 = 0, BC_COL5 = 7 * BC_HCH, BC_COL3 = 12 * BC_HCH;
 
 struct BankConvParams {
-  const float* bank; float* pb; const float* bias3; const float* bias5; const float* bias7;
+  const float* bank; half_t* pb; const float* bias3; const float* bias5; const float* bias7;
   int64_t n_rows; int64_t row_base; int64_t pb_rows; int64_t r_lo;   // bank_r holds rows r_lo .. (TMA row = row - r_lo)
   int64_t num_tiles;                                                  // row blocks x 32 channel tiles
   float* q_out; int raw;   // raw: emit the UNSHIFTED tap products Q[row][15][512] instead of the 7 variants
+#ifdef TMR_EXPERIMENT
+  int ablate;              // timing experiments, env TMR_BC_ABL: 1 = MMAs of N = 256, 2 = no epilogue work, 4 = no weight
+                           // loads (stale shared memory), 16 = no output store (all WRONG results); 8 = st.global
+                           // instead of the TMA store (correct)
+#endif
 };
+#ifdef TMR_EXPERIMENT
+#define BC_ABL(p, bit) (((p).ablate & (bit)) != 0)
+#else
+#define BC_ABL(p, bit) false
+#endif
 
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
 // (warp w reads TMEM lane quarter w & 3 and owns the 8-channel half (w - 2) >> 2 of the tile).  The MMAs compute
@@ -94,12 +128,13 @@ struct BankConvParams {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BC_THREADS, 1)
 umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w3,
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
-                     const BankConvParams p) {
+                     const __grid_constant__ CUtensorMap tma_pb, const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [BC_KB][128 rows][64 fp16], resident per row block
   uint8_t* sW = sA + BC_A_TOTAL;                        // [BC_STAGES][120 weight rows][64 fp16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + BC_STAGES * BC_W_BYTES);
+  uint8_t* sO = sW + BC_STAGES * BC_W_BYTES;            // [BC_EPI_WARPS] output staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + BC_EPI_WARPS * BC_OUT_BYTES);
   uint64_t* a_full = bars;                              // [BC_KB]      TMA -> MMA, once per row block
   uint64_t* a_empty = a_full + BC_KB;                   // [BC_KB]      MMA -> TMA: the block's last tile has read this k-step
   uint64_t* w_full = a_empty + BC_KB;                   // [BC_STAGES]
@@ -125,6 +160,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
+    if (!p.raw) tma_prefetch_desc(&tma_pb);
     for (int k = 0; k < BC_KB; ++k) { mbar_init(&a_full[k], 1); mbar_init(&a_empty[k], 1); }
     for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * BC_EPI_WARPS); }
@@ -160,6 +196,11 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           }
           mbar_wait(&w_empty[stage], phase ^ 1);
           uint8_t* sw = sW + stage * BC_W_BYTES;
+          if (BC_ABL(p, 4)) {
+            if (crank == 0) mbar_arrive(&w_full[stage]);
+            if (++stage == BC_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (crank == 0) mbar_expect_tx(&w_full[stage], 2 * BC_W_BYTES);
           tma_load_3d_2sm(sw, &tma_w7, &w_full[stage], c0, 0, n0);                             // [8 ch][7 taps] rows
           tma_load_3d_2sm(sw + BC_W7_BYTES, &tma_w5, &w_full[stage], c0, 0, n0);               // [8 ch][5 taps]
@@ -171,7 +212,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(2 * BC_BM, BC_N);
+      const uint32_t idesc = BC_ABL(p, 1) ? make_idesc_f16(2 * BC_BM, 256) : make_idesc_f16(2 * BC_BM, BC_N);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       int64_t rb_prev = -1; int nb = -1;
@@ -205,6 +246,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     const int q = warp & 3;                                     // TMEM lane quarter = row group
     const int part = (warp - 2) >> 2;                           // 8-channel half of the tile
     const bool lane_emits = lane >= halo && lane < BC_GROUP - halo;
+    uint8_t* so = sO + (warp - 2) * BC_OUT_BYTES;               // my staging tile
     int it = 0;
     for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
       const int64_t rb = tile / BC_NTILES;
@@ -213,17 +255,20 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       const int64_t rho = group_row0(rb, q) + lane;             // my bank row
       const int64_t prow = rho - p.row_base;
       const bool valid = lane_emits && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
-      // exact bank values of my row and of the next one (identity / pool branches), requested before the
-      // accumulator is awaited so their latency hides behind the main loop
-      float x0[8], x1[8];
+      // exact bank values of my row (identity branch; the pool branch takes the next row's from lane + 1), requested
+      // before the accumulator is awaited so their latency hides behind the main loop.  Rows outside the bank are 0.
+      float x0[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { x0[k] = 0.f; x1[k] = 0.f; }
-      if (valid && !p.raw) {
-        ldg8(p.bank + rho * kD + n0, x0);
-        if (rho + 1 < p.n_rows) ldg8(p.bank + (rho + 1) * kD + n0, x1);
-      }
+      for (int k = 0; k < 8; ++k) x0[k] = 0.f;
+      if (!p.raw && rho >= 0 && rho < p.n_rows) ldg8(p.bank + rho * kD + n0, x0);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (BC_ABL(p, 2)) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+        continue;
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + part * BC_HALF_COLS);
 
       if (p.raw) {
@@ -341,7 +386,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           const float r0 = b3[c] + P[1], r1 = r0 + P[2];
           const float l1 = P[0];
           const float full = l1 + r1;
-          const float idp = fmaxf(x0[c], x1[c]);
+          const float idp = fmaxf(x0[c], __shfl_down_sync(0xffffffffu, x0[c], 1));   // lane 31 is never emitted
           out[0][c] = fmaxf(fmaxf(out[0][c], full), idp);
           out[1][c] = fmaxf(fmaxf(out[1][c], r1), fmaxf(x0[c], 0.f));
           out[2][c] = fmaxf(fmaxf(out[2][c], full), idp);
@@ -351,12 +396,35 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           out[6][c] = fmaxf(fmaxf(out[6][c], full), idp);
         }
       }
-      if (valid) {
-        float* dst = p.pb + prow * (7 * kD) + n0;       // 32 bytes per variant: whole sectors
+      // out -> fp16 -> my staging tile [row][variant][8 channels] -> one TMA store of the [26][7][8] box (rows past the
+      // end of PB are clipped by the tensor map).  The previous tile's store must have READ the staging tile first.
+      if (BC_ABL(p, 8 | 16)) {                          // experiment: 16-byte st.global per variant (8), no store at all (16)
+        if (BC_ABL(p, 8) && valid) {
+          half_t* dst = p.pb + prow * (7 * kD) + n0;
 #pragma unroll
-        for (int v = 0; v < 7; ++v) stg256(dst + v * kD, out[v]);
+          for (int v = 0; v < 7; ++v)
+            *reinterpret_cast<uint4*>(dst + v * kD) = make_uint4(pack_h2(out[v][0], out[v][1]), pack_h2(out[v][2], out[v][3]),
+                                                                 pack_h2(out[v][4], out[v][5]), pack_h2(out[v][6], out[v][7]));
+        } else if (out[0][0] == 123.456f) {
+          p.pb[0] = 0;                                  // keeps the epilogue math alive
+        }
+        continue;
       }
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      if (lane_emits) {
+        uint8_t* row = so + (lane - halo) * BC_OUT_PITCH;
+#pragma unroll
+        for (int v = 0; v < 7; ++v)
+          sts128(row + v * 16, pack_h2(out[v][0], out[v][1]), pack_h2(out[v][2], out[v][3]), pack_h2(out[v][4], out[v][5]),
+                 pack_h2(out[v][6], out[v][7]));
+      }
+      fence_proxy_async_smem();                         // my generic-proxy writes before the async-proxy read
+      __syncwarp();
+      const int64_t prow0 = group_row0(rb, q) + halo - p.row_base;      // PB row of lane `halo`: >= 0
+      if (lane == 0 && prow0 < p.pb_rows) tma_store_3d(&tma_pb, so, n0, 0, (int)prow0);
     }
+    if (lane == 0) tma_store_wait_read();               // the staging tile outlives every store that reads it
   }
 
   tc_fence_before();
@@ -382,11 +450,11 @@ int umma_bankconv_raw(const float* packed, const half_t* rows16, int64_t n, floa
   return launch_bankconv(packed, rows16, n, p, st);
 }
 
-// pb[(row - row_base)*7 + v][512] for bank rows row_base .. row_base + pb_rows - 1.
+// pb[(row - row_base)*7 + v][512] (fp16) for bank rows row_base .. row_base + pb_rows - 1.
 // bank = exact values (identity / pool branches); bank16 = rows r_lo .. r_lo + r_cnt - 1 of the bank
 // in fp16 (MMA operand) — must cover row_base - 3 .. row_base + pb_rows + 2 where they exist.
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,
-                  int64_t r_cnt, int64_t row_base, int64_t pb_rows, float* pb, cudaStream_t st) {
+                  int64_t r_cnt, int64_t row_base, int64_t pb_rows, half_t* pb, cudaStream_t st) {
   using namespace umma;
   if (pb_rows <= 0) return TMR_OK;
   TMR_CHECK_ARG(n_rows < (int64_t)INT32_MAX - 256, "bankconv: bank too large");
@@ -401,7 +469,10 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
   using namespace umma;
   const int64_t rows_per_pair = 2 * (p.raw ? BC_BM : BC_OUT);                       // a CTA pair emits 2 x 104 rows (2 x 128 raw)
   p.num_tiles = ((p.pb_rows + rows_per_pair - 1) / rows_per_pair) * BC_NTILES;
-  CUtensorMap tx, tw3, tw5, tw7;
+#ifdef TMR_EXPERIMENT
+  p.ablate = env_int("TMR_BC_ABL", 0);
+#endif
+  CUtensorMap tx, tw3, tw5, tw7, tpb;
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
     uint64_t str[1] = {(uint64_t)kD * 2};
@@ -417,6 +488,13 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
       uint32_t bw[3] = {BC_BK, (uint32_t)taps, BC_HCH};
       TMR_TRY(make_tmap(tw[i], w[i], 3, dw, sw, bw, 2));
     }
+    tpb = tx;
+    if (!p.raw) {                      // PB[row][variant][channel] (fp16) viewed as (channel, variant, row): a warp's store box
+      uint64_t dp[3] = {(uint64_t)kD, 7, (uint64_t)p.pb_rows};
+      uint64_t sp[2] = {(uint64_t)kD * 2, (uint64_t)7 * kD * 2};
+      uint32_t bp[3] = {BC_HCH, 7, BC_GOUT};
+      TMR_TRY(make_tmap(&tpb, p.pb, 3, dp, sp, bp, 2, 0));
+    }
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -427,7 +505,7 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
-  umma_bankconv_kernel<<<(unsigned)(2 * pairs), BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, p);
+  umma_bankconv_kernel<<<(unsigned)(2 * pairs), BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, tpb, p);
   TMR_LAUNCH_CHECK("umma_bankconv_kernel");
   return TMR_OK;
 }

@@ -273,8 +273,8 @@ __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------
-// fp16 (elem_bytes 2) or fp32 (4) tensor of rank 2 or 3, innermost dimension contiguous, 128-byte (or 64-byte)
-// swizzle, zero OOB fill.
+// fp16 (elem_bytes 2) or fp32 (4) tensor of rank 2 or 3, innermost dimension contiguous, 128-byte (or 64-byte, or
+// with swizzle_bytes = 0 no) swizzle, zero OOB fill.
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int elem_bytes, int swizzle_bytes = 128);
 

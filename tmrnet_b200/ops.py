@@ -279,12 +279,12 @@ def linear(a, w, bias=None, relu=False, math_mode=None):
 
 
 def bankconv(timeconv_packed, bank, row_base: int = 0, pb_rows: int = None):
-    """Bank-level TimeConv (tensor-core mode only): (pb_rows, 7, 512) variants per bank row."""
+    """Bank-level TimeConv (tensor-core mode only): (pb_rows, 7, 512) variants per bank row, as float16."""
     bank = _dev(bank, "bank")
     if pb_rows is None:
         pb_rows = bank.shape[0] - row_base
     lib = _lib.load()
-    pb = torch.empty((pb_rows, 7, D), dtype=torch.float32, device=bank.device)
+    pb = torch.empty((pb_rows, 7, D), dtype=torch.float16, device=bank.device)
     ws = _ws(lib.tmr_bankconv_workspace_bytes(pb_rows, D), bank.device)
     with torch.cuda.device(bank.device):
         check(lib.tmr_bankconv_fwd(_ptr(timeconv_packed), _ptr(bank), bank.shape[0], int(row_base), int(pb_rows), D,
