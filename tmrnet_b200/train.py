@@ -166,6 +166,9 @@ class HeadTrainer:
             raise ValueError("batch size mismatch between x, long_feature and labels")
         if self.class_weight is not None and self.class_weight.numel() != Cn:
             raise ValueError(f"class_weight has {self.class_weight.numel()} entries for {Cn} classes")
+        # labels outside [0, C) would index the logits / class weights out of bounds in the fused loss kernel; torch's
+        # CrossEntropyLoss raises for them - so does this, as a device-side assert (no host synchronisation)
+        torch._assert_async(((labels >= 0) & (labels < Cn)).all())
         # parameters may have been moved / reassigned since construction (model.to(), load_state_dict keeps storage)
         if any(p is not None and p.data_ptr() != int(self._pp[i] or 0) for i, p in enumerate(self.params)):
             named = dict(self.model.named_parameters())
