@@ -3,6 +3,8 @@
 import os, sys, json
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tmrnet_b200 import _lib, build
+if os.environ.get("TMR_LSTM_PERSIST_MIN"): _lib.LIB_PATH = build.LIB_EXP      # experiment build reads the switch
 import tmrnet_b200 as tb
 from tmrnet_b200 import synth
 from tmrnet_b200.graphs import GraphedHead

@@ -310,7 +310,7 @@ class BankInference:
         """Kernel launches of one run() (bench.py's gpu_launches), counted from the launch sequences in csrc/api.cu.
         LSTM, fp32 mode: projection + cell0 + (seq-1) steps.  Tensor-core mode: feature conversion (none for fp16
         features) + row->clip table + projection (step 0 fused) + step-0 fix-up + the recurrence - ONE persistent launch
-        for batches of >= 256 clips, seq-1 step launches below.  Tail, fp32: gather | timeconv | q, u, attention, v,
+        for batches of >= 96 clips, seq-1 step launches below.  Tail, fp32: gather | timeconv | q, u, attention, v,
         layernorm, out | fc_h_c, fc_c; tensor-core mode folds q, u into one GEMM and adds the fp16 conversions of the
         window, St and [St|y1]; the bank-level path replaces gather + conversion + timeconv over all clips by
         conversion(bank rows) + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw
@@ -325,7 +325,7 @@ class BankInference:
         def lstm(b):
             if self.seq == 1:
                 return (0 if feats_f16 else 1) + 1 + 1
-            rec = 1 if b >= 256 else self.seq - 1
+            rec = 1 if b >= 96 else self.seq - 1
             return (0 if feats_f16 else 1) + 1 + 1 + 1 + rec
 
         if not self._use_dedup():
