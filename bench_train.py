@@ -48,7 +48,6 @@ def run(batch=40, steps=20, warmup=3):
     model = tb.resnet_lstm(num_class=C, sequence_length=seq)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     model = model.to(dev)
-    tr = HeadTrainer(model, lr=5e-7, class_weight=np.ones(C, np.float32), seed=1)
     # union batch of world*B clips; rank r owns rows [r*B, (r+1)*B)
     x_all = torch.from_numpy(synth.features(world * B * seq, seed=7).reshape(world * B, seq, 2048)).to(dev)
     lf_all = torch.from_numpy(synth.bank(world * B * L, seed=8).reshape(world * B, L, 512)).to(dev)
@@ -56,52 +55,59 @@ def run(batch=40, steps=20, warmup=3):
     sl = slice(rank * B, (rank + 1) * B)
     x, lf, y = x_all[sl].contiguous(), lf_all[sl].contiguous(), y_all[sl].contiguous()
 
-    # correctness: all-reduced gradient == single-GPU gradient of the union batch
-    tr.forward_backward(x, lf, y, dropout=False)
-    tr.allreduce_grads()
-    reduced = tr.grads.flat.clone()
-    tr.forward_backward(x_all, lf_all, y_all, dropout=False)
-    union = tr.grads.flat.clone()
-    grad_err = float((reduced - union).abs().max() / union.abs().max())
-
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        tr.step(x, lf, y)
-    sync()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_fb = t_ar = t_sgd = 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e[0].record(); tr.forward_backward(x, lf, y)
-        e[1].record(); tr.allreduce_grads()
-        e[2].record(); tr.sgd_update()
-        e[3].record()
-        torch.cuda.synchronize()
-        t_fb += e[0].elapsed_time(e[1]); t_ar += e[1].elapsed_time(e[2]); t_sgd += e[2].elapsed_time(e[3])
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms, t_fb, t_ar, t_sgd, grad_err], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
+    def measure(mode):
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        tr = HeadTrainer(model, lr=5e-7, class_weight=np.ones(C, np.float32), seed=1, math_mode=mode)
+        # correctness: all-reduced gradient == single-GPU gradient of the union batch
+        tr.forward_backward(x, lf, y, dropout=False)
+        tr.allreduce_grads()
+        reduced = tr.grads.flat.clone()
+        tr.forward_backward(x_all, lf_all, y_all, dropout=False)
+        union = tr.grads.flat.clone()
+        grad_err = float((reduced - union).abs().max() / union.abs().max())
+        for _ in range(args.warmup):
+            tr.step(x, lf, y)
+        sync()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_fb = t_ar = t_sgd = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e[0].record(); tr.forward_backward(x, lf, y)
+            e[1].record(); tr.allreduce_grads()
+            e[2].record(); tr.sgd_update()
+            e[3].record()
+            torch.cuda.synchronize()
+            t_fb += e[0].elapsed_time(e[1]); t_ar += e[1].elapsed_time(e[2]); t_sgd += e[2].elapsed_time(e[3])
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, t_fb, t_ar, t_sgd, grad_err], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, t_fb, t_ar, t_sgd, grad_err = (float(v) for v in t)
         nbytes = tr.num_grad_elements * 4
-        print(json.dumps({
-            "metric": "TMRNet head training clips/sec (fwd+bwd+allreduce+SGD)", "value": world * B * args.steps / (ms / 1e3),
-            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps,
-            "ms_fwd_bwd": t_fb / args.steps, "ms_allreduce": t_ar / args.steps, "ms_sgd": t_sgd / args.steps,
-            "allreduce_bytes": nbytes,
-            "allreduce_busbw_gbs": (2 * (world - 1) / world * nbytes / (t_ar / args.steps / 1e3) / 1e9) if world > 1 else None,
-            "grad_elements": tr.num_grad_elements,
-            "allreduced_vs_union_batch_grad_rel_err": grad_err,
-            "config": {"workload": "head training step, synthetic M2CAI-shaped (C=8), L=30, seq=10", "clips_per_gpu": B,
-                       "math": "fp32 CUDA cores", "collective": "one NCCL all-reduce(SUM) of the flat head gradient"}}))
+        return {"value": world * B * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps, "ms_fwd_bwd": t_fb / args.steps,
+                "ms_allreduce": t_ar / args.steps, "ms_sgd": t_sgd / args.steps, "allreduce_bytes": nbytes,
+                "allreduce_busbw_gbs": (2 * (world - 1) / world * nbytes / (t_ar / args.steps / 1e3) / 1e9) if world > 1 else None,
+                "grad_elements": tr.num_grad_elements, "allreduced_vs_union_batch_grad_rel_err": grad_err}
+
+    f16 = measure("f16")
+    fp32 = measure("fp32")
+    if rank == 0:
+        line = {"metric": "TMRNet head training clips/sec (fwd+bwd+allreduce+SGD)", "unit": "clips/s", "n_gpus": world,
+                "steps": args.steps}
+        line.update(f16)
+        line["fp32_math"] = fp32
+        line["config"] = {"workload": "head training step, synthetic M2CAI-shaped (C=8), L=30, seq=10", "clips_per_gpu": B,
+                          "math": "headline: fp16-rounded GEMM operands on tcgen05, fp32 accumulate (TMR_MATH_F16); fp32_math: every "
+                                  "GEMM in fp32 on CUDA cores", "collective": "one NCCL all-reduce(SUM) of the flat head gradient"}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -222,7 +222,11 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
                               size_t workspace_bytes, void* stream);
 
 /* ---- a10: head training step (TRAIN:780,856-887) ----------------------------------------------
- * Forward in training mode + full backward of the head, fp32.  params/grads: 24 DEVICE pointers in
+ * Forward in training mode + full backward of the head.  math_mode TMR_MATH_FP32: every GEMM in fp32 on CUDA cores
+ * (gradients within 2e-4 of torch autograd over the fp64 graph); TMR_MATH_F16: the GEMMs of the forward and of the
+ * backward (input and weight gradients) take fp16-rounded operands on the tensor cores with fp32 accumulation
+ * (gradients within 3e-3 of each tensor's largest entry); element-wise math, reductions, the loss, saved activations,
+ * gradients and parameters stay fp32 in both modes.  params/grads: 24 DEVICE pointers in
  * reference state-dict order and layouts:
  *   lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
  *   time_conv.timeconv{1,2,3}.{weight,bias} (NULL x6 for the NL-only wiring),
@@ -236,7 +240,7 @@ size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C
 int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
                            const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
                            float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
-                           void* workspace, size_t workspace_bytes, void* stream);
+                           void* workspace, size_t workspace_bytes, int math_mode, void* stream);
 /* The same step split at the logits, for torch.autograd: what lets the reference's loop body run unchanged -
  *   model.train(); outputs = model.forward(inputs, long_feature); loss = criterion(outputs, labels);
  *   loss.backward(); optimizer.step()                                              (TRAIN:876-887)
@@ -246,10 +250,10 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
  * dlogits (B,C), overwrites the 24 grads.  logits_scratch: any (B,C) fp32 buffer. */
 int tmr_head_train_fwd(const float* const* params, const float* x, const float* long_feature, int B, int seq, int L, int F,
                        int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       size_t workspace_bytes, int math_mode, void* stream);
 int tmr_head_train_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
                        const float* dlogits, int B, int seq, int L, int F, int D, int C, float* logits_scratch,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       void* workspace, size_t workspace_bytes, int math_mode, void* stream);
 /* torch.optim.SGD update on one flat fp32 tensor (momentum, weight decay, dampening 0, no nesterov),
  * TRAIN:797-805,887:  d = g + wd*p ; buf = first_step ? d : momentum*buf + d ; p -= lr*buf. */
 int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,

@@ -55,9 +55,9 @@ SIGNATURES = {
     "tmr_head_frames_dedup_fwd": (_i, [_p] * 5 + [_i, _i64, _i64, _p, _i64, _p, _p, _i64, _p, _i, _p, _p, _i, _p, _i, _i64, _i64]
                                   + [_i] * 6 + [_p, _p, _p, _p, _p, _sz, _p]),
     "tmr_head_train_workspace_bytes": (_sz, [_i] * 6),
-    "tmr_head_train_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _p, _p, _sz, _p]),
-    "tmr_head_train_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _sz, _p]),
-    "tmr_head_train_bwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 6 + [_p, _p, _sz, _p]),
+    "tmr_head_train_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _p, _p, _sz, _i, _p]),
+    "tmr_head_train_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _sz, _i, _p]),
+    "tmr_head_train_bwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 6 + [_p, _p, _sz, _i, _p]),
     "tmr_sgd_step": (_i, [_p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, _i, _p]),
     "tmr_linear_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _i, _p]),
 }

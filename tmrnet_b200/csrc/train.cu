@@ -17,7 +17,7 @@ namespace tmr {
 namespace train {
 
 static inline size_t fb(size_t n) { return align_up(n * sizeof(float), 256); }
-static inline int64_t pad16(int64_t v) { return (v + 15) / 16 * 16; }
+static inline int64_t pad16(int64_t v) { return (v + 63) / 64 * 64; }   // 64: a whole k-step of the tensor-core GEMM
 
 // ---------------------------------------------------------------------------------------------
 // small kernels
@@ -327,10 +327,14 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 // ---------------------------------------------------------------------------------------------
 // GEMM helpers on top of simt_linear (out = a . w^T, K-major operands)
 // ---------------------------------------------------------------------------------------------
-static int gemm_nt(const float* a, int64_t lda, const float* w, int64_t ldw, const float* bias, float* out, int64_t ldo,
-                   int64_t M, int N, int K, cudaStream_t st) {
-  LinearArgs g; g.a = a; g.lda = lda; g.w = w; g.ldw = ldw; g.bias = bias; g.out = out; g.ldo = ldo; g.M = M; g.N = N; g.K = K;
-  return simt_linear(g, st);
+
+// fp16 operand scratch of the tensor-core GEMMs: the largest [rows][K] operand of the step
+static inline size_t tc_scratch_halves(size_t T, size_t Tp, size_t R, size_t Rp) {
+  size_t rows = kF;                                   // Wih (4D x F), x^T (F x Tp), dpre^T (4D x Tp) ...
+  size_t k = kF > Tp ? kF : Tp;
+  if (Rp > k) k = Rp;
+  size_t a = rows * k, b = (T > R ? T : R) * (size_t)kF;
+  return a > b ? a : b;
 }
 
 struct Ws {
@@ -357,6 +361,7 @@ size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C
   n += 2 * fb((size_t)2 * D * Bp) + fb((size_t)16 * Bp);                                              // small transposes
   n += 4 * fb(R * D) + 2 * fb((size_t)D * Rp) + fb((size_t)D * D);                                    // TimeConv backward
   n += fb(T * 4 * D) + fb((size_t)4 * D * Tp) + fb((size_t)F * Tp);                                   // BPTT
+  n += 2 * fb(tc_scratch_halves(T, Tp, R, Rp) / 2) + 2 * fb((size_t)4 * D * D / 2);                   // fp16 operands (TMR_MATH_F16)
   return n + (1 << 16);
 }
 
@@ -372,6 +377,26 @@ size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C
  * dlogits_ext (B,C): the caller's gradient w.r.t. the logits (autograd) instead of the built-in loss. */
 enum { PH_FWD = 1, PH_LOSS = 2, PH_BWD = 4 };
 
+// TMR_MATH_F16: the backward runs on gradients scaled by 2^10 (exact in fp32), so that the small entries of dpre / dLt
+// stay inside fp16's normal range when they become GEMM operands; every parameter gradient is linear in dlogits and is
+// scaled back by one launch over the 24 tensors at the end.
+constexpr float kGradScale = 1024.f;
+__global__ void scale_vec_kernel(float* p, int64_t n, float sc) { GRID_STRIDE(i, n) p[i] *= sc; }
+struct GradTable { float* p[24]; int64_t n[24]; };
+__global__ void unscale_grads_kernel(GradTable t, float sc) {
+  float* p = t.p[blockIdx.y];
+  const int64_t n = t.n[blockIdx.y];
+  if (!p) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {           // 128-bit body, scalar tail
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (int64_t i = i0; i < n / 4; i += stride) { float4 v = p4[i]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; p4[i] = v; }
+    for (int64_t i = (n / 4) * 4 + i0; i < n; i += stride) p[i] *= sc;
+  } else {
+    for (int64_t i = i0; i < n; i += stride) p[i] *= sc;
+  }
+}
+
 __global__ void pad_dlogits_kernel(const float* __restrict__ d, int B, int C, float* __restrict__ d16) {
   const int64_t n = (int64_t)B * 16;
   GRID_STRIDE(i, n) { const int64_t b = i / 16; const int c = (int)(i % 16); d16[i] = c < C ? d[b * C + c] : 0.f; }
@@ -380,8 +405,12 @@ __global__ void pad_dlogits_kernel(const float* __restrict__ d, int B, int C, fl
 static int train_impl(int phase, const float* const* params, float* const* grads, const float* x, const float* long_feature,
                       const int64_t* labels, const float* class_weight, const float* dlogits_ext, int B, int seq, int L,
                       int F, int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
   TMR_CHECK_ARG(D == kD && F == kF, "train: D/F unsupported");
+  TMR_CHECK_ARG(math_mode == TMR_MATH_FP32 || math_mode == TMR_MATH_F16, "train: unknown math_mode %d", math_mode);
+  if (math_mode == TMR_MATH_F16 && !umma_available())
+    return set_error(TMR_ERR_UNSUPPORTED, "train: TMR_MATH_F16 needs the tcgen05 kernels (sm_100a device + build)");
+  const bool tcm = math_mode == TMR_MATH_F16;
   TMR_CHECK_ARG(B >= 1 && seq >= 1 && L >= 1 && C >= 1 && C <= 16, "train: bad sizes (C <= 16)");
   TMR_CHECK_ARG(params && x && long_feature && logits && workspace, "train: null pointer");
   TMR_CHECK_ARG(!(phase & PH_LOSS) || (labels && loss), "train: loss phase needs labels and loss");
@@ -425,6 +454,27 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   }
   TAKE(dpre, (size_t)T * 4 * kD); TAKE(dc, (size_t)B * kD); TAKE(dh, (size_t)B * kD);
   TAKE(dpT, (size_t)4 * kD * Tp); TAKE(opT, (size_t)kF * Tp);
+  // fp16 operand scratch of the tensor-core GEMMs (carved in either mode: the layout is phase- and mode-independent)
+  const size_t tc_halves = tc_scratch_halves((size_t)T, (size_t)Tp, (size_t)R, (size_t)Rp);
+  TAKE(a16f, tc_halves / 2); TAKE(w16f, tc_halves / 2); TAKE(whh16f, (size_t)4 * kD * kD / 2); TAKE(whhT16f, (size_t)4 * kD * kD / 2);
+  half_t* a16 = reinterpret_cast<half_t*>(a16f); half_t* w16 = reinterpret_cast<half_t*>(w16f);
+  half_t* Whh16 = reinterpret_cast<half_t*>(whh16f); half_t* WhhT16 = reinterpret_cast<half_t*>(whhT16f);
+  // out[M,N] (ldo) = a[M,K] . w[N,K]^T (+ bias) (+ residual).  TMR_MATH_F16: both operands are rounded to fp16 (one
+  // conversion launch each; w16_pre = an operand converted earlier in this call) and multiplied on the tensor cores with
+  // fp32 accumulation; shapes the tcgen05 engine does not take (K not a multiple of 64: the 16-wide padded class
+  // dimension) stay on the fp32 CUDA-core GEMM.
+  auto gemm_nt = [&](const float* a, int64_t lda, const float* wgt, int64_t ldw, const float* bias, float* out, int64_t ldo,
+                     int64_t M, int N, int K, cudaStream_t s2, const float* residual = nullptr, int64_t ldr = 0,
+                     const half_t* w16_pre = nullptr) -> int {
+    LinearArgs g; g.a = a; g.lda = lda; g.w = wgt; g.ldw = ldw; g.bias = bias; g.out = out; g.ldo = ldo; g.M = M; g.N = N; g.K = K;
+    g.residual = residual; g.ldr = ldr;
+    if (!tcm || K % 64 != 0 || N % 4 != 0 || ldo % 4 != 0) return simt_linear(g, s2);
+    TMR_CHECK_ARG((size_t)M * K <= tc_halves && (size_t)N * K <= tc_halves, "train: fp16 scratch too small");
+    TMR_TRY(launch_half_concat(a, lda, nullptr, 0, K, K, M, a16, s2));
+    if (!w16_pre) TMR_TRY(launch_half_concat(wgt, ldw, nullptr, 0, K, K, N, w16, s2));
+    g.a16 = a16; g.lda = K; g.w16 = w16_pre ? w16_pre : w16; g.ldw = K;
+    return umma_linear(g, s2);
+  };
   const float* St = hst + (size_t)(S - 1) * B * kD;
   const float* Lt = has_tc ? Ltb : long_feature;
   float* convs[3] = {c3, c5, c7};
@@ -434,8 +484,10 @@ static int train_impl(int phase, const float* const* params, float* const* grads
     permute_bsf_kernel<<<nblk(T * kF), 256, 0, st>>>(x, B, S, kF, x_tm);
     add_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(params[2], params[3], bsum, 4 * kD);
     TMR_TRY(gemm_nt(x_tm, kF, Wih, kF, bsum, xp, 4 * kD, T, 4 * kD, kF, st));
+    if (tcm && S > 1) TMR_TRY(launch_half_concat(Whh, kD, nullptr, 0, kD, kD, 4 * kD, Whh16, st));
     for (int t = 0; t < S; ++t) {
-      if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st));
+      if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st, nullptr, 0,
+                                 tcm ? Whh16 : nullptr));
       lstm_cell_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(xp + (size_t)t * B * 4 * kD, t > 0 ? hh : nullptr,
                                                                  t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
                                                                  gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
@@ -450,9 +502,8 @@ static int train_impl(int phase, const float* const* params, float* const* grads
           // wtap[o][c] = Wk[o][c][j]  (strided gather = transpose_pad of a (D*D) x K matrix column j)
           transpose_pad_kernel<<<dim3(1, (unsigned)((kD * kD + 31) / 32)), dim3(32, 8), 0, st>>>(Wk + j, (int64_t)kD * kD, 1, K, wtap, (int64_t)kD * kD);
           shift_rows_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, L, j - h, R * kD, shiftb);
-          LinearArgs g; g.a = shiftb; g.lda = kD; g.w = wtap; g.ldw = kD; g.bias = j == 0 ? params[5 + 2 * ci] : nullptr;
-          g.residual = j == 0 ? nullptr : convs[ci]; g.ldr = kD; g.out = convs[ci]; g.ldo = kD; g.M = R; g.N = kD; g.K = kD;
-          TMR_TRY(simt_linear(g, st));
+          TMR_TRY(gemm_nt(shiftb, kD, wtap, kD, j == 0 ? params[5 + 2 * ci] : nullptr, convs[ci], kD, R, kD, kD, st,
+                          j == 0 ? nullptr : convs[ci], kD));
         }
       }
       timeconv_max_train_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, c3, c5, c7, L, R * kD, Ltb, branch);
@@ -481,6 +532,7 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   }
   if (!do_bwd) return TMR_OK;
   if (!do_loss) pad_dlogits_kernel<<<nblk((int64_t)B * 16), 256, 0, st>>>(dlogits_ext, B, C, dlog16);
+  if (tcm) scale_vec_kernel<<<nblk((int64_t)B * 16), 256, 0, st>>>(dlog16, (int64_t)B * 16, kGradScale);
 
   // weight transposes the backward GEMMs read (recomputed here: the weights cannot have changed since the forward,
   // autograd's version counters check that)
@@ -555,11 +607,13 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   // ---------------- backward: LSTM (BPTT) ----------------
   zero_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dc, (int64_t)B * kD);
   copy_vec_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dSt, dh, (int64_t)B * kD);
+  if (tcm && S > 1) TMR_TRY(launch_half_concat(WhhT, 4 * kD, nullptr, 0, 4 * kD, 4 * kD, kD, WhhT16, st));
   for (int t = S - 1; t >= 0; --t) {
     lstm_cell_bwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(dh, dc, gates + (size_t)t * B * 4 * kD, cst + (size_t)t * B * kD,
                                                                t > 0 ? cst + (size_t)(t - 1) * B * kD : nullptr,
                                                                dpre + (size_t)t * B * 4 * kD, B);
-    if (t > 0) TMR_TRY(gemm_nt(dpre + (size_t)t * B * 4 * kD, 4 * kD, WhhT, 4 * kD, nullptr, dh, kD, B, kD, 4 * kD, st));   // dh_{t-1} = dpre_t Whh
+    if (t > 0) TMR_TRY(gemm_nt(dpre + (size_t)t * B * 4 * kD, 4 * kD, WhhT, 4 * kD, nullptr, dh, kD, B, kD, 4 * kD, st, nullptr, 0,
+                               tcm ? WhhT16 : nullptr));   // dh_{t-1} = dpre_t Whh
   }
   TMR_TRY(transpose_pad(dpre, T, 4 * kD, 4 * kD, dpT, Tp, st));                              // (4D, Tp)
   TMR_TRY(transpose_pad(x_tm, T, kF, kF, opT, Tp, st));                                      // (F, Tp)
@@ -573,6 +627,15 @@ static int train_impl(int phase, const float* const* params, float* const* grads
     TMR_TRY(gemm_nt(dpT, T1p, opT, T1p, nullptr, grads[1], kD, 4 * kD, kD, (int)T1p, st));
   } else {
     zero_kernel<<<nblk((int64_t)4 * kD * kD), 256, 0, st>>>(grads[1], (int64_t)4 * kD * kD);
+  }
+  if (tcm) {
+    GradTable gt{};
+    const int64_t sizes[24] = {(int64_t)4 * kD * kF, (int64_t)4 * kD * kD, 4 * kD, 4 * kD,
+                               (int64_t)kD * kD * 3, kD, (int64_t)kD * kD * 5, kD, (int64_t)kD * kD * 7, kD,
+                               (int64_t)kD * kD, kD, (int64_t)kD * kD, kD, (int64_t)kD * kD, kD, (int64_t)kD * kD, kD, kD, kD,
+                               (int64_t)kD * 2 * kD, kD, (int64_t)C * kD, C};
+    for (int i = 0; i < 24; ++i) { gt.p[i] = (has_tc || i < 4 || i >= 10) ? grads[i] : nullptr; gt.n[i] = sizes[i]; }
+    unscale_grads_kernel<<<dim3(296, 24), 256, 0, st>>>(gt, 1.f / kGradScale);
   }
   TMR_LAUNCH_CHECK("train backward");
 #undef TAKE
@@ -589,9 +652,9 @@ extern "C" {
 int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
                            const int64_t* labels, const float* class_weight, int B, int seq, int L, int F, int D, int C,
                            float p_nl, float p_fc, uint64_t seed, float* logits, float* loss, int64_t* pred,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
   return train_impl(PH_FWD | PH_LOSS | PH_BWD, params, grads, x, long_feature, labels, class_weight, nullptr, B, seq, L, F, D, C,
-                    p_nl, p_fc, seed, logits, loss, pred, workspace, workspace_bytes, stream);
+                    p_nl, p_fc, seed, logits, loss, pred, workspace, workspace_bytes, math_mode, stream);
 }
 
 /* The same step split at the logits, for torch.autograd (tmrnet_b200.modules: model.train(); out = model(x, lf);
@@ -600,16 +663,16 @@ int tmr_head_train_fwd_bwd(const float* const* params, float* const* grads, cons
  * in between), the same params / x / long_feature and dlogits (B,C), overwrites grads. */
 int tmr_head_train_fwd(const float* const* params, const float* x, const float* long_feature, int B, int seq, int L, int F,
                        int D, int C, float p_nl, float p_fc, uint64_t seed, float* logits, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, int math_mode, void* stream) {
   return train_impl(PH_FWD, params, nullptr, x, long_feature, nullptr, nullptr, nullptr, B, seq, L, F, D, C, p_nl, p_fc, seed,
-                    logits, nullptr, nullptr, workspace, workspace_bytes, stream);
+                    logits, nullptr, nullptr, workspace, workspace_bytes, math_mode, stream);
 }
 int tmr_head_train_bwd(const float* const* params, float* const* grads, const float* x, const float* long_feature,
                        const float* dlogits, int B, int seq, int L, int F, int D, int C, float* logits_scratch,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       void* workspace, size_t workspace_bytes, int math_mode, void* stream) {
   TMR_CHECK_ARG(dlogits, "train_bwd: dlogits is null");
   return train_impl(PH_BWD, params, grads, x, long_feature, nullptr, nullptr, dlogits, B, seq, L, F, D, C, 0.f, 0.f, 0,
-                    logits_scratch, nullptr, nullptr, workspace, workspace_bytes, stream);
+                    logits_scratch, nullptr, nullptr, workspace, workspace_bytes, math_mode, stream);
 }
 
 /* torch.optim.SGD step on one flat tensor (momentum mu, weight decay wd, dampening 0): see sgd_kernel. */

@@ -16,7 +16,17 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .ops import D, F, _dev, _ptr, _stream, _ws, check
+from .ops import D, F, TMR_MATH_F16, TMR_MATH_FP32, _dev, _ptr, _stream, _ws, check
+
+def _train_mode(mode) -> int:
+    """Training math mode: 'fp32' (default: exact-parity CUDA-core GEMMs, what the reference's fp32 training does) or
+    'f16' (fp16-rounded GEMM operands on the tensor cores, fp32 accumulation - see include/tmr_b200.h)."""
+    if mode is None or mode in ("fp32", TMR_MATH_FP32):
+        return TMR_MATH_FP32
+    if mode in ("f16", "fp16", TMR_MATH_F16):
+        return TMR_MATH_F16
+    raise ValueError(f"unknown training math mode {mode!r} (use 'fp32' or 'f16')")
+
 
 PARAM_ORDER = [
     "lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
@@ -50,7 +60,7 @@ class HeadTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, long_feature, meta, *params):
-        seq, num_class, p_nl, p_fc, seed = meta
+        seq, num_class, p_nl, p_fc, seed, mode = meta
         dev = x.device
         B, L = x.shape[0], long_feature.shape[1]
         lib = _lib.load()
@@ -59,7 +69,8 @@ class HeadTrainFunction(torch.autograd.Function):
         pp = (C.c_void_p * 24)(*[p.data_ptr() if p is not None else 0 for p in params])
         with torch.cuda.device(dev):
             check(lib.tmr_head_train_fwd(pp, _ptr(x), _ptr(long_feature), B, seq, L, F, D, num_class, float(p_nl), float(p_fc),
-                                         int(seed), _ptr(logits), _ptr(ws), ws.numel(), _stream()))
+                                         int(seed), _ptr(logits), _ptr(ws), ws.numel(), mode, _stream()))
+        ctx.mode = mode
         ctx.save_for_backward(x, long_feature, *[p for p in params if p is not None])
         ctx.present = [p is not None for p in params]
         ctx.shapes = [tuple(p.shape) if p is not None else None for p in params]
@@ -82,7 +93,7 @@ class HeadTrainFunction(torch.autograd.Function):
         scratch = torch.empty((B, num_class), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib.tmr_head_train_bwd(pp, gp, _ptr(x), _ptr(long_feature), _ptr(dlogits), B, seq, L, F, D, num_class,
-                                         _ptr(scratch), _ptr(ctx.ws), ctx.ws.numel(), _stream()))
+                                         _ptr(scratch), _ptr(ctx.ws), ctx.ws.numel(), ctx.mode, _stream()))
         ctx.ws = None
         return (None, None, None) + tuple(grads.views)
 
@@ -105,7 +116,7 @@ def head_train_forward(model, x, long_feature, dropout=True):
     seed = (torch.initial_seed() * 1000003 + model._train_calls) & 0x7FFFFFFFFFFFFFFF
     p_nl = model.nl_block.dropout.p if dropout else 0.0
     p_fc = model.dropout.p if dropout else 0.0
-    meta = (model.sequence_length, model.num_class, p_nl, p_fc, seed)
+    meta = (model.sequence_length, model.num_class, p_nl, p_fc, seed, _train_mode(getattr(model, "train_math_mode", None)))
     return HeadTrainFunction.apply(x, long_feature, meta, *params)
 
 
@@ -126,8 +137,9 @@ class HeadTrainer:
     """model: tmrnet_b200.resnet_lstm on a CUDA device.  One `step()` = TRAIN:856-887 for the head."""
 
     def __init__(self, model, lr=5e-4, momentum=0.9, weight_decay=5e-4, lstm_lr_scale=0.1, class_weight=None,
-                 p_nl=0.2, p_fc=0.5, seed=0, process_group=None):
+                 p_nl=0.2, p_fc=0.5, seed=0, process_group=None, math_mode=None):
         self.model = model
+        self.math_mode = _train_mode(math_mode)
         self.params = _param_list(model)
         self.has_tc = self.params[4] is not None
         dev = self.params[0].device
@@ -189,7 +201,7 @@ class HeadTrainer:
             check(lib.tmr_head_train_fwd_bwd(self._pp, self._gp, _ptr(x), _ptr(long_feature), _ptr(labels),
                                              _ptr(self.class_weight), B, seq, L, F, D, Cn, p_nl, p_fc,
                                              self.seed * 1000003 + self.steps, _ptr(logits), _ptr(loss), _ptr(pred),
-                                             _ptr(self._ws), self._ws.numel(), _stream()))
+                                             _ptr(self._ws), self._ws.numel(), self.math_mode, _stream()))
         return loss, logits, pred
 
     def allreduce_grads(self):
