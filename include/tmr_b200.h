@@ -258,6 +258,11 @@ int tmr_head_train_bwd(const float* const* params, float* const* grads, const fl
  * TRAIN:797-805,887:  d = g + wd*p ; buf = first_step ? d : momentum*buf + d ; p -= lr*buf. */
 int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                  float weight_decay, int first_step, void* stream);
+/* The same update over `count` (<= 24) tensors in ONE launch, each with its own learning rate (the reference's
+ * parameter groups, TRAIN:797-805).  params / grads / momentum_bufs: HOST arrays of device pointers (NULL = skip);
+ * sizes, lrs: host arrays.  Element-wise identical to `count` tmr_sgd_step calls. */
+int tmr_sgd_step_multi(float* const* params, const float* const* grads, float* const* momentum_bufs, const int64_t* sizes,
+                       const float* lrs, int count, float momentum, float weight_decay, int first_step, void* stream);
 
 /* ---- generic linear used by the stages above (exposed for tests) -------------------------------
  * out[M,N] = a[M,K] . w[N,K]^T + bias[N] (bias nullable), row-major, leading dims = K / K / N.

@@ -59,6 +59,7 @@ SIGNATURES = {
     "tmr_head_train_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [C.c_float, C.c_float, C.c_uint64, _p, _p, _sz, _i, _p]),
     "tmr_head_train_bwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 6 + [_p, _p, _sz, _i, _p]),
     "tmr_sgd_step": (_i, [_p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, _i, _p]),
+    "tmr_sgd_step_multi": (_i, [_p, _p, _p, _p, _p, _i, C.c_float, C.c_float, _i, _p]),
     "tmr_linear_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _i, _p]),
 }
 

@@ -159,6 +159,70 @@ __global__ void scatter_tap_kernel(const float* __restrict__ tmp, int K, int j, 
 }
 // direct conv forward for training: out[(b,k)][o] = bias[o] + sum_j sum_c w[o][c][j] x[(b,k+j-h)][c] is done as
 // K GEMMs on shifted copies (see conv_forward()).
+//
+// TMR_MATH_F16 batches the taps of a convolution into ONE GEMM each way (15 + 15 tap GEMMs with their conversions,
+// shifts and scatters cost ~1.3 ms of launch-bound time per step): the seven shifted copies of the window rows sit side
+// by side in xcat[r][(d+3)*512 + c] = x[(b,k+d)][c] (0 outside the window), d = -3..3, as fp16; conv_K reads the 512*K
+// columns of its taps (K-dimension of the GEMM) against wcat_K[o][j*512 + c] = w_K[o][c][j]; the weight gradient is
+// dcat_K[o][j*512 + c] = sum_r dconv_K[r][o] xcat[r][(j-h+3)*512 + c], permuted back to the (o, c, j) layout.
+constexpr int kTaps = 7;
+__global__ void build_xcat16_kernel(const float* __restrict__ x, int L, int64_t R, half_t* __restrict__ xcat) {
+  const int64_t n4 = R * kTaps * (kD / 4);
+  GRID_STRIDE(i, n4) {
+    const int c4 = (int)(i % (kD / 4));
+    const int dj = (int)((i / (kD / 4)) % kTaps);
+    const int64_t row = i / ((int64_t)kTaps * (kD / 4));
+    const int kk = (int)(row % L) + dj - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk >= 0 && kk < L) v = __ldg(reinterpret_cast<const float4*>(x + (row + dj - 3) * kD) + c4);
+    reinterpret_cast<uint2*>(xcat + (row * kTaps + dj) * kD)[c4] = pack_h4(v);
+  }
+}
+// wcat[o][j*512 + c] = fp16(w[o][c][j]),  w: (512, 512, K)
+__global__ void permute_wcat16_kernel(const float* __restrict__ w, int K, half_t* __restrict__ wcat) {
+  const int64_t n = (int64_t)kD * kD * K;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % kD); const int j = (int)((i / kD) % K); const int64_t o = i / ((int64_t)kD * K);
+    const float v = w[(o * kD + c) * K + j];
+    wcat[i] = (half_t)(pack_h2(v, 0.f) & 0xffffu);
+  }
+}
+// dW[(o*512 + c)*K + j] = dcat[o][j*512 + c]
+__global__ void permute_dwcat_kernel(const float* __restrict__ dcat, int K, float* __restrict__ dW) {
+  const int64_t n = (int64_t)kD * kD * K;
+  GRID_STRIDE(i, n) {
+    const int j = (int)(i % K); const int c = (int)((i / K) % kD); const int64_t o = i / ((int64_t)kD * K);
+    dW[i] = dcat[(o * K + j) * kD + c];
+  }
+}
+// dst[c][r] = fp16(src[r][c]) for r < R, 0 for R <= r < Rpad.  SRC = float or half_t
+template <class SRC>
+__global__ void transpose_pad16_kernel(const SRC* __restrict__ src, int64_t R, int Ccols, int64_t ld, half_t* __restrict__ dst, int64_t Rpad) {
+  __shared__ half_t t[32][34];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i; const int c = c0 + threadIdx.x;
+    half_t v = 0;
+    if (r < R && c < Ccols) {
+      if constexpr (sizeof(SRC) == 4) v = (half_t)(pack_h2((float)src[r * ld + c], 0.f) & 0xffffu);
+      else v = (half_t)src[r * ld + c];
+    }
+    t[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i; const int64_t r = r0 + threadIdx.x;
+    if (c < Ccols && r < Rpad) dst[(int64_t)c * Rpad + r] = t[threadIdx.x][i];
+  }
+}
+template <class SRC>
+static int transpose_pad16(const SRC* src, int64_t R, int Ccols, int64_t ld, half_t* dst, int64_t Rpad, cudaStream_t st) {
+  dim3 grid((Ccols + 31) / 32, (unsigned)((Rpad + 31) / 32));
+  transpose_pad16_kernel<SRC><<<grid, dim3(32, 8), 0, st>>>(src, R, Ccols, ld, dst, Rpad);
+  TMR_LAUNCH_CHECK("transpose_pad16_kernel");
+  return TMR_OK;
+}
 
 // attention, training forward: warp per clip; saves the softmax p (B,L)
 __global__ void attention_train_fwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
@@ -324,6 +388,23 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
   }
 }
 
+// the same update over up to 24 tensors in ONE launch (blockIdx.y = tensor; each with its own learning rate: the
+// reference's parameter groups)
+struct SgdTable { float* p[24]; const float* g[24]; float* buf[24]; int64_t n[24]; float lr[24]; };
+__global__ void sgd_multi_kernel(SgdTable t, float mu, float wd, int first) {
+  const int k = blockIdx.y;
+  float* __restrict__ p = t.p[k]; const float* __restrict__ g = t.g[k]; float* __restrict__ buf = t.buf[k];
+  const int64_t n = t.n[k];
+  const float lr = t.lr[k];
+  if (!p) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = g[i] + wd * p[i];
+    const float bv = first ? d : mu * buf[i] + d;
+    buf[i] = bv;
+    p[i] -= lr * bv;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // GEMM helpers on top of simt_linear (out = a . w^T, K-major operands)
 // ---------------------------------------------------------------------------------------------
@@ -362,6 +443,7 @@ size_t tmr_head_train_workspace_bytes(int B, int seq, int L, int D, int F, int C
   n += 4 * fb(R * D) + 2 * fb((size_t)D * Rp) + fb((size_t)D * D);                                    // TimeConv backward
   n += fb(T * 4 * D) + fb((size_t)4 * D * Tp) + fb((size_t)F * Tp);                                   // BPTT
   n += 2 * fb(tc_scratch_halves(T, Tp, R, Rp) / 2) + 2 * fb((size_t)4 * D * D / 2);                   // fp16 operands (TMR_MATH_F16)
+  n += fb(R * 7 * D / 2) + fb((size_t)7 * D * Rp / 2) + fb((size_t)15 * D * D / 2) + fb((size_t)D * Rp / 2) + fb((size_t)7 * D * D);   // batched taps
   return n + (1 << 16);
 }
 
@@ -457,6 +539,13 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   // fp16 operand scratch of the tensor-core GEMMs (carved in either mode: the layout is phase- and mode-independent)
   const size_t tc_halves = tc_scratch_halves((size_t)T, (size_t)Tp, (size_t)R, (size_t)Rp);
   TAKE(a16f, tc_halves / 2); TAKE(w16f, tc_halves / 2); TAKE(whh16f, (size_t)4 * kD * kD / 2); TAKE(whhT16f, (size_t)4 * kD * kD / 2);
+  half_t *xcat16 = nullptr, *xcatT16 = nullptr, *wcat16 = nullptr, *dcT16 = nullptr; float* dwcat = nullptr;
+  if (has_tc) {     // batched-tap TimeConv of TMR_MATH_F16 (carved in either mode)
+    xcat16 = reinterpret_cast<half_t*>(w.f((size_t)R * kTaps * kD / 2)); xcatT16 = reinterpret_cast<half_t*>(w.f((size_t)kTaps * kD * Rp / 2));
+    wcat16 = reinterpret_cast<half_t*>(w.f((size_t)15 * kD * kD / 2)); dcT16 = reinterpret_cast<half_t*>(w.f((size_t)kD * Rp / 2));
+    dwcat = w.f((size_t)kTaps * kD * kD);
+    TMR_CHECK_ARG(xcat16 && xcatT16 && wcat16 && dcT16 && dwcat, "train: workspace too small (batched taps)");
+  }
   half_t* a16 = reinterpret_cast<half_t*>(a16f); half_t* w16 = reinterpret_cast<half_t*>(w16f);
   half_t* Whh16 = reinterpret_cast<half_t*>(whh16f); half_t* WhhT16 = reinterpret_cast<half_t*>(whhT16f);
   // out[M,N] (ldo) = a[M,K] . w[N,K]^T (+ bias) (+ residual).  TMR_MATH_F16: both operands are rounded to fp16 (one
@@ -494,7 +583,19 @@ static int train_impl(int phase, const float* const* params, float* const* grads
                                                                  hst + (size_t)t * B * kD, B);
     }
     // ---------------- forward: TimeConv ----------------
-    if (has_tc) {
+    if (has_tc && tcm) {
+      build_xcat16_kernel<<<nblk(R * kTaps * (kD / 4)), 256, 0, st>>>(long_feature, L, R, xcat16);
+      size_t woff = 0;
+      for (int ci = 0; ci < 3; ++ci) {         // conv_K = bias + xcat[:, taps of K] . wcat_K^T: one GEMM per convolution
+        const int K = 3 + 2 * ci, h = K / 2;
+        permute_wcat16_kernel<<<nblk((int64_t)kD * kD * K), 256, 0, st>>>(params[4 + 2 * ci], K, wcat16 + woff);
+        LinearArgs g; g.a16 = xcat16 + (size_t)(3 - h) * kD; g.lda = kTaps * kD; g.w16 = wcat16 + woff; g.ldw = (int64_t)K * kD;
+        g.bias = params[5 + 2 * ci]; g.out = convs[ci]; g.ldo = kD; g.M = R; g.N = kD; g.K = K * kD;
+        TMR_TRY(umma_linear(g, st));
+        woff += (size_t)kD * kD * K;
+      }
+      timeconv_max_train_kernel<<<nblk(R * kD), 256, 0, st>>>(long_feature, c3, c5, c7, L, R * kD, Ltb, branch);
+    } else if (has_tc) {
       for (int ci = 0; ci < 3; ++ci) {         // conv_K = bias + sum_j shift_j(x) . W_K[:,:,j]^T  (tap matrices gathered from (D,D,K))
         const int K = 3 + 2 * ci, h = K / 2;
         const float* Wk = params[4 + 2 * ci];
@@ -589,7 +690,22 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   TMR_TRY(gemm_nt(dq, kD, W1T, kD, nullptr, tmpBD, kD, B, kD, kD, st));
   axpy_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(tmpBD, dSt, (int64_t)B * kD);
   // ---------------- backward: TimeConv (weights only; the bank has no gradient) ----------------
-  if (has_tc) {
+  if (has_tc && tcm) {
+    conv_route_kernel<<<nblk(R * kD), 256, 0, st>>>(dLt, branch, R * kD, d3, d5, d7);
+    float* dcs[3] = {d3, d5, d7};
+    // xcat may come from a forward in the other math mode (or not at all): rebuild it, it is one launch
+    build_xcat16_kernel<<<nblk(R * kTaps * (kD / 4)), 256, 0, st>>>(long_feature, L, R, xcat16);
+    TMR_TRY(transpose_pad16<half_t>(xcat16, R, kTaps * kD, kTaps * kD, xcatT16, Rp, st));          // (7*512, Rp)
+    for (int ci = 0; ci < 3; ++ci) {
+      const int K = 3 + 2 * ci, h = K / 2;
+      TMR_TRY(colsum(dcs[ci], nullptr, R, kD, kD, grads[5 + 2 * ci], 0, st));
+      TMR_TRY(transpose_pad16<float>(dcs[ci], R, kD, kD, dcT16, Rp, st));                          // (D_out, Rp)
+      LinearArgs g; g.a16 = dcT16; g.lda = Rp; g.w16 = xcatT16 + (size_t)(3 - h) * kD * Rp; g.ldw = Rp;
+      g.out = dwcat; g.ldo = (int64_t)K * kD; g.M = kD; g.N = K * kD; g.K = (int)Rp;
+      TMR_TRY(umma_linear(g, st));                                                                  // dcat[o][j*512 + c]
+      permute_dwcat_kernel<<<nblk((int64_t)kD * kD * K), 256, 0, st>>>(dwcat, K, grads[4 + 2 * ci]);
+    }
+  } else if (has_tc) {
     conv_route_kernel<<<nblk(R * kD), 256, 0, st>>>(dLt, branch, R * kD, d3, d5, d7);
     float* dcs[3] = {d3, d5, d7};
     for (int ci = 0; ci < 3; ++ci) {
@@ -682,6 +798,22 @@ int tmr_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
   if (n == 0) return TMR_OK;
   sgd_kernel<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, mu, wd, first_step);
   TMR_LAUNCH_CHECK("sgd_kernel");
+  return TMR_OK;
+}
+
+/* The same update over `count` (<= 24) tensors in one launch: params / grads / momentum_bufs are HOST arrays of device
+ * pointers (NULL entries are skipped), sizes and lrs host arrays; element-wise identical to `count` tmr_sgd_step calls. */
+int tmr_sgd_step_multi(float* const* params, const float* const* grads, float* const* momentum_bufs, const int64_t* sizes,
+                       const float* lrs, int count, float mu, float wd, int first_step, void* stream) {
+  TMR_CHECK_ARG(params && grads && momentum_bufs && sizes && lrs && count >= 0 && count <= 24, "sgd_multi: bad arguments");
+  if (count == 0) return TMR_OK;
+  SgdTable t{};
+  for (int i = 0; i < count; ++i) {
+    TMR_CHECK_ARG(!params[i] || (grads[i] && momentum_bufs[i] && sizes[i] >= 0), "sgd_multi: tensor %d incomplete", i);
+    t.p[i] = params[i]; t.g[i] = grads[i]; t.buf[i] = momentum_bufs[i]; t.n[i] = params[i] ? sizes[i] : 0; t.lr[i] = lrs[i];
+  }
+  sgd_multi_kernel<<<dim3(296, (unsigned)count), 256, 0, (cudaStream_t)stream>>>(t, mu, wd, first_step);
+  TMR_LAUNCH_CHECK("sgd_multi_kernel");
   return TMR_OK;
 }
 

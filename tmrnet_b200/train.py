@@ -213,13 +213,15 @@ class HeadTrainer:
     def sgd_update(self):
         lib = _lib.load()
         first = 1 if self.steps == 0 else 0
-        with torch.cuda.device(self.device):
-            for i, p in enumerate(self.params):
-                if p is None:
-                    continue
-                lr = self.lstm_lr if PARAM_ORDER[i].startswith("lstm.") else self.lr
-                check(lib.tmr_sgd_step(_ptr(p), _ptr(self.grads.views[i]), _ptr(self.momentum_buf.views[i]), p.numel(),
-                                       lr, self.momentum, self.weight_decay, first, _stream()))
+        n = len(self.params)
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        pp = (C.c_void_p * n)(*[ptr(p) for p in self.params])
+        gp = (C.c_void_p * n)(*[ptr(g) for g in self.grads.views])
+        bp = (C.c_void_p * n)(*[ptr(b) for b in self.momentum_buf.views])
+        sizes = (C.c_int64 * n)(*[p.numel() if p is not None else 0 for p in self.params])
+        lrs = (C.c_float * n)(*[self.lstm_lr if PARAM_ORDER[i].startswith("lstm.") else self.lr for i in range(n)])
+        with torch.cuda.device(self.device):       # all 24 tensors in one launch, each with its group's learning rate
+            check(lib.tmr_sgd_step_multi(pp, gp, bp, sizes, lrs, n, self.momentum, self.weight_decay, first, _stream()))
         self.steps += 1
         self.model.invalidate_packs()          # weights changed under the inference caches
 
