@@ -494,6 +494,11 @@ def run_ours(args):
                 "ms_lstm_total": ls["ms_lstm_total"], "share_of_step": ls["ms_recurrence"] * (total_clips / world) / ls["clips"] / (ms / args.steps),
                 "how": "CUDA events on one batch of the full job: (10-step LSTM - 2-step LSTM) x 9/8 - both legs run the same "
                        "projection with step 0 fused and the same persistent kernel over 9 / 1 steps, so fixed costs cancel",
+                "previous_round": {"kernel": "umma_lstm_ws_kernel x 9 launches (round 1)", "frac_of_the_same_tensor_peak": 0.43,
+                                   "ms_for_the_same_work": 2.36,
+                                   "note": "round 1 reported that kernel against HBM (0.73 of peak on 14 336 B per clip and step, "
+                                           "125 KB per clip over the recurrence); the persistent kernel no longer moves those bytes, so "
+                                           "it is reported on the roofline SURVEY.md 8(d) assigns the LSTM: tensor"},
                 "hbm": {"dram_bytes_per_clip": dram_per_clip,
                         "note": "measured DRAM traffic of the whole recurrence per clip (c never leaves the SM, h is exchanged "
                                 "through L2, projected rows of consecutive steps hit L2); the per-step kernels of round 1 moved "
