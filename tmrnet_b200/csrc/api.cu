@@ -131,7 +131,7 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
     g.row2clip = row2clip; g.c0 = ws.c; g.h0_16 = reinterpret_cast<half_t*>(ws.h0);
   }
   TMR_TRY(do_linear(g, mode, st));
-  if (fuse0)     // clips sharing a start with another clip lost the table slot: their step 0 runs here
+  if (fuse0 && starts)   // clips sharing a start with another clip lost the table slot: their step 0 runs here
     TMR_TRY(launch_lstm_cell0_fix(ws.xp, starts, B, n_rows_x, frame0, g.row2clip, ws.c, reinterpret_cast<half_t*>(ws.h0), st));
   const float* xp = ws.xp - frame0 * 4 * kD;   // rows addressed by GLOBAL frame id (starts[m] + t)
   // (Running the recurrence in L2-sized sub-batches - all steps of one before the next, so that the projected

@@ -21,16 +21,18 @@
 //
 // Layout of the work (round 2; the first version exchanged accumulator rows through shared memory between two
 // CTA-wide barriers per 8 channels and re-fetched the row tile for each of the 32 channel tiles: tensor pipe 49 %):
-//  * the time shifts are WARP-LOCAL.  A TMEM lane quarter (32 lanes = the rows one epilogue warp may read) holds 32
-//    CONSECUTIVE bank rows, of which the inner 26 are emitted; the next quarter starts 26 rows further, i.e. the four
-//    32-row TMA boxes of a CTA's A tile overlap by 6 rows.  P_{K,t}[rho] = Q_{K,t}[rho - t] is then one
-//    __shfl_up/down of the accumulator value read from TMEM - no shared memory, no barrier, and each epilogue
-//    warp runs on its own.  Cost: 26 of 32 MMA rows are useful (the exchange version used 122 of 128).
+//  * the time shifts are (almost) WARP-LOCAL.  A CTA's 128 MMA rows are 128 consecutive bank rows (122 emitted, a 3-row
+//    halo at either end of the tile); a TMEM lane quarter (32 lanes = the rows one epilogue warp may read) holds 32 of
+//    them, so P_{K,t}[rho] = Q_{K,t}[rho - t] is one __shfl_up/down of the accumulator value read from TMEM for all but
+//    the |t| lanes at a quarter's edge, which take it from the neighbouring quarter's warp through a 5 KB shared-memory
+//    halo (10 values per channel and side) under one 128-thread named barrier per convolution - no accumulator-sized
+//    exchange buffer, no CTA-wide barrier.  (A first warp-local version overlapped the four 32-row groups by 6 rows
+//    instead: no halo at all, but only 104 of 128 MMA rows useful, and the MMAs alone are 75 % of this kernel.)
 //  * the fp16 rows of a CTA (128 x 512 = 128 KB) stay RESIDENT in shared memory for all 32 channel tiles of their
 //    row block; only the stacked tap weights (15 KB per CTA and 64-channel k-step) stream.  L2 -> SM traffic per
 //    launch halves, and the six-stage weight ring is all the staging the kernel needs.
-//  * the 7 variants leave through shared memory and ONE TMA store per warp and tile (a [26 rows][7 variants]
-//    [8 channels] fp16 box of PB through a 2.9 KB staging tile; what is left of shared memory beside the resident rows
+//  * the 7 variants leave through shared memory and ONE TMA store per warp and tile (a [32 or 29 rows][7 variants]
+//    [8 channels] fp16 box of PB through a 3.5 KB staging tile; what is left of shared memory beside the resident rows
 //    goes to the weight ring - with three weight stages the MMAs starved, tensor pipe 48 %): a row-per-thread epilogue writing 32-byte pieces with st.global costs one L1 wavefront per lane and
 //    instruction, and with the exact-value loads of the identity / pool branches that kept the LSU data pipe 75 % busy
 //    - the limiter of the first warp-local version (ncu: tensor pipe 61 %).  The pool branch's next-row values come
@@ -38,6 +40,7 @@
 //  * a CTA pair owns a CONTIGUOUS range of (row block, channel tile) items, equal for all pairs, so the grid is
 //    balanced to one tile and a pair reloads its rows only when its range crosses into the next row block.
 #include <stdlib.h>
+#include <type_traits>
 #include "tmr_internal.h"
 #include "umma_common.cuh"
 
@@ -46,9 +49,8 @@ namespace umma {
 
 constexpr int BC_BM = 128;                 // MMA rows per CTA (TMEM lanes)
 constexpr int BC_GROUP = 32;               // rows per TMEM lane quarter = rows one epilogue warp sees
-constexpr int BC_HALO = 3;                 // rows on either side of a group that only feed the shifts
-constexpr int BC_GOUT = BC_GROUP - 2 * BC_HALO;   // 26 rows a group emits
-constexpr int BC_OUT = 4 * BC_GOUT;        // 104 rows a CTA emits per row block (128 in raw mode: no shifts, no halo)
+constexpr int BC_HALO = 3;                 // rows at either end of a CTA's tile that only feed the shifts
+constexpr int BC_OUT = BC_BM - 2 * BC_HALO;       // 122 rows a CTA emits per row block (128 in raw mode: no shifts, no halo)
 constexpr int BC_NCH = 16;                 // output channels per tile: 15 taps x 16 = 240 TMEM columns, double-buffered
 constexpr int BC_BK = 64;                  // fp16 input channels per k-step = one 128-byte swizzle row
 constexpr int BC_KB = kD / BC_BK;          // 8 k-steps
@@ -63,12 +65,16 @@ constexpr int BC_W5_BYTES = 5 * BC_HCH * BC_BK * 2;            //  5 KB
 constexpr int BC_W3_BYTES = 3 * BC_HCH * BC_BK * 2;            //  3 KB
 constexpr int BC_W_BYTES = BC_W7_BYTES + BC_W5_BYTES + BC_W3_BYTES;   // 15 KB = 120 rows per CTA: ONE MMA of N = 240 per k-step
 constexpr int BC_EPI_WARPS = 8;            // two per TMEM lane quarter: one per 8-channel half of the tile
-// output staging of one epilogue warp: [26 rows][7 variants][8 channels] fp16, dense (the box of its TMA store).  The
+// output staging of one epilogue warp: [32 rows][7 variants][8 channels] fp16, dense (the box of its TMA store).  The
 // row pitch of 112 bytes puts the 16-byte stores of eight consecutive rows (a quarter warp) into eight different bank
 // groups.
 constexpr int BC_OUT_PITCH = 7 * BC_HCH * 2;                   // 112 bytes per row
-constexpr int BC_OUT_BYTES = ((BC_GOUT * BC_OUT_PITCH + 127) / 128) * 128;     // 2944 bytes per warp
-constexpr int BC_SMEM_BYTES = BC_A_TOTAL + BC_STAGES * BC_W_BYTES + BC_EPI_WARPS * BC_OUT_BYTES + 1024 + 512;
+constexpr int BC_OUT_BYTES = BC_GROUP * BC_OUT_PITCH;          // 3584 bytes per warp
+// halo exchange between the lane quarters: [convolution][part*4 + quarter][side: 0 = my last rows, 1 = my first rows]
+// [slot][8 channels] fp32; slots per side = 1 + 2 + 3 (conv7), 1 + 2 (conv5), 1 (conv3)
+constexpr int BC_HALO_F7 = 0, BC_HALO_F5 = BC_HALO_F7 + 8 * 2 * 6 * 8, BC_HALO_F3 = BC_HALO_F5 + 8 * 2 * 3 * 8;
+constexpr int BC_HALO_FLOATS = BC_HALO_F3 + 8 * 2 * 1 * 8;     // 1280 floats = 5 KB
+constexpr int BC_SMEM_BYTES = BC_A_TOTAL + BC_STAGES * BC_W_BYTES + BC_EPI_WARPS * BC_OUT_BYTES + BC_HALO_FLOATS * 4 + 1024 + 512;
 constexpr int BC_THREADS = 64 + 32 * BC_EPI_WARPS;
 constexpr int BC_TMEM_COLS = 512;          // 2 accumulator buffers of 256 columns (240 used)
 constexpr int BC_N = 15 * BC_NCH;          // 240
@@ -128,13 +134,15 @@ struct BankConvParams {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BC_THREADS, 1)
 umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w3,
                      const __grid_constant__ CUtensorMap tma_w5, const __grid_constant__ CUtensorMap tma_w7,
-                     const __grid_constant__ CUtensorMap tma_pb, const BankConvParams p) {
+                     const __grid_constant__ CUtensorMap tma_pb, const __grid_constant__ CUtensorMap tma_pb29,
+                     const BankConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [BC_KB][128 rows][64 fp16], resident per row block
   uint8_t* sW = sA + BC_A_TOTAL;                        // [BC_STAGES][120 weight rows][64 fp16]
   uint8_t* sO = sW + BC_STAGES * BC_W_BYTES;            // [BC_EPI_WARPS] output staging
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + BC_EPI_WARPS * BC_OUT_BYTES);
+  float* sH = reinterpret_cast<float*>(sO + BC_EPI_WARPS * BC_OUT_BYTES);     // halo exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH + BC_HALO_FLOATS);
   uint64_t* a_full = bars;                              // [BC_KB]      TMA -> MMA, once per row block
   uint64_t* a_empty = a_full + BC_KB;                   // [BC_KB]      MMA -> TMA: the block's last tile has read this k-step
   uint64_t* w_full = a_empty + BC_KB;                   // [BC_STAGES]
@@ -150,17 +158,16 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
   // my pair's contiguous range of (row block, channel tile) items
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int64_t t_begin = p.num_tiles * pair / n_pairs, t_end = p.num_tiles * (pair + 1) / n_pairs;
-  // rows: raw mode multiplies 128 distinct rows per CTA; otherwise four 32-row groups that overlap by 2 x 3 halo rows
+  // rows: a CTA multiplies 128 consecutive rows; raw mode emits them all, otherwise the first and last 3 are halo
   const int out_per_cta = p.raw ? BC_BM : BC_OUT;
-  const int group_stride = p.raw ? BC_GROUP : BC_GOUT;
   const int halo = p.raw ? 0 : BC_HALO;
   auto group_row0 = [&](int64_t rb, int j) -> int64_t {        // bank row in lane 0 of lane quarter j of this CTA
-    return p.row_base + (rb * 2 + crank) * out_per_cta + (int64_t)j * group_stride - halo;
+    return p.row_base + (rb * 2 + crank) * out_per_cta + (int64_t)j * BC_GROUP - halo;
   };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_x); tma_prefetch_desc(&tma_w3); tma_prefetch_desc(&tma_w5); tma_prefetch_desc(&tma_w7);
-    if (!p.raw) tma_prefetch_desc(&tma_pb);
+    if (!p.raw) { tma_prefetch_desc(&tma_pb); tma_prefetch_desc(&tma_pb29); }
     for (int k = 0; k < BC_KB; ++k) { mbar_init(&a_full[k], 1); mbar_init(&a_empty[k], 1); }
     for (int s = 0; s < BC_STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * BC_EPI_WARPS); }
@@ -245,8 +252,12 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
     // ===================== epilogue warps =====================
     const int q = warp & 3;                                     // TMEM lane quarter = row group
     const int part = (warp - 2) >> 2;                           // 8-channel half of the tile
-    const bool lane_emits = lane >= halo && lane < BC_GROUP - halo;
+    // the tile's first / last 3 rows (lanes 0..2 of quarter 0, 29..31 of quarter 3) only feed the shifts
+    const int first_lane = (q == 0) ? halo : 0;
+    const int n_emit = (q == 0 || q == 3) ? BC_GROUP - halo : BC_GROUP;
+    const bool lane_emits = lane >= first_lane && lane < first_lane + n_emit;
     uint8_t* so = sO + (warp - 2) * BC_OUT_BYTES;               // my staging tile
+    const int hw = part * 4 + q;                                // my slot in the halo exchange
     int it = 0;
     for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
       const int64_t rb = tile / BC_NTILES;
@@ -257,10 +268,11 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       const bool valid = lane_emits && prow >= 0 && prow < p.pb_rows && rho < p.n_rows;
       // exact bank values of my row (identity branch; the pool branch takes the next row's from lane + 1), requested
       // before the accumulator is awaited so their latency hides behind the main loop.  Rows outside the bank are 0.
-      float x0[8];
+      float x0[8], x1e[8];                                      // x1e: the next row's values, loaded by lane 31 only
 #pragma unroll
-      for (int k = 0; k < 8; ++k) x0[k] = 0.f;
+      for (int k = 0; k < 8; ++k) { x0[k] = 0.f; x1e[k] = 0.f; }
       if (!p.raw && rho >= 0 && rho < p.n_rows) ldg8(p.bank + rho * kD + n0, x0);
+      if (!p.raw && lane == 31 && rho + 1 >= 0 && rho + 1 < p.n_rows) ldg8(p.bank + (rho + 1) * kD + n0, x1e);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
       if (BC_ABL(p, 2)) {
@@ -314,13 +326,54 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         continue;
       }
 
-      // P_{K,t}[rho] = Q_{K,t}[rho - t]: the value lane - t read from TMEM (every lane takes part in the shuffles)
-      auto shifted = [&](uint32_t u, int t) -> float {
-        const float f = __uint_as_float(u);
-        if (t > 0) return __shfl_up_sync(0xffffffffu, f, (unsigned)t);
-        if (t < 0) return __shfl_down_sync(0xffffffffu, f, (unsigned)(-t));
-        return f;
+      // P_{K,t}[rho] = Q_{K,t}[rho - t]: the value lane - t read from TMEM (every lane takes part in the shuffles); the
+      // |t| lanes whose source row sits in the neighbouring lane quarter are patched from the halo exchange afterwards.
+      auto shifted = [&](uint32_t u, int t) -> uint32_t {
+        if (t > 0) return __shfl_up_sync(0xffffffffu, u, (unsigned)t);
+        if (t < 0) return __shfl_down_sync(0xffffffffu, u, (unsigned)(-t));
+        return u;
       };
+      // Halo exchange of one convolution with H = (K - 1) / 2 taps a side, on the raw values q(c, j) = Q_{K, j - H}[my
+      // row] of channel c: a lane among my quarter's last a rows publishes Q_{K,+a} (side 0: the next quarter's first a
+      // lanes need it), a lane among its first a rows publishes Q_{K,-a} (side 1).  Slot of (a, i-th row) = a(a-1)/2 + i.
+      // One predicated 2 x 128-bit store per a: the lanes of either end pick their tap and address.
+      const bool tail_lane = lane >= BC_GROUP - BC_HALO;
+      auto publish = [&](float* base, int slots, auto q, auto H_) {
+        constexpr int H = decltype(H_)::value;
+        float* mine = base + (size_t)hw * 2 * slots * 8;
+#pragma unroll
+        for (int a = 1; a <= H; ++a) {
+          const bool t_on = lane >= BC_GROUP - a, h_on = lane < a;
+          if (t_on || h_on) {
+            uint32_t e[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) e[c] = tail_lane ? q(c, H + a) : q(c, H - a);
+            float* dst = mine + ((tail_lane ? 0 : slots) + a * (a - 1) / 2 + (tail_lane ? lane - (BC_GROUP - a) : lane)) * 8;
+            sts128(dst, e[0], e[1], e[2], e[3]);
+            sts128(dst + 4, e[4], e[5], e[6], e[7]);
+          }
+        }
+      };
+      // after the barrier: lanes < a take P_{K,+a} from the previous quarter's side 0, lanes >= 32 - a take P_{K,-a} from
+      // the next quarter's side 1 (the tile's outer ends have no neighbour: those lanes are the halo rows, never emitted)
+      auto patch = [&](const float* base, int slots, auto set, auto H_) {
+        constexpr int H = decltype(H_)::value;
+#pragma unroll
+        for (int a = 1; a <= H; ++a) {
+          const bool from_prev = lane < a && q > 0, from_next = lane >= BC_GROUP - a && q < 3;
+          if (from_prev || from_next) {
+            const float* src = base + ((size_t)(from_prev ? hw - 1 : hw + 1) * 2 * slots + (from_prev ? 0 : slots) + a * (a - 1) / 2 +
+                                       (from_prev ? lane : lane - (BC_GROUP - a))) * 8;
+            const float4 lo = *reinterpret_cast<const float4*>(src), hi = *reinterpret_cast<const float4*>(src + 4);
+            const float e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (from_prev) set(c, H + a, e[c]); else set(c, H - a, e[c]);
+            }
+          }
+        }
+      };
+      auto halo_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory"); };
       float out[7][8];
       {   // conv7: 7 variants = left sums Lf_a = sum_{t=-a..-1} P_t plus right sums R_b = bias + sum_{t=0..b} P_t
         uint32_t v[32], w[32];
@@ -329,11 +382,21 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         float b7[8];
         ldg8(p.bias7 + n0, b7);
         tmem_ld_wait();
+        publish(sH + BC_HALO_F7, 6, [&](int c, int j) { const int idx = c * 7 + j; return idx < 32 ? v[idx] : w[idx - 32]; },
+                std::integral_constant<int, 3>{});
+#pragma unroll
+        for (int idx = 0; idx < 56; ++idx) {
+          if (idx < 32) v[idx] = shifted(v[idx], idx % 7 - 3); else w[idx - 32] = shifted(w[idx - 32], idx % 7 - 3);
+        }
+        halo_barrier();
+        patch(sH + BC_HALO_F7, 6, [&](int c, int j, float f) { const int idx = c * 7 + j;
+                                                               if (idx < 32) v[idx] = __float_as_uint(f); else w[idx - 32] = __float_as_uint(f); },
+              std::integral_constant<int, 3>{});
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float P[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) { const int idx = c * 7 + j; P[j] = shifted(idx < 32 ? v[idx] : w[idx - 32], j - 3); }
+          for (int j = 0; j < 7; ++j) { const int idx = c * 7 + j; P[j] = __uint_as_float(idx < 32 ? v[idx] : w[idx - 32]); }
           const float r0 = b7[c] + P[3], r1 = r0 + P[4], r2 = r1 + P[5], r3 = r2 + P[6];
           const float l1 = P[2], l2 = l1 + P[1], l3 = l2 + P[0];
           out[0][c] = l3 + r3;      // interior
@@ -352,11 +415,21 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         float b5[8];
         ldg8(p.bias5 + n0, b5);
         tmem_ld_wait();
+        publish(sH + BC_HALO_F5, 3, [&](int c, int j) { const int idx = c * 5 + j; return idx < 32 ? v[idx] : f8[idx - 32]; },
+                std::integral_constant<int, 2>{});
+#pragma unroll
+        for (int idx = 0; idx < 40; ++idx) {
+          if (idx < 32) v[idx] = shifted(v[idx], idx % 5 - 2); else f8[idx - 32] = shifted(f8[idx - 32], idx % 5 - 2);
+        }
+        halo_barrier();
+        patch(sH + BC_HALO_F5, 3, [&](int c, int j, float f) { const int idx = c * 5 + j;
+                                                               if (idx < 32) v[idx] = __float_as_uint(f); else f8[idx - 32] = __float_as_uint(f); },
+              std::integral_constant<int, 2>{});
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float P[5];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) { const int idx = c * 5 + j; P[j] = shifted(idx < 32 ? v[idx] : f8[idx - 32], j - 2); }
+          for (int j = 0; j < 5; ++j) { const int idx = c * 5 + j; P[j] = __uint_as_float(idx < 32 ? v[idx] : f8[idx - 32]); }
           const float r0 = b5[c] + P[2], r1 = r0 + P[3], r2 = r1 + P[4];
           const float l1 = P[1], l2 = l1 + P[0];
           const float full = l2 + r2;
@@ -378,15 +451,18 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         tc_fence_before();                              // last TMEM read of this tile: hand the buffer back
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+        publish(sH + BC_HALO_F3, 1, [&](int c, int j) { return v[c * 3 + j]; }, std::integral_constant<int, 1>{});
+#pragma unroll
+        for (int idx = 0; idx < 24; ++idx) v[idx] = shifted(v[idx], idx % 3 - 1);
+        halo_barrier();
+        patch(sH + BC_HALO_F3, 1, [&](int c, int j, float f) { v[c * 3 + j] = __float_as_uint(f); }, std::integral_constant<int, 1>{});
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float P[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) P[j] = shifted(v[c * 3 + j], j - 1);
-          const float r0 = b3[c] + P[1], r1 = r0 + P[2];
-          const float l1 = P[0];
+          const float r0 = b3[c] + __uint_as_float(v[c * 3 + 1]), r1 = r0 + __uint_as_float(v[c * 3 + 2]);
+          const float l1 = __uint_as_float(v[c * 3]);
           const float full = l1 + r1;
-          const float idp = fmaxf(x0[c], __shfl_down_sync(0xffffffffu, x0[c], 1));   // lane 31 is never emitted
+          const float nxt = __shfl_down_sync(0xffffffffu, x0[c], 1);             // the next row's exact value
+          const float idp = fmaxf(x0[c], lane == 31 ? x1e[c] : nxt);
           out[0][c] = fmaxf(fmaxf(out[0][c], full), idp);
           out[1][c] = fmaxf(fmaxf(out[1][c], r1), fmaxf(x0[c], 0.f));
           out[2][c] = fmaxf(fmaxf(out[2][c], full), idp);
@@ -396,8 +472,8 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
           out[6][c] = fmaxf(fmaxf(out[6][c], full), idp);
         }
       }
-      // out -> fp16 -> my staging tile [row][variant][8 channels] -> one TMA store of the [26][7][8] box (rows past the
-      // end of PB are clipped by the tensor map).  The previous tile's store must have READ the staging tile first.
+      // out -> fp16 -> my staging tile [row][variant][8 channels] -> one TMA store of the [32 or 29][7][8] box (rows past
+      // the end of PB are clipped by the tensor map).  The previous tile's store must have READ the staging tile first.
       if (BC_ABL(p, 8 | 16)) {                          // experiment: 16-byte st.global per variant (8), no store at all (16)
         if (BC_ABL(p, 8) && valid) {
           half_t* dst = p.pb + prow * (7 * kD) + n0;
@@ -413,7 +489,7 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
       if (lane_emits) {
-        uint8_t* row = so + (lane - halo) * BC_OUT_PITCH;
+        uint8_t* row = so + (lane - first_lane) * BC_OUT_PITCH;
 #pragma unroll
         for (int v = 0; v < 7; ++v)
           sts128(row + v * 16, pack_h2(out[v][0], out[v][1]), pack_h2(out[v][2], out[v][3]), pack_h2(out[v][4], out[v][5]),
@@ -421,8 +497,8 @@ umma_bankconv_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       }
       fence_proxy_async_smem();                         // my generic-proxy writes before the async-proxy read
       __syncwarp();
-      const int64_t prow0 = group_row0(rb, q) + halo - p.row_base;      // PB row of lane `halo`: >= 0
-      if (lane == 0 && prow0 < p.pb_rows) tma_store_3d(&tma_pb, so, n0, 0, (int)prow0);
+      const int64_t prow0 = group_row0(rb, q) + first_lane - p.row_base;      // PB row of my first emitting lane: >= 0
+      if (lane == 0 && prow0 < p.pb_rows) tma_store_3d(n_emit == BC_GROUP ? &tma_pb : &tma_pb29, so, n0, 0, (int)prow0);
     }
     if (lane == 0) tma_store_wait_read();               // the staging tile outlives every store that reads it
   }
@@ -467,12 +543,12 @@ int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, 
 
 static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_cnt, umma::BankConvParams p, cudaStream_t st) {
   using namespace umma;
-  const int64_t rows_per_pair = 2 * (p.raw ? BC_BM : BC_OUT);                       // a CTA pair emits 2 x 104 rows (2 x 128 raw)
+  const int64_t rows_per_pair = 2 * (p.raw ? BC_BM : BC_OUT);                       // a CTA pair emits 2 x 122 rows (2 x 128 raw)
   p.num_tiles = ((p.pb_rows + rows_per_pair - 1) / rows_per_pair) * BC_NTILES;
 #ifdef TMR_EXPERIMENT
   p.ablate = env_int("TMR_BC_ABL", 0);
 #endif
-  CUtensorMap tx, tw3, tw5, tw7, tpb;
+  CUtensorMap tx, tw3, tw5, tw7, tpb, tpb29;
   {
     uint64_t dims[2] = {(uint64_t)kD, (uint64_t)r_cnt};
     uint64_t str[1] = {(uint64_t)kD * 2};
@@ -488,12 +564,13 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
       uint32_t bw[3] = {BC_BK, (uint32_t)taps, BC_HCH};
       TMR_TRY(make_tmap(tw[i], w[i], 3, dw, sw, bw, 2));
     }
-    tpb = tx;
+    tpb = tx; tpb29 = tx;
     if (!p.raw) {                      // PB[row][variant][channel] (fp16) viewed as (channel, variant, row): a warp's store box
       uint64_t dp[3] = {(uint64_t)kD, 7, (uint64_t)p.pb_rows};
       uint64_t sp[2] = {(uint64_t)kD * 2, (uint64_t)7 * kD * 2};
-      uint32_t bp[3] = {BC_HCH, 7, BC_GOUT};
+      uint32_t bp[3] = {BC_HCH, 7, BC_GROUP}, bp29[3] = {BC_HCH, 7, BC_GROUP - BC_HALO};   // inner / outer lane quarters
       TMR_TRY(make_tmap(&tpb, p.pb, 3, dp, sp, bp, 2, 0));
+      TMR_TRY(make_tmap(&tpb29, p.pb, 3, dp, sp, bp29, 2, 0));
     }
   }
   static bool attr_set = false;
@@ -505,7 +582,7 @@ static int launch_bankconv(const float* packed, const half_t* bank16, int64_t r_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
-  umma_bankconv_kernel<<<(unsigned)(2 * pairs), BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, tpb, p);
+  umma_bankconv_kernel<<<(unsigned)(2 * pairs), BC_THREADS, BC_SMEM_BYTES, st>>>(tx, tw3, tw5, tw7, tpb, tpb29, p);
   TMR_LAUNCH_CHECK("umma_bankconv_kernel");
   return TMR_OK;
 }
