@@ -142,18 +142,23 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
   if (tc) {
     half_t* h16[2] = {reinterpret_cast<half_t*>(ws.h0), reinterpret_cast<half_t*>(ws.h1)};
     if (!fuse0) TMR_TRY(launch_lstm_cell0(xp, starts, seq, out, seq > 1 ? h16[0] : nullptr, ws.c, B, st, true));
-    // Batches of about half a 256-clip tile or more (measured: 120 clips 293 -> 265 us per head call, 32 clips 188 -> 195):
-    // ALL recurrent steps in one persistent launch (umma_lstm_persist.cu; c in
-    // registers, h exchanged through L2).  Its per-tile arrival counters sit behind the row -> clip table in the
-    // unused part of the fp16-feature slot.
-    if (fuse0 && B >= env_int("TMR_LSTM_PERSIST_MIN", 96) && env_int("TMR_LSTM_PERSIST", 1)) {
+    // ALL recurrent steps in one launch, c in registers, h exchanged through L2: up to 512 clips (the reference's own
+    // 120-clip calls) by the latency-oriented kernel of umma_lstm_small.cu (32 CTAs of 64 gate columns per 128-clip
+    // tile: 120 clips 128 -> 3x us per recurrence), larger batches by the throughput-oriented persistent kernel
+    // of umma_lstm_persist.cu (CTA pairs of 256 clips x 256 columns, two tiles in flight).  The per-tile arrival
+    // counters sit behind the row -> clip table in the unused part of the fp16-feature slot.
+    if (fuse0 && env_int("TMR_LSTM_PERSIST", 1)) {
       const size_t spare = (size_t)n_rows_x * kF * 2;                       // bytes of ws.xr the fp16 features do not use
       const size_t table = align_up((size_t)n_rows_x * sizeof(int32_t), 256);
       const size_t nflags = 2 * (((size_t)B + 255) / 256);
       if (table + nflags * sizeof(int32_t) <= spare) {
         int32_t* flags = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws.xr) + (size_t)n_rows_x * kF * 2 + table);
-        const int rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
-                                         ws.xp, n_rows_x, frame0);
+        int rc = TMR_ERR_UNSUPPORTED;
+        if (B <= umma_lstm_small_max_clips() && B <= env_int("TMR_LSTM_SMALL_MAX", 512))
+          rc = umma_lstm_small(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st);
+        else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96))
+          rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
+                                 ws.xp, n_rows_x, frame0);
         if (rc != TMR_ERR_UNSUPPORTED) return rc;
       }
     }
