@@ -149,6 +149,17 @@ int tmr_fc_argmax_fwd(const void* packed, const float* St, const float* y1, int 
                       float* logits, int64_t* pred, float* score, void* workspace,
                       size_t workspace_bytes, int math_mode, void* stream);
 
+/* ---- a6 + a8 + a9 in one call: everything of resnet_lstm.forward after the LSTM and the TimeConv
+ * (TRAIN:245-252 eval mode: y1 = NLBlock(St, Lt); logits = fc_c(relu(fc_h_c([St || y1]))), EVAL:491-493 score/argmax).
+ * St (B,D), Lt (B,L,D) -> logits (B,C), pred int64[B], score fp32[B] (pred/score nullable).
+ * In TMR_MATH_F16 batches of up to 512 clips - the reference's own 120-clip calls - run as ONE launch
+ * (csrc/umma_head_tail.cu); larger ones and TMR_MATH_FP32 as the launches of tmr_nlblock_fwd + tmr_fc_argmax_fwd.
+ * workspace >= tmr_relation_head_workspace_bytes(B,D). */
+size_t tmr_relation_head_workspace_bytes(int B, int D);
+int tmr_relation_head_fwd(const void* nlblock_packed, const void* classifier_packed, const float* St,
+                          const float* Lt, int B, int L, int D, int C, float* logits, int64_t* pred,
+                          float* score, void* workspace, size_t workspace_bytes, int math_mode, void* stream);
+
 /* ---- a11: whole head, resnet_lstm.forward minus `share` (TRAIN:237-253 / EVAL:110-126) --------
  * x (B,seq,F) backbone features, long_feature (B,L,D).  timeconv_packed may be NULL for the
  * NL-only wiring (train_only_non-local_pretrained.py:226-240). */

@@ -1031,3 +1031,54 @@ def test_stage1_surface_forward_matches_torch_lstm():
         got = s1.to(dev).eval()(x.to(dev))
     assert got.shape == (B * seq, C)
     assert rel_err(got, ref) < TOL["fp32"]
+
+
+# ------------------------------------------------------------------------------------------
+# fused relation block + classifier for the reference's own batch sizes (umma_head_tail.cu)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,L", [(1, 30), (4, 10), (120, 30), (129, 30), (300, 7), (512, 30)])
+def test_fused_relation_head_matches_oracle_and_the_separate_launches(B, L):
+    """Up to 512 clips the tensor-core relation block + classifier is ONE launch (32 CTAs per 128-clip tile, column
+    blocks exchanged through L2); above that it is the chain of GEMM / row kernels.  Both against the fp64 oracle,
+    and the fused launch bit for bit against the chain (same fp16 operands, K order, row code): the chain is run on
+    a 600-clip batch whose first B clips are the fused call's."""
+    _need_mode("f16")
+    dev = _dev()
+    m = _model(7)
+    packs = m.packs()
+    g = torch.Generator().manual_seed(100 * B + L)
+    Bbig = 600
+    St = (torch.rand(Bbig, 512, generator=g) * 2 - 1) * 0.7
+    Lt = torch.from_numpy(synth.bank(Bbig * L, seed=B + L).reshape(Bbig, L, 512))
+    sd = _sd(7)
+    y1_ref = orc.nlblock(St[:B], Lt[:B], sd, dtype=torch.float64)
+    ref = orc.classifier(St[:B].double(), y1_ref, sd, dtype=torch.float64)
+    logits, pred, score = ops.relation_head(packs[2], packs[3], St[:B].to(dev), Lt[:B].contiguous().to(dev), 7, "f16")
+    assert rel_err(logits, ref) < TOL["f16"]
+    s_ref, p_ref = orc.eval_postproc(logits.cpu())            # post-processing of the SAME logits: exact
+    assert torch.equal(pred.cpu(), p_ref)
+    assert rel_err(score, s_ref) < 1e-6
+    big_logits, big_pred, big_score = ops.relation_head(packs[2], packs[3], St.to(dev), Lt.to(dev), 7, "f16")
+    assert torch.equal(big_logits[:B], logits) and torch.equal(big_pred[:B], pred) and torch.equal(big_score[:B], score)
+    # the module-level NLBlock call (relation block only, residual added, fp32 out) takes the same fused launch
+    y1 = ops.nlblock(packs[2], St[:B].to(dev), Lt[:B].contiguous().to(dev), "f16")
+    assert rel_err(y1, y1_ref) < TOL["f16"]
+    y1_big = ops.nlblock(packs[2], St.to(dev), Lt.to(dev), "f16")
+    assert torch.equal(y1_big[:B], y1)
+
+
+def test_fused_relation_head_repeats_bit_identically():
+    """Any race in the L2 exchange between the tile's 32 CTAs (a stage read before every column block landed) would show
+    as run-to-run differences."""
+    _need_mode("f16")
+    dev = _dev()
+    m = _model(8)
+    packs = m.packs()
+    B, L = 500, 30
+    g = torch.Generator().manual_seed(7)
+    St = ((torch.rand(B, 512, generator=g) * 2 - 1) * 0.7).to(dev)
+    Lt = torch.from_numpy(synth.bank(B * L, seed=11).reshape(B, L, 512)).to(dev)
+    first = ops.relation_head(packs[2], packs[3], St, Lt, 8, "f16")
+    for _ in range(20):
+        again = ops.relation_head(packs[2], packs[3], St, Lt, 8, "f16")
+        assert all(torch.equal(a, b) for a, b in zip(first, again))

@@ -44,6 +44,8 @@ SIGNATURES = {
     "tmr_lstm_seq_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "tmr_classifier_workspace_bytes": (_sz, [_i, _i]),
     "tmr_fc_argmax_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _i, _p]),
+    "tmr_relation_head_workspace_bytes": (_sz, [_i, _i]),
+    "tmr_relation_head_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _i, _p]),
     "tmr_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tmr_head_fwd": (_i, [_p] * 6 + [_i] * 6 + [_p, _p, _p, _p, _sz, _i, _p]),
     "tmr_head_frames_workspace_bytes": (_sz, [_i64, _i, _i, _i]),

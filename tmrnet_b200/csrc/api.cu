@@ -109,9 +109,12 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
 
 struct LstmWs { float* xp; float* xr; float* h0; float* h1; float* c; };
 // x_f16: x points to fp16 features (tensor-core mode only): the conversion pass is skipped, the MMA reads them in place
+// st16: if the route taken also leaves fp16(h_T) somewhere in the workspace, *st16 points to it (else nullptr)
 static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const int64_t* starts, int B,
-                     int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0, bool x_f16 = false) {
+                     int seq, float* out, LstmWs ws, int mode, cudaStream_t st, int64_t frame0 = 0, bool x_f16 = false,
+                     const half_t** st16 = nullptr) {
   const bool tc = mode == TMR_MATH_F16;
+  if (st16) *st16 = nullptr;
   TMR_CHECK_ARG(!x_f16 || tc, "lstm: fp16 features need TMR_MATH_F16");
   const float* w = pk;
   const half_t* w16 = mirror16<LstmPacked>(pk);
@@ -154,9 +157,10 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
       if (table + nflags * sizeof(int32_t) <= spare) {
         int32_t* flags = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws.xr) + (size_t)n_rows_x * kF * 2 + table);
         int rc = TMR_ERR_UNSUPPORTED;
-        if (B <= umma_lstm_small_max_clips() && B <= env_int("TMR_LSTM_SMALL_MAX", 512))
+        if (B <= umma_lstm_small_max_clips() && B <= env_int("TMR_LSTM_SMALL_MAX", 512)) {
           rc = umma_lstm_small(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st);
-        else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96))
+          if (rc == TMR_OK && st16) *st16 = h16[(seq - 1) & 1];
+        } else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96))
           rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
                                  ws.xp, n_rows_x, frame0);
         if (rc != TMR_ERR_UNSUPPORTED) return rc;
@@ -195,6 +199,22 @@ static int classifier_impl(const float* pk, const float* St, const float* y1, in
   // fc_c (512 -> C) + softmax score + argmax stay fp32 on CUDA cores
   return launch_fc_argmax(ws.z, pk + ClassifierPacked::wc_off, pk + ClassifierPacked::bc_off, B, C, logits,
                           pred, score, st);
+}
+
+// Relation block + classifier in ONE launch for the reference's own batch sizes (umma_head_tail.cu); St16 = fp16(St)
+// if a producer left it, else it is converted here.  Returns TMR_ERR_UNSUPPORTED (nothing launched) when the batch
+// is too large for the co-resident grid or the mode is fp32: the caller then runs the separate launches.
+static int fused_tail(const float* nl_pk, const float* cls_pk, const float* St, const half_t* St16, const float* Lt,
+                      int B, int L, int C, float* y1_out, float* logits, int64_t* pred, float* score, NLWs nl,
+                      float* z, int32_t* flags, int mode, cudaStream_t st) {
+  if (mode != TMR_MATH_F16 || B > umma_head_tail_max_clips() || !env_int("TMR_FUSED_TAIL", 1)) return TMR_ERR_UNSUPPORTED;
+  half_t* s16 = reinterpret_cast<half_t*>(nl.s);        // [B][512] fp16(St) | [B][512] fp16(y)
+  if (!St16) {
+    TMR_TRY(launch_half_concat(St, kD, nullptr, 0, 0, kD, B, s16, st, false));
+    St16 = s16;
+  }
+  return umma_head_tail(nl_pk, cls_pk, St, St16, Lt, B, L, C, nl.w1, reinterpret_cast<half_t*>(nl.w0), s16 + (size_t)B * kD,
+                        z, y1_out, logits, pred, score, flags, st);
 }
 
 static int timeconv_impl(const float* pk, const float* x, int B, int L, float* out, float* xr, int mode,
@@ -348,6 +368,13 @@ int tmr_nlblock_fwd(const void* packed, const float* St, const float* Lt, int B,
   NLWs ws;
   ws.w0 = cv.take((size_t)B * kD); ws.w1 = cv.take((size_t)B * kD); ws.s = cv.take((size_t)B * kD);
   TMR_CHECK_ARG(ws.w0 && ws.w1 && ws.s, "nlblock: workspace too small (%zu < %zu)", workspace_bytes, tmr_nlblock_workspace_bytes(B, D));
+  {   // one launch for the reference's batch sizes; without the classifier the fp16(y) half of ws.s is free for the
+      // tile arrival counters
+    int32_t* flags = reinterpret_cast<int32_t*>(reinterpret_cast<half_t*>(ws.s) + (size_t)B * kD);
+    const int rc = fused_tail((const float*)packed, nullptr, St, nullptr, Lt, B, L, 0, out, nullptr, nullptr, nullptr, ws,
+                              nullptr, flags, math_mode, (cudaStream_t)stream);
+    if (rc != TMR_ERR_UNSUPPORTED) return rc;
+  }
   return nlblock_impl((const float*)packed, St, Lt, B, L, out, ws, math_mode, (cudaStream_t)stream);
 }
 
@@ -450,14 +477,46 @@ static size_t head_tail_bytes(size_t b, int L, int D) {
 }
 static int head_tail(const void* timeconv_packed, const void* nlblock_packed, const void* classifier_packed,
                      const float* St, const float* window, int B, int L, int C, float* logits, int64_t* pred,
-                     float* score, HeadWs& ws, int mode, cudaStream_t st) {
+                     float* score, HeadWs& ws, int mode, cudaStream_t st, const half_t* St16 = nullptr) {
   const float* Lt_in = window;     // NL-only wiring: Lt = long_feature
   if (timeconv_packed) {
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, window, B, L, ws.Lt, ws.xr, mode, st));
     Lt_in = ws.Lt;
   }
+  {   // the reference's own batch sizes: relation block + classifier in one launch (counters in the unused [St || y] slot)
+    const int rc = fused_tail((const float*)nlblock_packed, (const float*)classifier_packed, St, St16, Lt_in, B, L, C, nullptr,
+                              logits, pred, score, ws.nl, ws.cls.z, reinterpret_cast<int32_t*>(ws.cls.s), mode, st);
+    if (rc != TMR_ERR_UNSUPPORTED) return rc;
+  }
   TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st, nullptr, true));
   return classifier_impl((const float*)classifier_packed, St, ws.y1, B, C, logits, pred, score, ws.cls, mode, st, true);
+}
+
+size_t tmr_relation_head_workspace_bytes(int B, int D) {
+  return fbytes((size_t)(B > 0 ? B : 1) * D) + tmr_nlblock_workspace_bytes(B, D) + tmr_classifier_workspace_bytes(B, D);
+}
+int tmr_relation_head_fwd(const void* nlblock_packed, const void* classifier_packed, const float* St, const float* Lt,
+                          int B, int L, int D, int C, float* logits, int64_t* pred, float* score, void* workspace,
+                          size_t workspace_bytes, int math_mode, void* stream) {
+  TMR_TRY(check_dims(D));
+  TMR_TRY(check_mode(math_mode));
+  TMR_CHECK_ARG(B >= 0 && L >= 1, "relation_head: bad B=%d L=%d", B, L);
+  TMR_CHECK_ARG(C >= 1 && C <= ClassifierPacked::kMaxC, "relation_head: C=%d out of range", C);
+  if (B == 0) return TMR_OK;
+  TMR_CHECK_ARG(nlblock_packed && classifier_packed && St && Lt && logits && workspace, "relation_head: null pointer");
+  TMR_CHECK_ARG(aligned16(St) && aligned16(Lt) && aligned16(workspace), "relation_head: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace, workspace_bytes);
+  NLWs nl; ClsWs cls;
+  float* y1 = cv.take((size_t)B * kD);
+  nl.w0 = cv.take((size_t)B * kD); nl.w1 = cv.take((size_t)B * kD); nl.s = cv.take((size_t)B * kD);
+  TMR_CHECK_ARG(y1 && nl.w0 && nl.w1 && nl.s && carve_cls(cv, B, cls), "relation_head: workspace too small (%zu < %zu)",
+                workspace_bytes, tmr_relation_head_workspace_bytes(B, D));
+  const int rc = fused_tail((const float*)nlblock_packed, (const float*)classifier_packed, St, nullptr, Lt, B, L, C, nullptr,
+                            logits, pred, score, nl, cls.z, reinterpret_cast<int32_t*>(cls.s), math_mode, st);
+  if (rc != TMR_ERR_UNSUPPORTED) return rc;
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt, B, L, y1, nl, math_mode, st, nullptr, true));
+  return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, math_mode, st, true);
 }
 
 size_t tmr_head_workspace_bytes(int B, int seq, int L, int D) {
@@ -481,9 +540,10 @@ int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const voi
   LstmWs lw; HeadWs hw;
   TMR_CHECK_ARG(carve_lstm(cv, (int64_t)B * seq, B, lw) && carve_head(cv, B, L, hw),
                 "head: workspace too small (%zu < %zu)", workspace_bytes, tmr_head_workspace_bytes(B, seq, L, D));
-  TMR_TRY(lstm_impl((const float*)lstm_packed, x, (int64_t)B * seq, nullptr, B, seq, hw.St, lw, math_mode, st));
+  const half_t* st16 = nullptr;
+  TMR_TRY(lstm_impl((const float*)lstm_packed, x, (int64_t)B * seq, nullptr, B, seq, hw.St, lw, math_mode, st, 0, false, &st16));
   return head_tail(timeconv_packed, nlblock_packed, classifier_packed, hw.St, long_feature, B, L, C, logits, pred,
-                   score, hw, math_mode, st);
+                   score, hw, math_mode, st, st16);
 }
 
 size_t tmr_head_frames_workspace_bytes(int64_t n_feat_frames, int B, int L, int D) {

@@ -57,6 +57,12 @@ int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* start
 int umma_lstm_small_max_clips();
 int umma_lstm_small(const half_t* whh16, const float* xp, const int64_t* starts, int seq, half_t* h16a, half_t* h16b,
                     float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st);
+// relation block + classifier of B <= umma_head_tail_max_clips() clips in one launch (umma_head_tail.cu);
+// cls_packed == nullptr: relation block only (y1 with the residual, fp32 -> y1_out)
+int umma_head_tail_max_clips();
+int umma_head_tail(const float* nl_packed, const float* cls_packed, const float* St, const half_t* St16, const float* Lt,
+                   int B, int L, int C, float* u, half_t* a16, half_t* y16, float* z, float* y1_out, float* logits,
+                   int64_t* pred, float* score, int32_t* flags, cudaStream_t st);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] (fp16) for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,

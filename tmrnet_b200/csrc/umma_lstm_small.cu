@@ -178,6 +178,13 @@ umma_lstm_small_kernel(const __grid_constant__ CUtensorMap tma_h0, const __grid_
                        __uint_as_float(r[b + 3]) + xv[j].w, cst[j], cn, hn[j]);
         cst[j] = cn;
       }
+      if (valid) {                                      // fp16 h: the next step's MMA operand (the last step's: the
+        half_t* hdst = (t & 1) ? p.h16b : p.h16a;       // relation block's query operand), one 32-byte sector
+        const uint2 a = pack_h4(hn[0], hn[1], hn[2], hn[3]), b = pack_h4(hn[4], hn[5], hn[6], hn[7]);
+        const uint2 c = pack_h4(hn[8], hn[9], hn[10], hn[11]), d = pack_h4(hn[12], hn[13], hn[14], hn[15]);
+        const uint32_t w8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+        stg256u(hdst + clip * kD + u0, w8);
+      }
       if (last_step) {
         if (valid) {                                    // the last step's h is the clip's St: fp32
           const float lo[8] = {hn[0], hn[1], hn[2], hn[3], hn[4], hn[5], hn[6], hn[7]};
@@ -186,13 +193,6 @@ umma_lstm_small_kernel(const __grid_constant__ CUtensorMap tma_h0, const __grid_
           stg256(p.h_out + clip * kD + u0 + 8, hi);
         }
       } else {
-        if (valid) {                                    // h only feeds the next step's MMA: fp16, one 32-byte sector
-          half_t* hdst = (t & 1) ? p.h16b : p.h16a;
-          const uint2 a = pack_h4(hn[0], hn[1], hn[2], hn[3]), b = pack_h4(hn[4], hn[5], hn[6], hn[7]);
-          const uint2 c = pack_h4(hn[8], hn[9], hn[10], hn[11]), d = pack_h4(hn[12], hn[13], hn[14], hn[15]);
-          const uint32_t w8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-          stg256u(hdst + clip * kD + u0, w8);
-        }
         // my CTA's 128 clips x 16 units of h_t are stored -> one thread publishes them device-wide
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 2 && lane == 0) {
@@ -235,7 +235,8 @@ int umma_lstm_small_max_clips() {
 }
 
 // Recurrent steps 1 .. seq-1 of B <= umma_lstm_small_max_clips() clips in one launch.  c0 / h16a hold the state after
-// step 0; h16b is the second exchange buffer; flags: >= ceil(B / 128) int32 of scratch.
+// step 0; h16b is the second exchange buffer; flags: >= ceil(B / 128) int32 of scratch.  On return the buffer of
+// parity (seq - 1) & 1 (h16b for even seq) also holds fp16(h_T).
 int umma_lstm_small(const half_t* whh16, const float* xp, const int64_t* starts, int seq, half_t* h16a, half_t* h16b,
                     float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st) {
   using namespace umma;

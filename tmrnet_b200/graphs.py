@@ -5,7 +5,8 @@ The reference calls `model.forward(inputs, long_feature)` on batches of 1200 fra
 `tmr_head_fwd` are launch-bound, so `GraphedHead` captures them ONCE into a CUDA graph over static buffers
 and replays it per batch: inputs are copied into the static buffers on the caller's stream, outputs are
 views of static tensors (valid until the next `run`).  The graph runs the TimeConv of the window and the LSTM chain as
-parallel branches (two capture streams); otherwise nothing changes: same kernels, same results bit for bit.
+parallel branches (two capture streams) that join in the fused relation + classifier launch; same arithmetic, same
+results bit for bit as the direct call.
 """
 from __future__ import annotations
 
@@ -57,8 +58,7 @@ class GraphedHead:
                 Lt = ops.timeconv_max(packs[1], self.long_feature, mode)
             St = ops.lstm_last(packs[0], self.x, mode)
             cur.wait_stream(fork)
-            y1 = ops.nlblock(packs[2], St, Lt, mode)
-            return ops.fc_argmax(packs[3], St, y1, self.model.num_class, mode)
+            return ops.relation_head(packs[2], packs[3], St, Lt, self.model.num_class, mode)
 
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

@@ -242,6 +242,26 @@ def fc_argmax(packed, St, y1, num_class: int, math_mode=None, want_pred=True):
     return logits, pred, score
 
 
+def relation_head(nlblock_packed, classifier_packed, St, Lt, num_class: int, math_mode=None):
+    """Everything of resnet_lstm.forward after the LSTM and the TimeConv (TRAIN:245-252, eval): NLBlock(St, Lt), the
+    classifier, softmax score and argmax - ONE launch for batches of up to 512 clips in the tensor-core mode."""
+    St = _dev(St, "St").reshape(-1, D)
+    Lt = _dev(Lt, "Lt")
+    if Lt.dim() != 3 or Lt.shape[2] != D or Lt.shape[0] != St.shape[0]:
+        raise ValueError(f"relation_head: St {tuple(St.shape)} / Lt {tuple(Lt.shape)} mismatch")
+    B, L, _ = Lt.shape
+    lib = _lib.load()
+    logits = torch.empty((B, num_class), dtype=torch.float32, device=St.device)
+    pred = torch.empty((B,), dtype=torch.int64, device=St.device)
+    score = torch.empty((B,), dtype=torch.float32, device=St.device)
+    ws = _ws(lib.tmr_relation_head_workspace_bytes(B, D), St.device)
+    with torch.cuda.device(St.device):
+        check(lib.tmr_relation_head_fwd(_ptr(nlblock_packed), _ptr(classifier_packed), _ptr(St), _ptr(Lt), B, L, D,
+                                        int(num_class), _ptr(logits), _ptr(pred), _ptr(score), _ptr(ws), ws.numel(),
+                                        _mode(math_mode), _stream()))
+    return logits, pred, score
+
+
 def head_fwd(lstm_packed, timeconv_packed, nlblock_packed, classifier_packed, x, long_feature, num_class: int,
              math_mode=None):
     x = _dev(x, "x")
