@@ -1082,3 +1082,25 @@ def test_fused_relation_head_repeats_bit_identically():
     for _ in range(20):
         again = ops.relation_head(packs[2], packs[3], St, Lt, 8, "f16")
         assert all(torch.equal(a, b) for a, b in zip(first, again))
+
+
+@pytest.mark.parametrize("C", [7, 8])
+def test_classifier_large_batch_kernel_equals_small_batch_kernel(C):
+    """From 4096 clips the 512 -> C FC + softmax score + argmax keeps its weight rows in registers and walks clips
+    grid-stride (fc_argmax_regs_kernel); same products, order and reductions as the warp-per-clip kernel:
+    a 5000-clip call against the same clips in chunks of 1000, and the post-processing against the oracle's."""
+    dev = _dev()
+    m = _model(C)
+    pk = m.packs()[3]
+    g = torch.Generator().manual_seed(C)
+    St = ((torch.rand(5000, 512, generator=g) * 2 - 1) * 0.7).to(dev)
+    y1 = ((torch.rand(5000, 512, generator=g) * 2 - 1) * 0.9).to(dev)
+    for mode in MODES:
+        _need_mode(mode)
+        big = ops.fc_argmax(pk, St, y1, C, mode)
+        parts = [ops.fc_argmax(pk, St[i:i + 1000].contiguous(), y1[i:i + 1000].contiguous(), C, mode) for i in range(0, 5000, 1000)]
+        for k in range(3):
+            assert torch.equal(big[k], torch.cat([p[k] for p in parts]))
+        s_ref, p_ref = orc.eval_postproc(big[0].cpu())
+        assert torch.equal(big[1].cpu(), p_ref)
+        assert rel_err(big[2], s_ref) < 1e-6

@@ -65,8 +65,10 @@ struct NLWs { float* w0; float* w1; float* s; };
 struct PbSrc { const half_t* pb; const float* lt_irr; const int32_t* src; };   // bank-level TimeConv output (PB in fp16)
 // defer_residual (tensor-core head paths): `out` gets W4 r + b4 only; the consumer (classifier_impl with
 // y1_plus_St) adds St while it converts [St || y1] for its GEMM
+// St16: fp16(St) if its producer left it (the LSTM recurrence kernels do): the conversion pass of the first GEMM is skipped
 static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B, int L, float* out,
-                        NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr, bool defer_residual = false) {
+                        NLWs ws, int mode, cudaStream_t st, const PbSrc* pbs = nullptr, bool defer_residual = false,
+                        const half_t* St16 = nullptr) {
   const bool tc = mode == TMR_MATH_F16;
   const float* w = pk;
   const half_t* w16 = mirror16<NLBlockPacked>(pk);
@@ -77,6 +79,7 @@ static int nlblock_impl(const float* pk, const float* St, const float* Lt, int B
     g = LinearArgs(); g.a = St; g.lda = kD; g.w16 = w16 + NLBlockPacked::w21_off; g.ldw = kD;
     g.bias = pk + NLBlockPacked::bu_off; g.out = ws.w1; g.ldo = kD; g.M = B; g.N = kD; g.K = kD;
     g.a_scratch = reinterpret_cast<half_t*>(ws.s);
+    if (St16) { g.a16 = St16; g.lda = kD; }
     TMR_TRY(do_linear(g, mode, st));
   } else {
     // q = St W1^T + b1                                   (NLB:26-27)
@@ -160,9 +163,11 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
         if (B <= umma_lstm_small_max_clips() && B <= env_int("TMR_LSTM_SMALL_MAX", 512)) {
           rc = umma_lstm_small(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st);
           if (rc == TMR_OK && st16) *st16 = h16[(seq - 1) & 1];
-        } else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96))
+        } else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96)) {
           rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
                                  ws.xp, n_rows_x, frame0);
+          if (rc == TMR_OK && st16) *st16 = h16[(seq - 1) & 1];
+        }
         if (rc != TMR_ERR_UNSUPPORTED) return rc;
       }
     }
@@ -488,7 +493,7 @@ static int head_tail(const void* timeconv_packed, const void* nlblock_packed, co
                               logits, pred, score, ws.nl, ws.cls.z, reinterpret_cast<int32_t*>(ws.cls.s), mode, st);
     if (rc != TMR_ERR_UNSUPPORTED) return rc;
   }
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st, nullptr, true));
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, Lt_in, B, L, ws.y1, ws.nl, mode, st, nullptr, true, St16));
   return classifier_impl((const float*)classifier_packed, St, ws.y1, B, C, logits, pred, score, ws.cls, mode, st, true);
 }
 
@@ -576,11 +581,12 @@ int tmr_head_frames_fwd(const void* lstm_packed, const void* timeconv_packed,
   TMR_CHECK_ARG(ok, "head_frames: workspace too small (%zu < %zu)", workspace_bytes,
                 tmr_head_frames_workspace_bytes(n_feat_frames, B, L, D));
   float* St = St_out ? St_out : hw.St;
-  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, math_mode, st, frame0));
+  const half_t* st16 = nullptr;
+  TMR_TRY(lstm_impl((const float*)lstm_packed, feats, n_feat_frames, starts, B, seq, St, lw, math_mode, st, frame0, false, &st16));
   TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, starts, B, L, pad_mode, win,
                         nullptr, st));
   return head_tail(timeconv_packed, nlblock_packed, classifier_packed, St, win, B, L, C, logits, pred, score, hw,
-                   math_mode, st);
+                   math_mode, st, st16);
 }
 
 size_t tmr_bankconv_workspace_bytes(int64_t pb_rows, int D) { return fbytes((size_t)((pb_rows > 0 ? pb_rows : 1) + 8) * D); }
@@ -671,8 +677,9 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
   TMR_CHECK_ARG(ok, "head_frames_dedup: workspace too small (%zu < %zu)", workspace_bytes,
                 tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, n_irregular_rows, pb_rows, L, D));
   float* St = St_out ? St_out : St_ws;
+  const half_t* st16 = nullptr;
   TMR_TRY(lstm_impl((const float*)lstm_packed, (const float*)feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0,
-                    feats_f16 != 0));
+                    feats_f16 != 0, &st16));
   if (pb_rows > 0) {
     // fp16 copy of the bank rows the convolutions touch, then one pass of tap products per row
     half_t* bank16 = reinterpret_cast<half_t*>(bank_r);
@@ -697,7 +704,7 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, win_i, n_irregular, L, lt_i, xr_i, mode, st));
   }
   PbSrc pbs{pb, lt_i, src_idx};
-  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs, true));
+  TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs, true, st16));
   return classifier_impl((const float*)classifier_packed, St, y1, B, C, logits, pred, score, cls, mode, st, true);
 }
 

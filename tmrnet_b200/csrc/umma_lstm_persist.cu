@@ -293,7 +293,7 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
           ++use[s];
           tc_fence_after();
           if (warp == 2 && lane == 0) PTL(item, 5);
-          half_t* hdst = last_step ? nullptr : ((t & 1) ? p.h16b : p.h16a);
+          half_t* hdst = (t & 1) ? p.h16b : p.h16a;       // the last step's fp16 h is the relation block's query operand
           uint4 hpack = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int ch = 0; ch < P_NCH; ++ch) {
@@ -344,8 +344,9 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
                 cst[s][8 * ch + j] = cn;
               }
               const int64_t o = mrow * kD + ((ncol0 + cc) >> 2);
-              if (hdst) {
-                // h only feeds the next step's MMA: fp16; two 8-unit groups leave as one 32-byte sector
+              {
+                // h feeds the next step's MMA (the last step's: the relation block's first GEMM): fp16; two 8-unit groups
+                // leave as one 32-byte sector
                 const uint2 lo = pack_h4(hn[0], hn[1], hn[2], hn[3]), hi = pack_h4(hn[4], hn[5], hn[6], hn[7]);
                 if ((ch & 1) == 0) {
                   hpack = make_uint4(lo.x, lo.y, hi.x, hi.y);
@@ -353,12 +354,11 @@ umma_lstm_persist_kernel(const __grid_constant__ CUtensorMap tma_h0, const __gri
                   const uint32_t w8[8] = {hpack.x, hpack.y, hpack.z, hpack.w, lo.x, lo.y, hi.x, hi.y};
                   stg256u(hdst + o - 8, w8);
                 }
-              } else {
-                stg256(p.h_out + o, hn);                  // the last step's h is the clip's St: fp32
               }
+              if (last_step) stg256(p.h_out + o, hn);     // the last step's h is the clip's St: fp32
             }
           }
-          if (hdst) {                                     // my 32 clips x 32 units of h_t are stored -> publisher
+          if (!last_step) {                               // my 32 clips x 32 units of h_t are stored -> publisher
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_done[s]);
           }
@@ -415,7 +415,8 @@ static int persist_groups() {
 }
 
 // Recurrent steps 1 .. seq-1 of every clip in one launch.  c0 / h16a hold the state after step 0; h16b is the
-// second exchange buffer; flags: >= 2 * ceil(B / 256) int32 of scratch.  Returns TMR_ERR_UNSUPPORTED when the
+// second exchange buffer (on return the buffer of parity (seq - 1) & 1 also holds fp16(h_T)); flags: >= 2 * ceil(B / 256)
+// int32 of scratch.  Returns TMR_ERR_UNSUPPORTED when the
 // device cannot keep one group of 8 CTA pairs resident (the caller falls back to the per-step kernels).
 int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* starts, int seq, half_t* h16a, half_t* h16b,
                       float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st, const float* xp_base,
