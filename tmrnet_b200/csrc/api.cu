@@ -164,8 +164,23 @@ static int lstm_impl(const float* pk, const float* x, int64_t n_rows_x, const in
           rc = umma_lstm_small(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st);
           if (rc == TMR_OK && st16) *st16 = h16[(seq - 1) & 1];
         } else if (B >= env_int("TMR_LSTM_PERSIST_MIN", 96)) {
-          rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, B, flags, st,
+          // Every round of the persistent grid (2 x G tiles of 256 clips) costs the same whether it is full or holds
+          // one tile: a remainder of up to 512 clips beyond whole rounds (the 83 022-clip bench job: 78 clips = a 19th
+          // round for one tile, 85 us) goes to the small-batch kernel instead (40 us), launched behind it.
+          int b_main = B;
+          const int round = umma_lstm_persist_round_clips();
+          if (starts && round > 0 && B > round) {
+            const int rem = B % round;
+            const int small_max = umma_lstm_small_max_clips();
+            if (rem > 0 && rem <= small_max && rem <= 512 && table + (nflags + 4) * sizeof(int32_t) <= spare) b_main = B - rem;
+          }
+          rc = umma_lstm_persist(w16 + LstmPacked::whh_off, xp, starts, seq, h16[0], h16[1], out, ws.c, b_main, flags, st,
                                  ws.xp, n_rows_x, frame0);
+          if (rc == TMR_OK && b_main < B) {
+            const size_t o = (size_t)b_main * kD;
+            rc = umma_lstm_small(w16 + LstmPacked::whh_off, xp, starts + b_main, seq, h16[0] + o, h16[1] + o, out + o, ws.c + o,
+                                 B - b_main, flags + nflags, st);
+          }
           if (rc == TMR_OK && st16) *st16 = h16[(seq - 1) & 1];
         }
         if (rc != TMR_ERR_UNSUPPORTED) return rc;

@@ -52,6 +52,7 @@ int umma_lstm_step_ws(const half_t* whh16, const float* xp, const int64_t* start
 int umma_lstm_persist(const half_t* whh16, const float* xp, const int64_t* starts, int seq, half_t* h16a, half_t* h16b,
                       float* h_out, const float* c0, int B, int32_t* flags, cudaStream_t st, const float* xp_base,
                       int64_t xp_rows, int64_t xp_row0);
+int umma_lstm_persist_round_clips();
 // the same for the reference's own batch sizes (umma_lstm_small.cu): 128-clip tiles x 32 CTAs of 64 gate columns,
 // B <= umma_lstm_small_max_clips() (512 on a B200; 0 when the device cannot keep one tile's 32 CTAs resident)
 int umma_lstm_small_max_clips();

@@ -414,6 +414,11 @@ static int persist_groups() {
   return groups;
 }
 
+// Clips one full round of the persistent grid processes (2 tiles in flight x G groups x 256 clips), 0 if unavailable.
+// A launch runs ceil(B / that) rounds and every round costs the same (a tile step is a latency chain), so a caller
+// with a few hundred clips beyond a whole number of rounds does better handing them to the small-batch kernel.
+int umma_lstm_persist_round_clips() { return 2 * persist_groups() * 2 * umma::P_BM; }
+
 // Recurrent steps 1 .. seq-1 of every clip in one launch.  c0 / h16a hold the state after step 0; h16b is the
 // second exchange buffer (on return the buffer of parity (seq - 1) & 1 also holds fp16(h_T)); flags: >= 2 * ceil(B / 256)
 // int32 of scratch.  Returns TMR_ERR_UNSUPPORTED when the
