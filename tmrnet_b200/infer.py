@@ -309,8 +309,7 @@ class BankInference:
     def launches_per_run(self, feats_f16: bool = False) -> int:
         """Kernel launches of one run() (bench.py's gpu_launches), counted from the launch sequences in csrc/api.cu.
         LSTM, fp32 mode: projection + cell0 + (seq-1) steps.  Tensor-core mode: feature conversion (none for fp16
-        features) + row->clip table + projection (step 0 fused) + step-0 fix-up + the recurrence - ONE persistent launch
-        for batches of >= 96 clips, seq-1 step launches below.  Tail, fp32: gather | timeconv | q, u, attention, v,
+        features) + row->clip table + projection (step 0 fused) + step-0 fix-up + the recurrence (one launch, see lstm()).  Tail, fp32: gather | timeconv | q, u, attention, v,
         layernorm, out | fc_h_c, fc_c; tensor-core mode folds q, u into one GEMM and adds the fp16 conversions of the
         window, St and [St|y1]; the bank-level path replaces gather + conversion + timeconv over all clips by
         conversion(bank rows) + bankconv and, for the irregular clips of a batch, row-index gather + compact + raw
@@ -322,18 +321,27 @@ class BankInference:
             return (1 + 1 + (self.seq - 1) + 1 + tc + tail) * len(self.plan())
         tail -= 1                                      # u = W21 St + bu: one GEMM for q and u
 
+        # one full round of the persistent recurrence grid: 2 tiles in flight x G groups of 8 CTA pairs x 256 clips
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count if torch.cuda.is_available() else 148
+        rnd = 2 * ((sms // 2) // 8) * 256
+
         def lstm(b):
             if self.seq == 1:
                 return (0 if feats_f16 else 1) + 1 + 1
-            rec = 1 if b >= 96 else self.seq - 1
+            # the recurrence is ONE launch (small-batch kernel up to 512 clips, persistent kernel above), two when a
+            # remainder of <= 512 clips beyond whole rounds of the persistent grid goes to the small-batch kernel
+            rec = 2 if (b > rnd > 0 and 0 < b % rnd <= 512) else 1
             return (0 if feats_f16 else 1) + 1 + 1 + 1 + rec
 
+        st_conv = 1 if self.seq == 1 else 0            # the recurrence kernels leave fp16(St) for the relation block
         if not self._use_dedup():
-            return sum(lstm(hi - lo) + 1 + 1 + 2 * tc + tail + 2 for lo, hi, _, _ in self.plan())
+            # up to 512 clips the relation block + classifier are one fused launch
+            return sum(lstm(hi - lo) + 1 + 1 + 2 * tc + ((1 + st_conv) if hi - lo <= 512 else (tail + 1 + st_conv))
+                       for lo, hi, _, _ in self.plan())
         n = 0
         for (lo, hi, _, _), d in zip(self.plan(), self.dedup_plan()):
             n += (lstm(hi - lo) + (2 if d["pb_rows"] > 0 else 0) + (0 if not len(d["irr"]) else 4 if len(d["irr_rows"]) else 3)
-                  + tail + 2)
+                  + tail + 1 + st_conv)
         return n
 
 
