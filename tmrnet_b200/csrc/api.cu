@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include <vector>
+#include <mutex>
 
 #include <stdlib.h>
 #include "tmr_internal.h"
@@ -243,6 +244,32 @@ static int timeconv_impl(const float* pk, const float* x, int B, int L, float* o
   half_t* x16 = reinterpret_cast<half_t*>(xr);
   TMR_TRY(launch_to_half(x, x16, (int64_t)B * L * kD, st));
   return umma_timeconv(pk, x, x16, B, L, out, st);
+}
+
+// ---- fork / join for the two independent halves of the bank-level head ------------------------------------------
+// The LSTM chain (feature conversion, input projection, recurrence) and the bank-side chain (fp16 bank rows, TimeConv
+// per bank row, the irregular clips' windows) do not depend on each other until the relation block.  On one stream every
+// kernel's last, partly filled round leaves SMs idle (the recurrence of a 10 k-clip shard: 43 tiles over 18 slots per
+// round); on two, the other chain's CTAs take those SMs.  One side stream + two events per device, created on first use
+// (outside any capture: BankInference warms up before it captures); inside a stream capture the event wait forks the
+// capture and the join closes it, so the graph simply has two branches.  Callers that share a device share the side
+// stream: more ordering than needed, never less.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false, tried = false; };
+static SideStream* side_stream() {
+  static SideStream per_dev[64];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& ss = per_dev[dev];
+  if (!ss.tried) {
+    ss.tried = true;
+    ss.ok = cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ss.ok) cudaGetLastError();
+  }
+  return ss.ok ? &ss : nullptr;
 }
 
 }  // namespace tmr
@@ -693,8 +720,18 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
                 tmr_head_frames_dedup_workspace_bytes(n_feat_frames, B, n_irregular, n_irregular_rows, pb_rows, L, D));
   float* St = St_out ? St_out : St_ws;
   const half_t* st16 = nullptr;
+  // fork: the bank-side chain runs on the side stream `sb` beside the LSTM chain on `st` (see side_stream())
+  cudaStream_t sb = st;
+  SideStream* ss = env_int("TMR_FORK_BANK", 1) ? side_stream() : nullptr;
+  if (ss) {
+    TMR_CUDA(cudaEventRecord(ss->fork, st));
+    TMR_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    sb = ss->s;
+  }
   TMR_TRY(lstm_impl((const float*)lstm_packed, (const float*)feats, n_feat_frames, starts, B, seq, St, lw, mode, st, frame0,
                     feats_f16 != 0, &st16));
+  {
+  cudaStream_t st = sb;            // everything in this block is bank-side work
   if (pb_rows > 0) {
     // fp16 copy of the bank rows the convolutions touch, then one pass of tap products per row
     half_t* bank16 = reinterpret_cast<half_t*>(bank_r);
@@ -717,6 +754,11 @@ int tmr_head_frames_dedup_fwd(const void* lstm_packed, const void* timeconv_pack
     TMR_TRY(launch_gather(bank, n_rows, frame2row, frame2vstart, n_frames_total, irregular_starts, n_irregular, L,
                           pad_mode, win_i, nullptr, st));
     TMR_TRY(timeconv_impl((const float*)timeconv_packed, win_i, n_irregular, L, lt_i, xr_i, mode, st));
+  }
+  }
+  if (ss) {                        // join: the relation block needs St and PB / the irregular windows
+    TMR_CUDA(cudaEventRecord(ss->join, sb));
+    TMR_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
   }
   PbSrc pbs{pb, lt_i, src_idx};
   TMR_TRY(nlblock_impl((const float*)nlblock_packed, St, nullptr, B, L, y1, nl, mode, st, &pbs, true, st16));
