@@ -162,7 +162,10 @@ int tmr_relation_head_fwd(const void* nlblock_packed, const void* classifier_pac
 
 /* ---- a11: whole head, resnet_lstm.forward minus `share` (TRAIN:237-253 / EVAL:110-126) --------
  * x (B,seq,F) backbone features, long_feature (B,L,D).  timeconv_packed may be NULL for the
- * NL-only wiring (train_only_non-local_pretrained.py:226-240). */
+ * NL-only wiring (train_only_non-local_pretrained.py:226-240).
+ * TMR_MATH_F16, B <= 512 (the reference's own 120-clip calls): 7 launches - row table, feature conversion, input
+ * projection (LSTM step 0 in its epilogue), the recurrence (csrc/umma_lstm_small.cu), window conversion, TimeConv,
+ * relation block + classifier + score/argmax (csrc/umma_head_tail.cu). */
 size_t tmr_head_workspace_bytes(int B, int seq, int L, int D);
 int tmr_head_fwd(const void* lstm_packed, const void* timeconv_packed, const void* nlblock_packed,
                  const void* classifier_packed, const float* x, const float* long_feature, int B,

@@ -283,9 +283,9 @@ def test_lstm_sweep_and_frame_dedup(mode, B, seq):
 
 @pytest.mark.parametrize("B,contiguous", [(256, True), (300, True), (700, True), (700, False), (1025, False)])
 def test_lstm_weights_stationary_step(B, contiguous):
-    """Batches of >= 256 clips take the weights-stationary recurrent-step kernel (umma_lstm_ws.cu): contiguous
-    clip starts read their projected rows by TMA, video boundaries / random picks by per-thread loads; the last
-    256-clip tile is partial.  Against the oracle, and the frame-deduplicated entry against the per-clip one."""
+    """One-launch recurrences at tile boundaries: up to 512 clips the small-batch kernel (umma_lstm_small.cu, 128-clip
+    tiles, last one partial), above it the persistent kernel (umma_lstm_persist.cu: contiguous clip starts read their
+    projected rows by TMA, video boundaries / random picks by per-thread loads; the last 256-clip tile is partial).  Against the oracle, and the frame-deduplicated entry against the per-clip one."""
     _need_mode("f16")
     m = _model(7)
     seq = 10
@@ -307,9 +307,9 @@ def test_lstm_weights_stationary_step(B, contiguous):
 
 
 def test_lstm_large_batch_engine_equals_small_batch_engine():
-    """Batches of >= 256 clips take the weights-stationary / persistent recurrence kernels, smaller ones the
-    streamed GEMM engine (umma_gemm.cu, EPI_LSTM): same fp16 operands, same K order inside one accumulator ->
-    bit-identical h_T.  600 clips at once against the same clips in chunks of 200."""
+    """Batches above 512 clips take the persistent recurrence kernel (CTA pairs of 256 clips x 256 gate columns), smaller
+    ones the small-batch kernel (32 CTAs of 64 gate columns per 128-clip tile): same fp16 operands, same K order
+    inside one accumulator -> bit-identical h_T.  600 clips at once against the same clips in chunks of 200."""
     _need_mode("f16")
     dev = _dev()
     B, seq = 600, 10
