@@ -460,18 +460,21 @@ def run_ours(args):
             # BASELINE configs[3] / the reference's own call pattern: ONE head call on 120 clips (1200 frames) with an explicit
             # window, as the scripts issue it (EVAL:470-495) - 7 launches: row table, feature conversion, input projection,
             # small-batch recurrence, window conversion + per-clip TimeConv (parallel branch), fused relation + classifier
-            from tmrnet_b200.graphs import GraphedHead
-            Bs = 120
-            xs = feats_dev[: Bs * SEQ].reshape(Bs, SEQ, 2048).contiguous()
-            lfs = bank_dev[: Bs * L].reshape(Bs, L, 512).contiguous()
-            gh = GraphedHead(model, Bs, L)
-            t_direct = timeit(lambda: model.predict(xs, lfs), 50)
-            t_graph = timeit(lambda: gh.run(xs, lfs), 50)
-            small = {"batch_clips": Bs, "L": L, "us_per_call_cuda_graph": t_graph * 1e3, "us_per_call_direct": t_direct * 1e3,
-                     "frames_per_s": Bs / (t_graph * 1e-3), "kernels_per_call": 7,
-                     "note": "one resnet_lstm.forward-sized call (120 clips x 10 frames, window given) incl. the copy of its inputs "
-                             "into the graph's static buffers; round 1: 274 us"}
-            del gh
+            try:
+                from tmrnet_b200.graphs import GraphedHead
+                Bs = 120
+                xs = feats_dev[: Bs * SEQ].reshape(Bs, SEQ, 2048).contiguous()
+                lfs = bank_dev[: Bs * L].reshape(Bs, L, 512).contiguous()
+                gh = GraphedHead(model, Bs, L)
+                t_direct = timeit(lambda: model.predict(xs, lfs), 50)
+                t_graph = timeit(lambda: gh.run(xs, lfs), 50)
+                small = {"batch_clips": Bs, "L": L, "us_per_call_cuda_graph": t_graph * 1e3, "us_per_call_direct": t_direct * 1e3,
+                         "frames_per_s": Bs / (t_graph * 1e-3), "kernels_per_call": 7,
+                         "note": "one resnet_lstm.forward-sized call (120 clips x 10 frames, window given) incl. the copy of its inputs "
+                                 "into the graph's static buffers; round 1: 274 us"}
+                del gh
+            except Exception as e:          # a probe beside the headline: never let it take the bench line down
+                small = {"batch_clips": 120, "error": f"{type(e).__name__}: {e}"[:300]}
         if not args.no_cpu and world == 1:             # the CPU arm beside it: rank 0 at N = 1 only
             r = cpu_head_rate(256, iters=args.cpu_iters, warmup=1)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
