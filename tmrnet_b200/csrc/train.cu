@@ -574,7 +574,16 @@ static int train_impl(int phase, const float* const* params, float* const* grads
     add_vec_kernel<<<nblk(4 * kD), 256, 0, st>>>(params[2], params[3], bsum, 4 * kD);
     TMR_TRY(gemm_nt(x_tm, kF, Wih, kF, bsum, xp, 4 * kD, T, 4 * kD, kF, st));
     if (tcm && S > 1) TMR_TRY(launch_half_concat(Whh, kD, nullptr, 0, kD, kD, 4 * kD, Whh16, st));
-    for (int t = 0; t < S; ++t) {
+    // TMR_MATH_F16, batches the co-resident grid holds (<= 512 clips): ALL steps in one launch (umma_lstm_small.cu:
+    // c in registers, h exchanged through L2, every step's gates / c / h saved) instead of a conversion, a GEMM and a
+    // cell launch per step; same fp16 rounding of h, same K order: the same bits.  Its fp16 exchange buffers and
+    // arrival counters sit in the (idle) fp16 operand scratch.
+    int rec = TMR_ERR_UNSUPPORTED;
+    if (tcm && S > 1 && B <= umma_lstm_small_max_clips() && (size_t)2 * B * kD + 64 <= tc_halves)
+      rec = umma_lstm_train_fwd(Whh16, xp, B, S, gates, cst, hst, a16, a16 + (size_t)B * kD,
+                                reinterpret_cast<int32_t*>(a16 + (size_t)2 * B * kD), st);
+    if (rec != TMR_OK && rec != TMR_ERR_UNSUPPORTED) return rec;
+    for (int t = 0; rec == TMR_ERR_UNSUPPORTED && t < S; ++t) {
       if (t > 0) TMR_TRY(gemm_nt(hst + (size_t)(t - 1) * B * kD, kD, Whh, kD, nullptr, hh, 4 * kD, B, 4 * kD, kD, st, nullptr, 0,
                                  tcm ? Whh16 : nullptr));
       lstm_cell_fwd_kernel<<<nblk((int64_t)B * kD), 256, 0, st>>>(xp + (size_t)t * B * 4 * kD, t > 0 ? hh : nullptr,
