@@ -224,65 +224,100 @@ static int transpose_pad16(const SRC* src, int64_t R, int Ccols, int64_t ld, hal
   return TMR_OK;
 }
 
-// attention, training forward: warp per clip; saves the softmax p (B,L)
-__global__ void attention_train_fwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
-                                           float* __restrict__ p, float* __restrict__ abar) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const float* ub = u + (int64_t)b * kD;
-  const float* Lb = Lt + (int64_t)b * L * kD;
+// attention, training forward: ONE CTA of 8 warps per clip (a training batch is 40 clips: a warp per clip left the
+// GPU with 40 warps walking 30 slots one global round trip at a time, 103 us).  Warp w takes slots w, w + 8, ..; a lane
+// owns 16 channels as four coalesced float4; scores go through shared memory, the softmax is computed redundantly by
+// every thread, and the weighted sum runs one float2 of channels per thread over all slots (rows now in L1 / L2).
+// Saves the softmax p (B,L).
+constexpr int kAttnTrainWarps = 8;
+constexpr int kAttnTrainMaxL = 512;
+__device__ __forceinline__ float dot16(const float4 (&a)[4], const float4* __restrict__ row, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = __ldg(row + i * 32 + lane);
+    s = fmaf(a[i].x, v.x, s); s = fmaf(a[i].y, v.y, s); s = fmaf(a[i].z, v.z, s); s = fmaf(a[i].w, v.w, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__global__ void __launch_bounds__(kAttnTrainWarps * 32)
+attention_train_fwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, int B, int L, float scale,
+                           float* __restrict__ p, float* __restrict__ abar) {
+  __shared__ float sc[kAttnTrainMaxL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const float4* Lb = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
+  float4 uq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) uq[i] = __ldg(reinterpret_cast<const float4*>(u + (int64_t)b * kD) + i * 32 + lane);
+  for (int k = warp; k < L; k += kAttnTrainWarps) {
+    const float s = dot16(uq, Lb + (int64_t)k * (kD / 4), lane) * scale;
+    if (lane == 0) sc[k] = s;
+  }
+  __syncthreads();
   float mx = -INFINITY;
-  for (int k = 0; k < L; ++k) {
-    float s = 0.f;
-    for (int c = lane; c < kD; c += 32) s = fmaf(ub[c], Lb[(int64_t)k * kD + c], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s *= scale;
-    if (lane == 0) p[(int64_t)b * L + k] = s;
-    mx = fmaxf(mx, s);
-  }
-  __syncwarp();
+  for (int k = 0; k < L; ++k) mx = fmaxf(mx, sc[k]);
   float den = 0.f;
-  for (int k = 0; k < L; ++k) den += expf(p[(int64_t)b * L + k] - mx);
-  __syncwarp();
-  for (int k = lane; k < L; k += 32) p[(int64_t)b * L + k] = expf(p[(int64_t)b * L + k] - mx) / den;
-  __syncwarp();
-  for (int c = lane; c < kD; c += 32) {
-    float a = 0.f;
-    for (int k = 0; k < L; ++k) a = fmaf(p[(int64_t)b * L + k], Lb[(int64_t)k * kD + c], a);
-    abar[(int64_t)b * kD + c] = a;
+  for (int k = 0; k < L; ++k) den += expf(sc[k] - mx);
+  __syncthreads();                                       // every thread has read the raw scores
+  for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    const float pk = expf(sc[k] - mx) / den;
+    sc[k] = pk;
+    p[(int64_t)b * L + k] = pk;
   }
+  __syncthreads();
+  // abar[c] = sum_k p_k Lt[k][c]: thread t owns channels 2t, 2t+1
+  const float2* L2 = reinterpret_cast<const float2*>(Lt + (int64_t)b * L * kD);
+  float2 a = make_float2(0.f, 0.f);
+  for (int k = 0; k < L; ++k) {
+    const float2 v = __ldg(L2 + (int64_t)k * (kD / 2) + threadIdx.x);
+    a.x = fmaf(sc[k], v.x, a.x); a.y = fmaf(sc[k], v.y, a.y);
+  }
+  reinterpret_cast<float2*>(abar + (int64_t)b * kD)[threadIdx.x] = a;
 }
 // attention backward: dabar -> du, dLt.  dp_k = dabar.Lt_k ; ds = p (dp - sum p dp) ; du = scale sum ds_k Lt_k ;
-// dLt_k = p_k dabar + scale ds_k u
-__global__ void attention_train_bwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, const float* __restrict__ p,
-                                           const float* __restrict__ dabar, int B, int L, float scale, float* __restrict__ ds_buf,
-                                           float* __restrict__ du, float* __restrict__ dLt) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const float* ub = u + (int64_t)b * kD; const float* da = dabar + (int64_t)b * kD;
-  const float* Lb = Lt + (int64_t)b * L * kD; const float* pb = p + (int64_t)b * L;
-  float* dsb = ds_buf + (int64_t)b * L;
+// dLt_k = p_k dabar + scale ds_k u.  Same CTA-per-clip shape as the forward.
+__global__ void __launch_bounds__(kAttnTrainWarps * 32)
+attention_train_bwd_kernel(const float* __restrict__ u, const float* __restrict__ Lt, const float* __restrict__ p,
+                           const float* __restrict__ dabar, int B, int L, float scale, float* __restrict__ ds_buf,
+                           float* __restrict__ du, float* __restrict__ dLt) {
+  __shared__ float sd[kAttnTrainMaxL];
+  __shared__ float sp[kAttnTrainMaxL];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const float4* Lb = reinterpret_cast<const float4*>(Lt + (int64_t)b * L * kD);
+  const float* pb = p + (int64_t)b * L;
+  float4 dq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dq[i] = __ldg(reinterpret_cast<const float4*>(dabar + (int64_t)b * kD) + i * 32 + lane);
+  for (int k = warp; k < L; k += kAttnTrainWarps) {
+    const float s = dot16(dq, Lb + (int64_t)k * (kD / 4), lane);
+    if (lane == 0) { sd[k] = s; sp[k] = pb[k]; }
+  }
+  __syncthreads();
   float dot = 0.f;
+  for (int k = 0; k < L; ++k) dot = fmaf(sp[k], sd[k], dot);
+  __syncthreads();
+  for (int k = threadIdx.x; k < L; k += blockDim.x) {
+    const float ds = sp[k] * (sd[k] - dot);
+    sd[k] = ds;
+    ds_buf[(int64_t)b * L + k] = ds;
+  }
+  __syncthreads();
+  const float2* L2 = reinterpret_cast<const float2*>(Lt + (int64_t)b * L * kD);
+  const float2 da = __ldg(reinterpret_cast<const float2*>(dabar + (int64_t)b * kD) + threadIdx.x);
+  const float2 ub = __ldg(reinterpret_cast<const float2*>(u + (int64_t)b * kD) + threadIdx.x);
+  float2 acc = make_float2(0.f, 0.f);
   for (int k = 0; k < L; ++k) {
-    float s = 0.f;
-    for (int c = lane; c < kD; c += 32) s = fmaf(da[c], Lb[(int64_t)k * kD + c], s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) dsb[k] = s;
-    dot = fmaf(pb[k], s, dot);
+    const float2 v = __ldg(L2 + (int64_t)k * (kD / 2) + threadIdx.x);
+    acc.x = fmaf(sd[k], v.x, acc.x); acc.y = fmaf(sd[k], v.y, acc.y);
+    if (dLt)
+      reinterpret_cast<float2*>(dLt + ((int64_t)b * L + k) * kD)[threadIdx.x] =
+          make_float2(sp[k] * da.x + scale * sd[k] * ub.x, sp[k] * da.y + scale * sd[k] * ub.y);
   }
-  __syncwarp();
-  for (int k = lane; k < L; k += 32) dsb[k] = pb[k] * (dsb[k] - dot);
-  __syncwarp();
-  for (int c = lane; c < kD; c += 32) {
-    float acc = 0.f;
-    for (int k = 0; k < L; ++k) {
-      acc = fmaf(dsb[k], Lb[(int64_t)k * kD + c], acc);
-      if (dLt) dLt[((int64_t)b * L + k) * kD + c] = pb[k] * da[c] + scale * dsb[k] * ub[c];
-    }
-    du[(int64_t)b * kD + c] = scale * acc;
-  }
+  reinterpret_cast<float2*>(du + (int64_t)b * kD)[threadIdx.x] = make_float2(scale * acc.x, scale * acc.y);
 }
 
 // LayerNorm([1,D]) forward (saves xhat, rstd) + ReLU
@@ -493,7 +528,7 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   if (math_mode == TMR_MATH_F16 && !umma_available())
     return set_error(TMR_ERR_UNSUPPORTED, "train: TMR_MATH_F16 needs the tcgen05 kernels (sm_100a device + build)");
   const bool tcm = math_mode == TMR_MATH_F16;
-  TMR_CHECK_ARG(B >= 1 && seq >= 1 && L >= 1 && C >= 1 && C <= 16, "train: bad sizes (C <= 16)");
+  TMR_CHECK_ARG(B >= 1 && seq >= 1 && L >= 1 && L <= kAttnTrainMaxL && C >= 1 && C <= 16, "train: bad sizes (L <= 512, C <= 16)");
   TMR_CHECK_ARG(params && x && long_feature && logits && workspace, "train: null pointer");
   TMR_CHECK_ARG(!(phase & PH_LOSS) || (labels && loss), "train: loss phase needs labels and loss");
   TMR_CHECK_ARG(!(phase & PH_BWD) || grads, "train: backward phase needs grads");
@@ -622,7 +657,7 @@ static int train_impl(int phase, const float* const* params, float* const* grads
     TMR_TRY(transpose_pad(params[12], kD, kD, kD, W2T, kD, st));
     TMR_TRY(gemm_nt(St, kD, params[10], kD, params[11], q, kD, B, kD, kD, st));            // q = St W1^T + b1
     TMR_TRY(gemm_nt(q, kD, W2T, kD, nullptr, u, kD, B, kD, kD, st));                       // u = W2^T q
-    attention_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, B, L, scale, pbuf, abar);
+    attention_train_fwd_kernel<<<B, kAttnTrainWarps * 32, 0, st>>>(u, Lt, B, L, scale, pbuf, abar);
     TMR_TRY(gemm_nt(abar, kD, params[14], kD, params[15], v, kD, B, kD, kD, st));          // v = W3 abar + b3
     layernorm_train_fwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(v, params[18], params[19], B, xhat, rstd, nrm, r);
     TMR_TRY(gemm_nt(r, kD, params[16], kD, params[17], o, kD, B, kD, kD, st));             // o = W4 r + b4
@@ -684,7 +719,7 @@ static int train_impl(int phase, const float* const* params, float* const* grads
   TMR_TRY(gemm_nt(tA, Bp, tB, Bp, nullptr, grads[14], kD, kD, kD, (int)Bp, st));           // dW3 = dv^T abar
   TMR_TRY(colsum(dv, nullptr, B, kD, kD, grads[15], 0, st));
   TMR_TRY(gemm_nt(dv, kD, W3T, kD, nullptr, dabar, kD, B, kD, kD, st));                    // dabar = dv W3
-  attention_train_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(u, Lt, pbuf, dabar, B, L, scale, dsb, du, dLt);
+  attention_train_bwd_kernel<<<B, kAttnTrainWarps * 32, 0, st>>>(u, Lt, pbuf, dabar, B, L, scale, dsb, du, dLt);
   // u = W2^T q : dq = du W2^T (out[b,i] = sum_j du[b,j] W2[i][j]) ; dW2 = q^T du ; db2 = 0
   TMR_TRY(gemm_nt(du, kD, params[12], kD, nullptr, dq, kD, B, kD, kD, st));
   TMR_TRY(transpose_pad(q, B, kD, kD, tA, Bp, st));
