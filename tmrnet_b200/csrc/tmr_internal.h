@@ -67,6 +67,8 @@ int umma_head_tail(const float* nl_packed, const float* cls_packed, const float*
 // training forward of the recurrence in one launch (all steps, gates / c / h of every step saved; raw Whh layout)
 int umma_lstm_train_fwd(const half_t* whh16, const float* xp, int B, int seq, float* gates, float* c, float* h,
                         half_t* h16a, half_t* h16b, int32_t* flags, cudaStream_t st);
+// problems of at most one 128-row tile, cut by output column over N / 16 CTAs (umma_gemm_small.cu); called by umma_linear
+int umma_linear_small(const LinearArgs& g, cudaStream_t st);
 bool umma_available();
 // bank-level TimeConv: pb[(row-row_base)*7 + variant][512] (fp16) for bank rows row_base .. +pb_rows-1
 int umma_bankconv(const float* packed, const float* bank, const half_t* bank16, int64_t n_rows, int64_t r_lo,

@@ -547,6 +547,9 @@ int umma_linear(const LinearArgs& g, cudaStream_t st) {
   TMR_CHECK_ARG(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldo % 4 == 0, "f16 linear: leading dims must be multiples of 8 (A, W) / 4 (out)");
   TMR_CHECK_ARG(g.M < (int64_t)INT32_MAX, "f16 linear: M too large");
   if (g.M == 0) return TMR_OK;
+  // at most one 128-row tile (a training batch, a module-level call on a few clips): N / 16 CTAs instead of one or two
+  // busy CTA pairs of the persistent engine
+  if (g.M <= 128 && !g.row2clip && env_int("TMR_GEMM_SMALL", 1)) return umma_linear_small(g, st);
   umma::GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.k_split = g.K;
   p.bias = g.bias; p.residual = g.residual; p.ldr = g.ldr; p.out = g.out; p.ldo = g.ldo; p.relu = g.relu;

@@ -283,6 +283,7 @@ int umma_head_tail(const float* nl_packed, const float* cls_packed, const float*
   if (B == 0) return TMR_OK;
   if (B > umma_head_tail_max_clips())
     return set_error(TMR_ERR_UNSUPPORTED, "fused relation + classifier kernel: batch exceeds the co-resident grid");
+  TMR_CUDA(cudaFuncSetAttribute(umma_head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));   // per device
   HeadTailParams p{};
   p.M = B; p.L = L; p.C = C; p.cls = cls_packed ? 1 : 0;
   p.St = St; p.Lt = Lt; p.u = u; p.a16 = a16; p.y16 = y16; p.z = z; p.y1_out = y1_out;

@@ -422,6 +422,7 @@ int umma_lstm_small(const half_t* whh16, const float* xp, const int64_t* starts,
   if (B == 0 || seq < 2) return TMR_OK;
   if (B > umma_lstm_small_max_clips())
     return set_error(TMR_ERR_UNSUPPORTED, "small-batch LSTM recurrence: batch exceeds the co-resident grid");
+  TMR_CUDA(cudaFuncSetAttribute(umma_lstm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));   // per device
   LstmSmallParams p{};
   p.M = B; p.xp = xp; p.starts = starts; p.seq = seq; p.c0 = c0; p.h16a = h16a; p.h16b = h16b; p.h_out = h_out; p.flags = flags;
   const int tiles = (B + S_BM - 1) / S_BM;
@@ -466,11 +467,8 @@ int umma_lstm_train_fwd(const half_t* whh16, const float* xp, int B, int seq, fl
   if (B == 0 || seq < 1) return TMR_OK;
   if (B > umma_lstm_small_max_clips())
     return set_error(TMR_ERR_UNSUPPORTED, "one-launch training recurrence: batch exceeds the co-resident grid");
-  static bool attr_set = false;
-  if (!attr_set) {
-    TMR_CUDA(cudaFuncSetAttribute(umma_lstm_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
-    attr_set = true;
-  }
+  // (per call, not once per process: the attribute is per device, and one process may drive several)
+  TMR_CUDA(cudaFuncSetAttribute(umma_lstm_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
   LstmTrainParams p{};
   p.B = B; p.seq = seq; p.xp = xp; p.gates = gates; p.c = c; p.h = h; p.h16a = h16a; p.h16b = h16b; p.flags = flags;
   const int tiles = (B + S_BM - 1) / S_BM;
