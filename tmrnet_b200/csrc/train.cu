@@ -50,21 +50,31 @@ static int transpose_pad(const float* src, int64_t R, int Ccols, int64_t ld, flo
 // out[c] (+)= sum_r X[r][c] (* Y[r][c])
 __global__ void colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, int64_t R, int Ccols, int64_t ld,
                               float* __restrict__ out, int accumulate) {
+  // 32 columns x 32 row lanes per CTA, four independent partial sums per thread: the bias gradients of the convolutions
+  // sum 1200 rows, and with 8 row lanes and one dependent chain each of those launches took ~25 us
   const int c = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float part[8][33];
-  float s = 0.f;
-  if (c < Ccols)
-    for (int64_t r = threadIdx.y; r < R; r += blockDim.y) s += Y ? X[r * ld + c] * Y[r * ld + c] : X[r * ld + c];
-  part[threadIdx.y][threadIdx.x] = s;
+  __shared__ float part[32][33];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < Ccols) {
+    const int64_t step = blockDim.y;
+    int64_t r = threadIdx.y;
+    for (; r + 3 * step < R; r += 4 * step) {
+      const int64_t i0 = r * ld + c, i1 = (r + step) * ld + c, i2 = (r + 2 * step) * ld + c, i3 = (r + 3 * step) * ld + c;
+      s0 += Y ? X[i0] * Y[i0] : X[i0]; s1 += Y ? X[i1] * Y[i1] : X[i1];
+      s2 += Y ? X[i2] * Y[i2] : X[i2]; s3 += Y ? X[i3] * Y[i3] : X[i3];
+    }
+    for (; r < R; r += step) s0 += Y ? X[r * ld + c] * Y[r * ld + c] : X[r * ld + c];
+  }
+  part[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0 && c < Ccols) {
     float tsum = 0.f;
-    for (int i = 0; i < 8; ++i) tsum += part[i][threadIdx.x];
+    for (int i = 0; i < 32; ++i) tsum += part[i][threadIdx.x];
     out[c] = accumulate ? out[c] + tsum : tsum;
   }
 }
 static int colsum(const float* X, const float* Y, int64_t R, int Ccols, int64_t ld, float* out, int accumulate, cudaStream_t st) {
-  colsum_kernel<<<(Ccols + 31) / 32, dim3(32, 8), 0, st>>>(X, Y, R, Ccols, ld, out, accumulate);
+  colsum_kernel<<<(Ccols + 31) / 32, dim3(32, 32), 0, st>>>(X, Y, R, Ccols, ld, out, accumulate);
   TMR_LAUNCH_CHECK("colsum_kernel");
   return TMR_OK;
 }
@@ -222,6 +232,21 @@ static int transpose_pad16(const SRC* src, int64_t R, int Ccols, int64_t ld, hal
   transpose_pad16_kernel<SRC><<<grid, dim3(32, 8), 0, st>>>(src, R, Ccols, ld, dst, Rpad);
   TMR_LAUNCH_CHECK("transpose_pad16_kernel");
   return TMR_OK;
+}
+
+// fp16 copies of BOTH operands of a tensor-core GEMM in one launch (a: M x K with row stride lda, w: N x K with ldw;
+// K % 4 == 0): a training step converts ~25 operand pairs, and a launch costs more than either conversion.
+__global__ void half_pair_kernel(const float* __restrict__ a, int64_t lda, int64_t M, const float* __restrict__ w, int64_t ldw,
+                                 int64_t N, int K, half_t* __restrict__ a16, half_t* __restrict__ w16) {
+  const int k4 = K / 4;
+  const int64_t na = M * k4, n = na + N * k4;
+  GRID_STRIDE(i, n) {
+    const bool first = i < na;
+    const int64_t j = first ? i : i - na;
+    const int64_t r = j / k4; const int c = (int)(j - r * k4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>((first ? a + r * lda : w + r * ldw)) + c);
+    reinterpret_cast<uint2*>(first ? a16 : w16)[j] = pack_h4(v);
+  }
 }
 
 // attention, training forward: ONE CTA of 8 warps per clip (a training batch is 40 clips: a warp per clip left the
@@ -594,8 +619,13 @@ static int train_impl(int phase, const float* const* params, float* const* grads
     g.residual = residual; g.ldr = ldr;
     if (!tcm || K % 64 != 0 || N % 4 != 0 || ldo % 4 != 0) return simt_linear(g, s2);
     TMR_CHECK_ARG((size_t)M * K <= tc_halves && (size_t)N * K <= tc_halves, "train: fp16 scratch too small");
-    TMR_TRY(launch_half_concat(a, lda, nullptr, 0, K, K, M, a16, s2));
-    if (!w16_pre) TMR_TRY(launch_half_concat(wgt, ldw, nullptr, 0, K, K, N, w16, s2));
+    if (w16_pre || (lda % 4) || (ldw % 4) || !aligned16(a) || !aligned16(wgt)) {
+      TMR_TRY(launch_half_concat(a, lda, nullptr, 0, K, K, M, a16, s2));
+      if (!w16_pre) TMR_TRY(launch_half_concat(wgt, ldw, nullptr, 0, K, K, N, w16, s2));
+    } else {                                   // both operands in one launch
+      const int64_t n4 = (M + N) * (K / 4);
+      half_pair_kernel<<<nblk(n4), 256, 0, s2>>>(a, lda, M, wgt, ldw, N, K, a16, w16);
+    }
     g.a16 = a16; g.lda = K; g.w16 = w16_pre ? w16_pre : w16; g.ldw = K;
     return umma_linear(g, s2);
   };
