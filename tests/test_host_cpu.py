@@ -294,3 +294,22 @@ def test_stage1_checkpoint_feeds_the_head_and_the_stage1_surface():
     assert isinstance(s1.get_optimizers(), torch.optim.Adam)
     with pytest.raises(RuntimeError):
         s1.train()(torch.zeros(1, 10, 2048))
+
+
+def test_launch_accounting_of_the_bench_pass():
+    """bench.py's gpu_launches claim comes from BankInference.launches_per_run(): for the 83 022-clip bench job in the
+    tensor-core mode one resident pass is the 20 kernels of profiles/r2au_launches_one_pass.md (feature conversion,
+    row table, projection, step-0 fix-up, persistent recurrence + its small-batch remainder, 2 + 4 bank-side kernels,
+    3 relation GEMMs + attention + LayerNorm, [St || y] conversion, classifier GEMM, FC / argmax); fp16 features drop
+    the conversion."""
+    import tmrnet_b200 as tb
+    from tmrnet_b200 import synth
+    from tmrnet_b200.infer import BankInference
+    lengths = synth.video_lengths(40, seed=1234)
+    idx = tb.LFBIndex.from_lengths(lengths, 10)
+    m = tb.resnet_lstm(num_class=7)
+    m.math_mode = "f16"
+    eng = BankInference(m, idx, 10, 30)
+    assert len(eng.plan()) == 1 and len(eng.starts_host) == 83022
+    assert eng.launches_per_run() == 20
+    assert eng.launches_per_run(feats_f16=True) == 19
