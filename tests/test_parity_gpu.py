@@ -1104,3 +1104,21 @@ def test_classifier_large_batch_kernel_equals_small_batch_kernel(C):
         s_ref, p_ref = orc.eval_postproc(big[0].cpu())
         assert torch.equal(big[1].cpu(), p_ref)
         assert rel_err(big[2], s_ref) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 512), (40, 512, 2048), (128, 2048, 512), (100, 36, 1024), (77, 512, 64)])
+def test_small_m_gemm_equals_the_persistent_engine(M, N, K):
+    """Products with at most 128 rows run as N / 16 column-slice CTAs (umma_gemm_small.cu); same fp16 operands, same K
+    order, same bias / relu order as the persistent 256 x 256 engine: the first M rows of a 600-row call, bit for
+    bit, and both against an fp64 product of the fp16-rounded operands."""
+    _need_mode("f16")
+    dev = _dev()
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    a = torch.randn(600, K, generator=g) * 0.5
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g) * 0.1
+    big = ops.linear(a.to(dev), w.to(dev), b.to(dev), relu=True, math_mode="f16")
+    small = ops.linear(a[:M].contiguous().to(dev), w.to(dev), b.to(dev), relu=True, math_mode="f16")
+    assert torch.equal(big[:M], small)
+    ref = torch.relu(a[:M].half().double() @ w.half().double().t() + b.double())
+    assert rel_err(small, ref) < 2e-5
