@@ -1122,3 +1122,43 @@ def test_small_m_gemm_equals_the_persistent_engine(M, N, K):
     assert torch.equal(big[:M], small)
     ref = torch.relu(a[:M].half().double() @ w.half().double().t() + b.double())
     assert rel_err(small, ref) < 2e-5
+
+
+_FALLBACK_CHILD = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from tmrnet_b200 import _lib, build
+_lib.LIB_PATH = build.build(experiment=True)        # the experiment build reads TMR_LSTM_PERSIST (the product ignores it)
+import tmrnet_b200 as tb
+from tmrnet_b200 import ops, synth
+dev = torch.device("cuda:0")
+m = tb.resnet_lstm(num_class=7)
+m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.head_state_dict(num_class=7, seed=1234).items()})
+m = m.to(dev).eval()
+out = {}
+for B in (130, 300, 700):
+    feats = torch.from_numpy(synth.features(B + 9, seed=B)).to(dev)
+    out[str(B)] = ops.lstm_last_frames(m.packs()[0], feats, torch.arange(B, device=dev), 10, "f16").cpu().numpy()
+np.savez(sys.argv[2], **out)
+"""
+
+
+def test_per_step_lstm_fallback_kernels_equal_the_one_launch_kernels(tmp_path):
+    """The per-step recurrence kernels (umma_lstm_ws.cu from 256 clips, the streamed EPI_LSTM engine below) are what runs
+    when a device cannot keep the one-launch grids resident; on a B200 the product never takes them, so they are driven
+    here through the experiment build (TMR_LSTM_PERSIST=0, in a child process) and must give the bits of the one-launch
+    kernels of the product library."""
+    import subprocess
+    import sys
+    _need_mode("f16")
+    dev = _dev()
+    res = str(tmp_path / "fallback.npz")
+    env = dict(os.environ, TMR_LSTM_PERSIST="0")
+    r = subprocess.run([sys.executable, "-c", _FALLBACK_CHILD, ROOT, res], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    z = np.load(res)
+    m = _model(7)
+    for B in (130, 300, 700):
+        feats = torch.from_numpy(synth.features(B + 9, seed=B)).to(dev)
+        got = ops.lstm_last_frames(m.packs()[0], feats, torch.arange(B, device=dev), 10, "f16").cpu().numpy()
+        assert np.array_equal(got, z[str(B)]), f"B={B}: per-step fallback differs from the one-launch kernel"

@@ -37,6 +37,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
+def needs_build_experiment() -> bool:
+    """Same staleness rule for the experiment library (libtmr_b200_exp.so)."""
+    if not os.path.exists(LIB_EXP):
+        return True
+    t = os.path.getmtime(LIB_EXP)
+    return any(os.path.getmtime(p) > t for p in _deps())
+
+
 def nvcc_path() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -48,6 +56,8 @@ def build(force: bool = False, verbose: bool = False, experiment: bool = False) 
     """experiment=True builds libtmr_b200_exp.so with -DTMR_EXPERIMENT (environment switches and kernel
     timelines for the scripts/ measurements) next to the product library, which it never replaces."""
     if experiment:
+        if not force and not needs_build_experiment():
+            return LIB_EXP
         return _build(LIB_EXP, os.path.join(HERE, "build_exp"), verbose, ["-DTMR_EXPERIMENT"])
     if not force and not needs_build():
         return LIB
