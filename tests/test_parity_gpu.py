@@ -966,6 +966,11 @@ def test_graphed_head_is_bit_identical_to_direct_calls(mode, B):
         with torch.no_grad():
             l2, p2, s2 = m.predict(x, lf)
         assert torch.equal(logits, l2) and torch.equal(pred, p2) and torch.equal(score, s2)
+    # a producer may fill the graph's static buffers in place and pass them back: no copy, same results
+    gh.x.copy_(x)
+    gh.long_feature.copy_(lf)
+    logits, pred, score = (t.clone() for t in gh.run(gh.x, gh.long_feature))
+    assert torch.equal(logits, l2) and torch.equal(pred, p2) and torch.equal(score, s2)
     # a weight update rebuilds the packs: the graph must be re-captured, not replayed on stale weights
     with torch.no_grad():
         m.fc_c.bias.add_(0.25)

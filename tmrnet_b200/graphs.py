@@ -72,13 +72,18 @@ class GraphedHead:
         self._graph, self._out, self._packs = g, out, packs      # keep the packs (and workspace) alive
 
     def run(self, x, long_feature):
-        """x: (B, seq, 2048) or (B*seq, 2048); long_feature: (B, L, 512).  Returns (logits, pred, score)."""
+        """x: (B, seq, 2048) or (B*seq, 2048); long_feature: (B, L, 512) - any CUDA tensors (copied into the static buffers
+        on the caller's stream) or the static buffers `self.x` / `self.long_feature` themselves, filled in place by the
+        producer (no copy).  Returns (logits, pred, score), views of static tensors valid until the next run()."""
         with torch.no_grad(), torch.cuda.device(self.device):
             key = self._capture_key()
             if self._graph is None or key != self._key:
                 self._capture()
                 self._key = key
-            self.x.copy_(x.reshape(self.B, self.seq, F), non_blocking=True)
-            self.long_feature.copy_(long_feature, non_blocking=True)
+            # a caller that fills the static buffers itself (gh.x / gh.long_feature) pays no copy
+            if x.data_ptr() != self.x.data_ptr():
+                self.x.copy_(x.reshape(self.B, self.seq, F), non_blocking=True)
+            if long_feature.data_ptr() != self.long_feature.data_ptr():
+                self.long_feature.copy_(long_feature, non_blocking=True)
             self._graph.replay()
         return self._out
